@@ -1,0 +1,130 @@
+/* mmego_b200.h -- C ABI of libmmego_b200.so, the B200 (sm_100a) implementation of mmEgo's inference
+ * forward pass (IMU_Net -> Upper_Net -> Lower_Net/ST-GCN -> joint decode + metrics).
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the yenanjing/mmEgo
+ * checkout).  Plain pointers and sizes only; no C++/torch types; no exceptions cross this boundary.
+ *
+ *  - All `float*` tensor arguments are DEVICE pointers to contiguous fp32 unless the name ends in `_host`.
+ *  - Weights are passed as HOST pointers keyed by the checkpoint's state_dict names; the library folds
+ *    BatchNorm, permutes LSTM gates and uploads its own packed copies (owned by the handle).
+ *  - Calls are asynchronous on `stream` (a cudaStream_t passed as void*); nothing is retained past the call
+ *    except packed weights.  A handle is not thread-safe; use one per GPU / per thread.
+ *  - Return 0 on success, a negative MMEGO_E* code otherwise; text via mmego_last_error().
+ */
+#ifndef MMEGO_B200_H
+#define MMEGO_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMEGO_ABI_VERSION 1
+
+enum {
+    MMEGO_OK = 0,
+    MMEGO_EINVAL = -1,  /* null pointer / bad argument / unknown option */
+    MMEGO_ESHAPE = -2,  /* unsupported shape, missing or mis-sized weight tensor */
+    MMEGO_EARCH = -3,   /* device is not sm_100 */
+    MMEGO_ECUDA = -4,   /* CUDA runtime error */
+    MMEGO_ENOMEM = -5,  /* workspace too small / allocation failure */
+    MMEGO_ESTATE = -6   /* weights for this stage were never set */
+};
+
+enum { MMEGO_NET_IMU = 0, MMEGO_NET_UPPER = 1, MMEGO_NET_LOWER = 2 };
+enum { MMEGO_STAGE_IMU = 0, MMEGO_STAGE_UPPER = 1, MMEGO_STAGE_LOWER = 2, MMEGO_STAGE_GCN = 3, MMEGO_STAGE_PIPELINE = 4 };
+
+/* body_index_mode: which calibration skeleton flat frame r = b*L + l uses in forward kinematics.
+ * 0 = reference-exact `initial_body[r % B]` (the `.repeat(L,1,1,1)` of Net/Upper_Net.py:134, Net/Lower_Net.py:26),
+ * 1 = per-snippet `initial_body[r / L]`. */
+enum { MMEGO_BODY_REF = 0, MMEGO_BODY_PER_SNIPPET = 1 };
+
+/* Layout of the `sums` accumulator filled by mmego_assemble_metrics (all float64, ADDED to, never cleared):
+ * [0..20] per-joint sum of ||pred-gt||, [21] upper-body sum (15 joints, UpperNet's own hips),
+ * [22] lower-body sum (8 joints), [23..42] per-bone angle sum in degrees, [43] frame count. */
+#define MMEGO_SUMS_LEN 44
+
+typedef struct mmego_handle mmego_handle;
+
+int mmego_abi_version(void);
+
+/* Replaces model construction + `.to(device)` in Processor/Test/Demo_test.py:51-58.  Refuses non-sm_100 devices. */
+int mmego_create(mmego_handle** out, int device);
+int mmego_destroy(mmego_handle* h);
+/* Text of the last error on this handle (or of the last failed mmego_create when h is NULL). */
+const char* mmego_last_error(const mmego_handle* h);
+
+/* Options: "imu_chunk" (snippets per IMU_Net workspace chunk, default 512),
+ *          "imu_gemm"  (0 = fp32 FFMA recurrent GEMM, 1 = tcgen05 fp16x3 split-precision tensor-core GEMM). */
+int mmego_set_option(mmego_handle* h, const char* key, long long value);
+
+/* Replaces IMUNet.load / UpperNet.load / LowerNet.load (Net/IMU_Net.py:106-114, Net/Upper_Net.py:400-404,
+ * Net/Lower_Net.py:251-258): `names[i]` is a state_dict key, `ptrs_host[i]` its fp32 data on the HOST,
+ * `numels[i]` its element count.  Non-float entries (num_batches_tracked) and unused tensors may be omitted. */
+int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const float* const* ptrs_host,
+                      const long long* numels, int n);
+
+/* Bytes of device workspace the stage needs for these shapes (0 on error). */
+size_t mmego_workspace_bytes(const mmego_handle* h, int stage, int B, int L, int N, int n_imu);
+
+/* IMUNet.forward (Net/IMU_Net.py:67-94): imu [B,L,n_imu,15] -> R [B,L,3,3], t [B,L,3]. */
+int mmego_imu_forward(mmego_handle* h, const float* imu, float* R, float* t, int B, int L, int n_imu, void* ws,
+                      size_t ws_bytes, void* stream);
+
+/* UpperNet.forward (Net/Upper_Net.py:374-388).  x [B,L,N,6] is IN-OUT: xyz is overwritten with R(xyz - t) exactly
+ * as the reference's in-place Transform2H does.  h0,c0,hn,cn [6,B,64]; initial_body [B_global,20,3];
+ * outputs l [B,L,15,3], q [B,L,14,3,3], global_w [B*L,N,1].  q/global_w/hn/cn may be NULL.
+ * b_offset/B_global describe this shard's place in the unsharded batch (for MMEGO_BODY_REF). */
+int mmego_upper_forward(mmego_handle* h, float* x, const float* h0, const float* c0, const float* initial_body,
+                        const float* R, const float* t, float* l, float* q, float* global_w, float* hn, float* cn,
+                        int B, int L, int N, int body_index_mode, int b_offset, int B_global, void* ws,
+                        size_t ws_bytes, void* stream);
+
+/* LowerNet.forward (Net/Lower_Net.py:177-239).  x [B,L,N,6] IN-OUT (second in-place Transform2H);
+ * upper_l [B,L,15,3] is read only; outputs l [B,L,8,3], q [B,L,6,3,3] (q may be NULL).
+ * Top-64 tie rule: among equal keys the lowest slot index wins (torch.sort(stable=True)). */
+int mmego_lower_forward(mmego_handle* h, const float* upper_l, float* x, const float* initial_body, const float* R,
+                        const float* t, float* l, float* q, int B, int L, int N, int body_index_mode, int b_offset,
+                        int B_global, void* ws, size_t ws_bytes, void* stream);
+
+/* GCN.Model.extract_feature (Net/GCN.py:332-355) with the Lower_Net checkpoint's keyEncoder.gcn.* weights:
+ * x [B,3,T,15,1] -> out [B,T,15,64] (raw reinterpretation of the [B,64,T,15] block, as the reference). */
+int mmego_gcn_extract_feature(mmego_handle* h, const float* x, float* out, int B, int T, void* ws, size_t ws_bytes,
+                              void* stream);
+
+/* Util/Universal_Util/Utils.py:284-292: points [F,n,D] xyz <- R (xyz - t), in place; R [F,3,3], t [F,3]. */
+int mmego_transform2h(mmego_handle* h, float* points, const float* R, const float* t, long long F, int n, int D,
+                      void* stream);
+/* Util/Universal_Util/Utils.py:274-281: out [F,n,3] = R^T points + t. */
+int mmego_transform2r(mmego_handle* h, const float* points, const float* R, const float* t, float* out, long long F,
+                      int n, void* stream);
+
+/* Processor/Test/Demo_test.py:121-123 + 64-69,150-158: scatters upper_l/lower_l into pred [B,L,21,3] (pred may be
+ * NULL) and, when target [B,L,21,3] and sums are non-NULL, ADDS this batch's error sums into sums[MMEGO_SUMS_LEN]. */
+int mmego_assemble_metrics(mmego_handle* h, const float* upper_l, const float* lower_l, const float* target,
+                           float* pred, double* sums, int B, int L, void* stream);
+
+/* The whole chain of Demo_test.py:111-123 on device buffers: IMU -> Upper -> Lower -> assemble (+metrics when
+ * target/sums given).  x is IN-OUT as above.  R_out/t_out/upper_out/lower_out may be NULL (workspace is used). */
+int mmego_pipeline_forward(mmego_handle* h, const float* imu, float* x, const float* initial_body, const float* target,
+                           float* pred, double* sums, float* R_out, float* t_out, float* upper_out, float* lower_out,
+                           int B, int L, int N, int n_imu, int body_index_mode, int b_offset, int B_global, void* ws,
+                           size_t ws_bytes, void* stream);
+
+/* Same chain with HOST buffers (the call a reference-side binding makes per batch): copies imu/data/skeleton/target
+ * to the device, runs the pipeline, copies pred [B,L,21,3] and sums back.  Device staging is owned by the handle and
+ * grows on demand.  data_host is NOT modified.  Synchronous on return. */
+int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_host, const float* initial_body_host,
+                     const float* target_host, float* pred_host, double* sums_host, int B, int L, int N, int n_imu,
+                     int body_index_mode, int b_offset, int B_global);
+
+/* Test hook: the next forward copies the named intermediate tensor into dst (device, `bytes` capacity). */
+int mmego_debug_tap(mmego_handle* h, const char* name, void* dst, size_t bytes);
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+long long mmego_launch_count(const mmego_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMEGO_B200_H */

@@ -1,0 +1,690 @@
+// api.cu -- the C ABI of libmmego_b200 (include/mmego_b200.h): handle, weight upload, workspace planning and the
+// per-stage kernel schedules.  Everything here is host code; the kernels live in the other .cu files.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/mmego_b200.h"
+#include "internal.h"
+#include "pack.h"
+
+namespace mmego {
+long long g_launches = 0;
+}
+
+using namespace mmego;
+
+namespace {
+
+std::string g_create_err;
+
+int fail(mmego_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                                \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) return fail((h), MMEGO_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------- device buffers
+bool upload(mmego_handle* h, const std::vector<float>& v, DevBuf& out) {
+    if (out.p && out.n != v.size()) {   // re-pack with a different size: drop the old buffer
+        out.p = nullptr;
+    }
+    if (!out.p) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, std::max<size_t>(v.size(), 4) * sizeof(float)) != cudaSuccess) return false;
+        h->owned.push_back(p);
+        out.p = static_cast<float*>(p);
+        out.n = v.size();
+    }
+    return cudaMemcpy(out.p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+bool upload(mmego_handle* h, const HostPackedGemm& g, PackedGemm& out) {
+    out.N = g.N; out.ldw = g.ldw; out.nseg = g.nseg;
+    for (int i = 0; i < kMaxSeg; ++i) { out.k[i] = g.k[i]; out.kpad[i] = g.kpad[i]; }
+    return upload(h, g.w, out.w) && upload(h, g.bias, out.bias);
+}
+
+// ---------------------------------------------------------------------------------------------- workspace carving
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+    float* f(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+        off += n * sizeof(float);
+        return p;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- GEMM helpers
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+GemmArgs gemm_begin(const PackedGemm& w, float* c, long long ldc, long long M, int relu) {
+    GemmArgs g{};
+    g.nseg = 0;
+    g.w = w.w.p;
+    g.ldw = w.ldw;
+    g.ktot = 0;
+    g.bias = w.bias.p;
+    g.c = c;
+    g.ldc = ldc;
+    g.M = (int)M;
+    g.N = w.N;
+    g.relu = relu;
+    g.rowmod = 0;
+    g.cstate = nullptr;
+    g.ldcs = 0;
+    g.has_state = 0;
+    g.f6_period = 0;
+    return g;
+}
+// appends the next packed K segment of `w` (segments must be added in packing order)
+void gemm_seg(GemmArgs& g, const PackedGemm& w, const float* a, long long lda, int shift = 0, int period = 0) {
+    const int s = g.nseg++;
+    g.seg[s].a = a;
+    g.seg[s].lda = lda;
+    g.seg[s].k = w.k[s];
+    g.seg[s].kpad = w.kpad[s];
+    g.seg[s].shift = shift;
+    g.seg[s].period = period;
+    g.seg[s].vec = (aligned16(a) && lda % 4 == 0 && w.k[s] % 8 == 0) ? 1 : 0;
+    g.ktot += w.kpad[s];
+}
+int pick_bn(int N) { return N >= 96 ? 128 : (N >= 48 ? 64 : 32); }
+
+void run_gemm(mmego_handle* h, const GemmArgs& g, int epi, cudaStream_t st, int bn = 0) {
+    GemmBatch b{};
+    b.g[0] = g;
+    launch_gemm(b, 1, bn ? bn : pick_bn(g.N), epi, st);
+    (void)h;
+}
+// simple single-segment linear layer: c [M,N] = act(a [M,K] W^T + b)
+void linear(mmego_handle* h, const PackedGemm& w, const float* a, long long lda, float* c, long long ldc, long long M,
+            int relu, cudaStream_t st) {
+    GemmArgs g = gemm_begin(w, c, ldc, M, relu);
+    gemm_seg(g, w, a, lda);
+    run_gemm(h, g, EPI_STORE, st);
+}
+
+void tap(mmego_handle* h, const char* name, const void* src, size_t bytes, cudaStream_t st) {
+    auto it = h->taps.find(name);
+    if (it == h->taps.end()) return;
+    const size_t n = bytes < it->second.second ? bytes : it->second.second;
+    cudaMemcpyAsync(it->second.first, src, n, cudaMemcpyDeviceToDevice, st);
+    h->taps.erase(it);
+}
+
+// ---------------------------------------------------------------------------------------------- H=64 bi-LSTM stack
+struct SmallLstmWs {
+    float* gx;       // [S*T, 512]
+    float* y[2];     // ping-pong [S*T, 128]
+};
+void plan_small_lstm(Carver& c, long long S, int T, SmallLstmWs& w) {
+    w.gx = c.f((size_t)S * T * 512);
+    w.y[0] = c.f((size_t)S * T * 128);
+    w.y[1] = c.f((size_t)S * T * 128);
+}
+// in [S*T, In] -> returns pointer to the last layer's output [S*T, 128]
+const float* run_small_lstm(mmego_handle* h, const PackedSmallLstmLayer* layers, const float* in, int in_ld,
+                            const float* h0, const float* c0, float* hn, float* cn, long long S, int T,
+                            const SmallLstmWs& w, cudaStream_t st) {
+    const float* cur = in;
+    long long ld = in_ld;
+    for (int l = 0; l < 3; ++l) {
+        linear(h, layers[l].ih, cur, ld, w.gx, 512, S * T, 0, st);
+        const size_t so = (size_t)l * 2 * S * kSmallH;
+        launch_lstm_small(w.gx, layers[l].whh.p, h0 ? h0 + so : nullptr, c0 ? c0 + so : nullptr, w.y[l & 1],
+                          hn ? hn + so : nullptr, cn ? cn + so : nullptr, (int)S, T, st);
+        cur = w.y[l & 1];
+        ld = 128;
+    }
+    return cur;
+}
+
+// ---------------------------------------------------------------------------------------------- IMU_Net schedule
+struct ImuWs {
+    float *u, *y0, *y1, *cst, *s, *z0, *z1;
+};
+void plan_imu(Carver& c, long long Bc, int L, int n, ImuWs& w) {
+    const size_t S = (size_t)Bc * L;
+    w.u = c.f(S * n * kImuH);
+    w.y0 = c.f(S * n * 2 * kImuH);
+    w.y1 = c.f(S * n * 2 * kImuH);
+    w.cst = c.f(2 * S * kImuH);
+    w.s = c.f(S * 2 * kImuH);
+    w.z0 = c.f(S * 2 * kImuH);
+    w.z1 = c.f(S * 2 * kImuH);
+}
+
+// one bidirectional H=512 layer over `T` steps for `S` sequences; x [S, T, In] -> y [S, T, 1024]
+// Each timestep is ONE launch covering both directions (blockIdx.z) of an fp32 GEMM over K = [x_t | h_{t-1}] with the
+// LSTM cell fused into the epilogue (gemm_ffma.cu).
+void run_big_lstm_layer(mmego_handle* h, const PackedBigLstmLayer& lw, const float* x, int In, float* y, float* cst,
+                        long long S, int T, cudaStream_t st) {
+    const int H = kImuH;
+    for (int step = 0; step < T; ++step) {
+        GemmBatch b{};
+        for (int d = 0; d < 2; ++d) {
+            const int tt = d ? (T - 1 - step) : step;
+            const int tp = d ? (tt + 1) : (tt - 1);
+            const PackedGemm& w = lw.dir[d];
+            GemmArgs g = gemm_begin(w, y + (size_t)tt * 2 * H + d * H, (long long)T * 2 * H, S, 0);
+            gemm_seg(g, w, x + (size_t)tt * In, (long long)T * In);
+            if (step > 0) gemm_seg(g, w, y + (size_t)tp * 2 * H + d * H, (long long)T * 2 * H);
+            g.cstate = cst + (size_t)d * S * H;
+            g.ldcs = H;
+            g.has_state = step > 0;
+            b.g[d] = g;
+        }
+        launch_gemm(b, 2, 128, EPI_LSTM, st);
+    }
+    (void)h;
+}
+
+int imu_chunk_forward(mmego_handle* h, const float* imu, float* R, float* t, long long Bc, int L, int n,
+                      const ImuWs& w, cudaStream_t st) {
+    const long long S = Bc * L;
+    const ImuWeights& W = h->imu;
+    linear(h, W.fc1, imu, kImuFeat, w.u, kImuH, S * n, 1, st);                          // Net/IMU_Net.py:79
+    tap(h, "imu.u", w.u, (size_t)S * n * kImuH * 4, st);
+    run_big_lstm_layer(h, W.fast[0], w.u, kImuH, w.y0, w.cst, S, n, st);                 // :80
+    run_big_lstm_layer(h, W.fast[1], w.y0, 2 * kImuH, w.y1, w.cst, S, n, st);
+    tap(h, "imu.f", w.y1, (size_t)S * n * 2 * kImuH * 4, st);
+    launch_imu_pool(w.y1, W.attn.p, w.s, S, n, st);                                      // :82-83
+    tap(h, "imu.s", w.s, (size_t)S * 2 * kImuH * 4, st);
+    run_big_lstm_layer(h, W.slow[0], w.s, 2 * kImuH, w.z0, w.cst, Bc, L, st);            // :85
+    run_big_lstm_layer(h, W.slow[1], w.z0, 2 * kImuH, w.z1, w.cst, Bc, L, st);
+    tap(h, "imu.g", w.z1, (size_t)S * 2 * kImuH * 4, st);
+    launch_imu_decode(w.z1, W.fc2.p, R, t, S, st);                                       // :87-93
+    return MMEGO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- Upper_Net schedule
+struct UpperWs {
+    float* g;        // [F,64]
+    SmallLstmWs lstm;
+    float* h1;       // [F,128]
+    float* o;        // [F,87]
+};
+void plan_upper(Carver& c, long long B, int L, UpperWs& w) {
+    const size_t F = (size_t)B * L;
+    w.g = c.f(F * 64);
+    plan_small_lstm(c, B, L, w.lstm);
+    w.h1 = c.f(F * 128);
+    w.o = c.f(F * 87);
+}
+
+// ---------------------------------------------------------------------------------------------- Lower_Net schedule
+struct LowerWs {
+    float *uh, *ya, *u, *y[2], *kf, *ak, *f0, *f1, *o;
+    SmallLstmWs lstm;
+};
+void plan_lower(Carver& c, long long B, int L, LowerWs& w) {
+    const size_t F = (size_t)B * L, FV = F * kGcnV;
+    w.uh = c.f(F * 45);
+    w.ya = c.f(FV * 128);       // aggregated input of the widest layer: 2 * 64
+    w.u = c.f(FV * 128);        // graph-conv output of the widest layer
+    w.y[0] = c.f(FV * 128);
+    w.y[1] = c.f(FV * 128);
+    w.kf = c.f(FV * 64);
+    w.ak = c.f(F * 192);
+    plan_small_lstm(c, B, L, w.lstm);
+    w.f0 = c.f(F * 128);
+    w.f1 = c.f(F * 64);
+    w.o = c.f(F * 42);
+}
+
+// GCN.Model.extract_feature body on channel-last rows; y0 [F*15, 3] (data_bn already applied) -> kf [B][64][L*15]
+void run_gcn(mmego_handle* h, const float* y0, int B, int L, const LowerWs& w, cudaStream_t st) {
+    const LowerWeights& W = h->lower;
+    const long long F = (long long)B * L, FV = F * kGcnV;
+    const float* y = y0;
+    for (int i = 0; i < 3; ++i) {
+        const GcnLayerWeights& g = W.gcn[i];
+        launch_gcn_agg(y, g.ahat.p, w.ya, F, g.cin, h->sm_count, st);                    // Net/GCN.py:62 (commuted)
+        {
+            GemmArgs a = gemm_begin(g.gconv, w.u, g.cout, FV, 1);                        // :58 + tcn.0/1 (BN, ReLU)
+            gemm_seg(a, g.gconv, w.ya, 2 * g.cin);
+            a.rowmod = kGcnV;
+            run_gemm(h, a, EPI_STORE, st);
+        }
+        {
+            float* out = w.y[i & 1];
+            GemmArgs a = gemm_begin(g.tconv, out, g.cout, FV, 1);                        // :109-116 + residual :128-147
+            for (int tau = 0; tau < 9; ++tau) gemm_seg(a, g.tconv, w.u, g.cout, (tau - 4) * kGcnV, L * kGcnV);
+            gemm_seg(a, g.tconv, y, g.cin);
+            run_gemm(h, a, EPI_STORE, st);
+            y = out;
+        }
+    }
+    GemmArgs a = gemm_begin(W.fcn, w.kf, 0, FV, 0);                                      // :352-353 (F6 layout)
+    gemm_seg(a, W.fcn, y, 128);
+    a.f6_period = L * kGcnV;
+    run_gemm(h, a, EPI_F6, st, 64);
+}
+
+bool is_stream_ok(void*) { return true; }
+
+int check_dims(mmego_handle* h, int B, int L, int N) {
+    if (!h) return MMEGO_EINVAL;
+    if (B <= 0 || L <= 0 || N <= 0) return fail(h, MMEGO_ESHAPE, "B, L, N must be positive (got %d, %d, %d)", B, L, N);
+    if ((long long)B * L * kGcnV * 128 > 2000000000LL) return fail(h, MMEGO_ESHAPE, "batch too large for one call: B*L = %lld", (long long)B * L);
+    return MMEGO_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int mmego_abi_version(void) { return MMEGO_ABI_VERSION; }
+
+int mmego_create(mmego_handle** out, int device) {
+    if (!out) return fail(nullptr, MMEGO_EINVAL, "mmego_create: out is NULL");
+    *out = nullptr;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, MMEGO_ECUDA, "cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, MMEGO_EARCH, "device %d (%s) is sm_%d%d; libmmego_b200 is built for sm_100a only", device,
+                    prop.name, prop.major, prop.minor);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, MMEGO_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    mmego_handle* h = new mmego_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    *out = h;
+    return MMEGO_OK;
+}
+
+int mmego_destroy(mmego_handle* h) {
+    if (!h) return MMEGO_EINVAL;
+    cudaSetDevice(h->device);
+    for (void* p : h->owned) cudaFree(p);
+    if (h->stage_dev) cudaFree(h->stage_dev);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return MMEGO_OK;
+}
+
+const char* mmego_last_error(const mmego_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int mmego_set_option(mmego_handle* h, const char* key, long long value) {
+    if (!h || !key) return MMEGO_EINVAL;
+    if (!strcmp(key, "imu_chunk")) {
+        if (value <= 0) return fail(h, MMEGO_EINVAL, "imu_chunk must be positive");
+        h->imu_chunk = value;
+        return MMEGO_OK;
+    }
+    if (!strcmp(key, "imu_gemm")) {
+        if (value != 0) return fail(h, MMEGO_EINVAL, "imu_gemm=%lld is not available in this build", value);
+        h->imu_gemm = (int)value;
+        return MMEGO_OK;
+    }
+    return fail(h, MMEGO_EINVAL, "unknown option '%s'", key);
+}
+
+int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const float* const* ptrs_host,
+                      const long long* numels, int n) {
+    if (!h || !names || !ptrs_host || !numels || n < 0) return MMEGO_EINVAL;
+    cudaSetDevice(h->device);
+    StateDict sd;
+    for (int i = 0; i < n; ++i) {
+        if (!names[i] || !ptrs_host[i]) return fail(h, MMEGO_EINVAL, "set_weights: entry %d is NULL", i);
+        sd.m[names[i]] = {ptrs_host[i], numels[i]};
+    }
+    bool ok = true;
+    try {
+        if (net == MMEGO_NET_IMU) {
+            ImuWeights& W = h->imu;
+            W.ready = false;
+            const int H = kImuH;
+            ok &= upload(h, pack_linear(sd.get("fc1.weight", H * kImuFeat), sd.get("fc1.bias", H), H, {kImuFeat}), W.fc1);
+            for (int l = 0; l < 2; ++l) {
+                HostBigLstm f = pack_big_lstm(sd, "rnn_fast.", l, l == 0 ? H : 2 * H, H);
+                HostBigLstm s = pack_big_lstm(sd, "rnn_slow.", l, 2 * H, H);
+                for (int d = 0; d < 2; ++d) {
+                    ok &= upload(h, f.dir[d], W.fast[l].dir[d]);
+                    ok &= upload(h, s.dir[d], W.slow[l].dir[d]);
+                }
+            }
+            std::vector<float> attn(2 * H + 4, 0.f);
+            memcpy(attn.data(), sd.get("attn.weight", 2 * H), sizeof(float) * 2 * H);
+            attn[2 * H] = sd.get("attn.bias", 1)[0];
+            ok &= upload(h, attn, W.attn);
+            std::vector<float> fc2(9 * 2 * H + 12, 0.f);
+            memcpy(fc2.data(), sd.get("fc2.weight", 9 * 2 * H), sizeof(float) * 9 * 2 * H);
+            memcpy(fc2.data() + 9 * 2 * H, sd.get("fc2.bias", 9), sizeof(float) * 9);
+            ok &= upload(h, fc2, W.fc2);
+            W.ready = ok;
+        } else if (net == MMEGO_NET_UPPER) {
+            UpperWeights& W = h->upper;
+            W.ready = false;
+            ok &= upload(h, pack_upper_point(sd), W.point);
+            for (int l = 0; l < 3; ++l) {
+                HostSmallLstm s = pack_small_lstm(sd, "module1.grnn.", l, l == 0 ? 64 : 128);
+                ok &= upload(h, s.ih, W.lstm[l].ih) && upload(h, s.whh, W.lstm[l].whh);
+                W.lstm[l].in = s.in;
+            }
+            ok &= upload(h, pack_linear(sd.get("mlpHead.fc1.weight", 128 * 128), sd.get("mlpHead.fc1.bias", 128), 128, {128}), W.fc1);
+            ok &= upload(h, pack_linear(sd.get("mlpHead.fc2.weight", 87 * 128), sd.get("mlpHead.fc2.bias", 87), 87, {128}), W.fc2);
+            W.ready = ok;
+        } else if (net == MMEGO_NET_LOWER) {
+            LowerWeights& W = h->lower;
+            W.ready = false;
+            ok &= upload(h, pack_lower_frame(sd), W.frame);
+            const std::string gp = "keyEncoder.gcn.";
+            ok &= upload(h, pack_data_bn(sd, gp), W.data_bn);
+            const int ch[4] = {3, 32, 64, 128};
+            for (int i = 0; i < 3; ++i) {
+                HostGcnLayer L = pack_gcn_layer(sd, gp, i, ch[i], ch[i + 1]);
+                ok &= upload(h, L.ahat, W.gcn[i].ahat) && upload(h, L.gconv, W.gcn[i].gconv) && upload(h, L.tconv, W.gcn[i].tconv);
+                W.gcn[i].cin = L.cin;
+                W.gcn[i].cout = L.cout;
+            }
+            ok &= upload(h, pack_linear(sd.get(gp + "fcn.weight", 64 * 128), sd.get(gp + "fcn.bias", 64), 64, {128}), W.fcn);
+            for (int l = 0; l < 3; ++l) {
+                HostSmallLstm s = pack_small_lstm(sd, "fusion.rnn_pk.", l, l == 0 ? 192 : 128);
+                ok &= upload(h, s.ih, W.lstm[l].ih) && upload(h, s.whh, W.lstm[l].whh);
+                W.lstm[l].in = s.in;
+            }
+            ok &= upload(h, pack_linear(sd.get("fusion.fc0.weight", 128 * 173), sd.get("fusion.fc0.bias", 128), 128, {128, 45}), W.fc0);
+            ok &= upload(h, pack_linear(sd.get("fusion.fc1.weight", 64 * 128), sd.get("fusion.fc1.bias", 64), 64, {128}), W.fc1);
+            ok &= upload(h, pack_linear(sd.get("fusion.fc2.weight", 42 * 64), sd.get("fusion.fc2.bias", 42), 42, {64}), W.fc2);
+            W.ready = ok;
+        } else {
+            return fail(h, MMEGO_EINVAL, "set_weights: unknown net %d", net);
+        }
+    } catch (const std::exception& ex) {
+        return fail(h, MMEGO_ESHAPE, "set_weights: %s", ex.what());
+    }
+    if (!ok) return fail(h, MMEGO_ENOMEM, "set_weights: device allocation or upload failed");
+    return MMEGO_OK;
+}
+
+size_t mmego_workspace_bytes(const mmego_handle* h, int stage, int B, int L, int N, int n_imu) {
+    if (!h || B <= 0 || L <= 0) return 0;
+    (void)N;
+    Carver c(nullptr);
+    const long long Bc = B < h->imu_chunk ? B : h->imu_chunk;
+    if (stage == MMEGO_STAGE_IMU) {
+        ImuWs w;
+        plan_imu(c, Bc, L, n_imu, w);
+    } else if (stage == MMEGO_STAGE_UPPER) {
+        UpperWs w;
+        plan_upper(c, B, L, w);
+    } else if (stage == MMEGO_STAGE_LOWER || stage == MMEGO_STAGE_GCN) {
+        LowerWs w;
+        plan_lower(c, B, L, w);
+    } else if (stage == MMEGO_STAGE_PIPELINE) {
+        // R, t, upper_l, lower_l + the largest stage workspace (stages run back to back and reuse it)
+        const size_t F = (size_t)B * L;
+        c.f(F * 9); c.f(F * 3); c.f(F * 45); c.f(F * 24);
+        size_t best = 0;
+        {
+            Carver s(nullptr); ImuWs w; plan_imu(s, Bc, L, n_imu, w); best = std::max(best, s.off);
+        }
+        {
+            Carver s(nullptr); UpperWs w; plan_upper(s, B, L, w); best = std::max(best, s.off);
+        }
+        {
+            Carver s(nullptr); LowerWs w; plan_lower(s, B, L, w); best = std::max(best, s.off);
+        }
+        c.f(best / sizeof(float) + 64);
+    } else {
+        return 0;
+    }
+    return c.off + 256;
+}
+
+int mmego_imu_forward(mmego_handle* h, const float* imu, float* R, float* t, int B, int L, int n_imu, void* ws,
+                      size_t ws_bytes, void* stream) {
+    if (int rc = check_dims(h, B, L, 1)) return rc;
+    if (!imu || !R || !t || !ws) return fail(h, MMEGO_EINVAL, "imu_forward: NULL argument");
+    if (!h->imu.ready) return fail(h, MMEGO_ESTATE, "imu_forward: IMU_Net weights were never set");
+    if (n_imu <= 0 || n_imu > 64) return fail(h, MMEGO_ESHAPE, "imu_forward: n_imu must be in 1..64 (got %d)", n_imu);
+    if (ws_bytes < mmego_workspace_bytes(h, MMEGO_STAGE_IMU, B, L, 0, n_imu))
+        return fail(h, MMEGO_ENOMEM, "imu_forward: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long Bc = B < h->imu_chunk ? B : h->imu_chunk;
+    Carver c(ws);
+    ImuWs w;
+    plan_imu(c, Bc, L, n_imu, w);
+    for (long long b0 = 0; b0 < B; b0 += Bc) {
+        const long long nb = (B - b0) < Bc ? (B - b0) : Bc;
+        imu_chunk_forward(h, imu + (size_t)b0 * L * n_imu * kImuFeat, R + (size_t)b0 * L * 9, t + (size_t)b0 * L * 3, nb, L,
+                          n_imu, w, st);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches = g_launches;
+    return MMEGO_OK;
+}
+
+int mmego_upper_forward(mmego_handle* h, float* x, const float* h0, const float* c0, const float* initial_body,
+                        const float* R, const float* t, float* l, float* q, float* global_w, float* hn, float* cn,
+                        int B, int L, int N, int body_index_mode, int b_offset, int B_global, void* ws,
+                        size_t ws_bytes, void* stream) {
+    if (int rc = check_dims(h, B, L, N)) return rc;
+    if (!x || !initial_body || !R || !t || !l || !ws) return fail(h, MMEGO_EINVAL, "upper_forward: NULL argument");
+    if (!h->upper.ready) return fail(h, MMEGO_ESTATE, "upper_forward: Upper_Net weights were never set");
+    if (body_index_mode != MMEGO_BODY_REF && body_index_mode != MMEGO_BODY_PER_SNIPPET)
+        return fail(h, MMEGO_EINVAL, "upper_forward: bad body_index_mode %d", body_index_mode);
+    if (B_global < B + b_offset || b_offset < 0) return fail(h, MMEGO_EINVAL, "upper_forward: bad shard (b_offset %d, B %d, B_global %d)", b_offset, B, B_global);
+    if (ws_bytes < mmego_workspace_bytes(h, MMEGO_STAGE_UPPER, B, L, N, 0))
+        return fail(h, MMEGO_ENOMEM, "upper_forward: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long F = (long long)B * L;
+    Carver c(ws);
+    UpperWs w;
+    plan_upper(c, B, L, w);
+    const UpperWeights& W = h->upper;
+    launch_upper_point(x, R, t, W.point.p, w.g, global_w, F, N, h->sm_count, st);       // Upper_Net.py:379-381 (+gpointnet)
+    tap(h, "upper.g", w.g, (size_t)F * 64 * 4, st);
+    const float* hs = run_small_lstm(h, W.lstm, w.g, 64, h0, c0, hn, cn, B, L, w.lstm, st);   // :339
+    tap(h, "upper.lstm", hs, (size_t)F * 128 * 4, st);
+    linear(h, W.fc1, hs, 128, w.h1, 128, F, 1, st);                                     // :351-353
+    linear(h, W.fc2, w.h1, 128, w.o, 87, F, 0, st);
+    tap(h, "upper.o", w.o, (size_t)F * 87 * 4, st);
+    launch_upper_decode(w.o, initial_body, R, t, l, q, F, L, body_index_mode, (long long)b_offset * L, B_global, st);   // :355-387
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches = g_launches;
+    return MMEGO_OK;
+}
+
+int mmego_lower_forward(mmego_handle* h, const float* upper_l, float* x, const float* initial_body, const float* R,
+                        const float* t, float* l, float* q, int B, int L, int N, int body_index_mode, int b_offset,
+                        int B_global, void* ws, size_t ws_bytes, void* stream) {
+    if (int rc = check_dims(h, B, L, N)) return rc;
+    if (!upper_l || !x || !initial_body || !R || !t || !l || !ws) return fail(h, MMEGO_EINVAL, "lower_forward: NULL argument");
+    if (!h->lower.ready) return fail(h, MMEGO_ESTATE, "lower_forward: Lower_Net weights were never set");
+    if (N < kLowerPts || N > lower_frame_max_points())
+        return fail(h, MMEGO_ESHAPE, "lower_forward: N must be in %d..%d (got %d)", kLowerPts, lower_frame_max_points(), N);
+    if (body_index_mode != MMEGO_BODY_REF && body_index_mode != MMEGO_BODY_PER_SNIPPET)
+        return fail(h, MMEGO_EINVAL, "lower_forward: bad body_index_mode %d", body_index_mode);
+    if (B_global < B + b_offset || b_offset < 0) return fail(h, MMEGO_EINVAL, "lower_forward: bad shard (b_offset %d, B %d, B_global %d)", b_offset, B, B_global);
+    if (ws_bytes < mmego_workspace_bytes(h, MMEGO_STAGE_LOWER, B, L, N, 0))
+        return fail(h, MMEGO_ENOMEM, "lower_forward: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long F = (long long)B * L;
+    Carver c(ws);
+    LowerWs w;
+    plan_lower(c, B, L, w);
+    const LowerWeights& W = h->lower;
+    float* y0 = w.y[1];   // layer 0 writes y[0], so y[1] is free to hold the 3-channel input
+    launch_gcn_prep(upper_l, R, t, W.data_bn.p, w.uh, y0, F, st);                         // Lower_Net.py:229, GCN.py:339-344
+    tap(h, "lower.uh", w.uh, (size_t)F * 45 * 4, st);
+    run_gcn(h, y0, B, L, w, st);
+    tap(h, "lower.K", w.kf, (size_t)F * kGcnV * 64 * 4, st);
+    launch_lower_frame(x, R, t, w.kf, W.frame.p, w.ak, F, N, h->sm_count, st);           // :191-192, 216-227, 231, 104-116
+    tap(h, "lower.ak", w.ak, (size_t)F * 192 * 4, st);
+    const float* hs = run_small_lstm(h, W.lstm, w.ak, 192, nullptr, nullptr, nullptr, nullptr, B, L, w.lstm, st);   // :117
+    tap(h, "lower.lstm", hs, (size_t)F * 128 * 4, st);
+    {
+        GemmArgs a = gemm_begin(W.fc0, w.f0, 128, F, 1);                                  // :119-121
+        gemm_seg(a, W.fc0, hs, 128);
+        gemm_seg(a, W.fc0, w.uh, 45);
+        run_gemm(h, a, EPI_STORE, st);
+    }
+    linear(h, W.fc1, w.f0, 128, w.f1, 64, F, 1, st);                                      // :122-123
+    linear(h, W.fc2, w.f1, 64, w.o, 42, F, 0, st);                                        // :124
+    tap(h, "lower.o", w.o, (size_t)F * 42 * 4, st);
+    launch_lower_decode(w.o, initial_body, R, t, l, q, F, L, body_index_mode, (long long)b_offset * L, B_global, st);   // :126-135, 235-238
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches = g_launches;
+    return MMEGO_OK;
+}
+
+int mmego_gcn_extract_feature(mmego_handle* h, const float* x, float* out, int B, int T, void* ws, size_t ws_bytes,
+                              void* stream) {
+    if (int rc = check_dims(h, B, T, 1)) return rc;
+    if (!x || !out || !ws) return fail(h, MMEGO_EINVAL, "gcn_extract_feature: NULL argument");
+    if (!h->lower.ready) return fail(h, MMEGO_ESTATE, "gcn_extract_feature: Lower_Net weights were never set");
+    if (ws_bytes < mmego_workspace_bytes(h, MMEGO_STAGE_GCN, B, T, 0, 0))
+        return fail(h, MMEGO_ENOMEM, "gcn_extract_feature: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Carver c(ws);
+    LowerWs w;
+    plan_lower(c, B, T, w);
+    float* y0 = w.y[1];
+    launch_gcn_prep_raw(x, h->lower.data_bn.p, y0, B, T, st);
+    run_gcn(h, y0, B, T, w, st);
+    CUDA_TRY(h, cudaMemcpyAsync(out, w.kf, (size_t)B * T * kGcnV * 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches = g_launches;
+    return MMEGO_OK;
+}
+
+int mmego_transform2h(mmego_handle* h, float* points, const float* R, const float* t, long long F, int n, int D,
+                      void* stream) {
+    if (!h) return MMEGO_EINVAL;
+    if (!points || !R || !t || F < 0 || n <= 0 || D < 3) return fail(h, MMEGO_EINVAL, "transform2h: bad argument");
+    launch_transform2h(points, R, t, F, n, D, static_cast<cudaStream_t>(stream));
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches = g_launches;
+    return MMEGO_OK;
+}
+
+int mmego_transform2r(mmego_handle* h, const float* points, const float* R, const float* t, float* out, long long F,
+                      int n, void* stream) {
+    if (!h) return MMEGO_EINVAL;
+    if (!points || !R || !t || !out || F < 0 || n <= 0) return fail(h, MMEGO_EINVAL, "transform2r: bad argument");
+    launch_transform2r(points, R, t, out, F, n, static_cast<cudaStream_t>(stream));
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches = g_launches;
+    return MMEGO_OK;
+}
+
+int mmego_assemble_metrics(mmego_handle* h, const float* upper_l, const float* lower_l, const float* target,
+                           float* pred, double* sums, int B, int L, void* stream) {
+    if (int rc = check_dims(h, B, L, 1)) return rc;
+    if (!upper_l || !lower_l) return fail(h, MMEGO_EINVAL, "assemble_metrics: NULL argument");
+    launch_assemble_metrics(upper_l, lower_l, target, pred, sums, (long long)B * L, static_cast<cudaStream_t>(stream));
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches = g_launches;
+    return MMEGO_OK;
+}
+
+int mmego_pipeline_forward(mmego_handle* h, const float* imu, float* x, const float* initial_body, const float* target,
+                           float* pred, double* sums, float* R_out, float* t_out, float* upper_out, float* lower_out,
+                           int B, int L, int N, int n_imu, int body_index_mode, int b_offset, int B_global, void* ws,
+                           size_t ws_bytes, void* stream) {
+    if (int rc = check_dims(h, B, L, N)) return rc;
+    if (!imu || !x || !initial_body || !ws) return fail(h, MMEGO_EINVAL, "pipeline_forward: NULL argument");
+    if (ws_bytes < mmego_workspace_bytes(h, MMEGO_STAGE_PIPELINE, B, L, N, n_imu))
+        return fail(h, MMEGO_ENOMEM, "pipeline_forward: workspace too small");
+    const size_t F = (size_t)B * L;
+    Carver c(ws);
+    float* R = c.f(F * 9);
+    float* t = c.f(F * 3);
+    float* up = c.f(F * 45);
+    float* lo = c.f(F * 24);
+    float* sub = c.f(64);
+    const size_t sub_bytes = ws_bytes - (size_t)(reinterpret_cast<char*>(sub) - static_cast<char*>(ws));
+    if (R_out) R = R_out;
+    if (t_out) t = t_out;
+    if (upper_out) up = upper_out;
+    if (lower_out) lo = lower_out;
+    int rc = mmego_imu_forward(h, imu, R, t, B, L, n_imu, sub, sub_bytes, stream);
+    if (rc) return rc;
+    // h0 = c0 = 0 as built at Processor/Test/Demo_test.py:106-107
+    rc = mmego_upper_forward(h, x, nullptr, nullptr, initial_body, R, t, up, nullptr, nullptr, nullptr, nullptr, B, L, N,
+                             body_index_mode, b_offset, B_global, sub, sub_bytes, stream);
+    if (rc) return rc;
+    rc = mmego_lower_forward(h, up, x, initial_body, R, t, lo, nullptr, B, L, N, body_index_mode, b_offset, B_global, sub,
+                             sub_bytes, stream);
+    if (rc) return rc;
+    return mmego_assemble_metrics(h, up, lo, target, pred, sums, B, L, stream);
+}
+
+int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_host, const float* initial_body_host,
+                     const float* target_host, float* pred_host, double* sums_host, int B, int L, int N, int n_imu,
+                     int body_index_mode, int b_offset, int B_global) {
+    if (int rc = check_dims(h, B, L, N)) return rc;
+    if (!imu_host || !data_host || !initial_body_host) return fail(h, MMEGO_EINVAL, "infer_host: NULL argument");
+    cudaSetDevice(h->device);
+    if (!h->own_stream) CUDA_TRY(h, cudaStreamCreate(&h->own_stream));
+    cudaStream_t st = h->own_stream;
+    const size_t F = (size_t)B * L;
+    const size_t ws_bytes = mmego_workspace_bytes(h, MMEGO_STAGE_PIPELINE, B, L, N, n_imu);
+    Carver c(nullptr);
+    // staging layout: imu, data, body, target, pred, sums(double), ws
+    auto plan = [&](Carver& k, float*& imu, float*& data, float*& body, float*& tg, float*& pred, float*& sums, float*& ws) {
+        imu = k.f(F * n_imu * kImuFeat);
+        data = k.f(F * N * 6);
+        body = k.f((size_t)B_global * 60);
+        tg = k.f(F * 63);
+        pred = k.f(F * 63);
+        sums = k.f(2 * MMEGO_SUMS_LEN);
+        ws = k.f(ws_bytes / sizeof(float) + 64);
+    };
+    float *imu, *data, *body, *tg, *pred, *sums, *ws;
+    plan(c, imu, data, body, tg, pred, sums, ws);
+    const size_t need = c.off + 256;
+    if (need > h->stage_bytes) {
+        if (h->stage_dev) cudaFree(h->stage_dev);
+        h->stage_dev = nullptr;
+        h->stage_bytes = 0;
+        if (cudaMalloc(&h->stage_dev, need) != cudaSuccess) return fail(h, MMEGO_ENOMEM, "infer_host: cannot allocate %zu staging bytes", need);
+        h->stage_bytes = need;
+    }
+    Carver k(h->stage_dev);
+    plan(k, imu, data, body, tg, pred, sums, ws);
+    CUDA_TRY(h, cudaMemcpyAsync(imu, imu_host, F * n_imu * kImuFeat * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(data, data_host, F * N * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(body, initial_body_host, (size_t)B_global * 60 * sizeof(float), cudaMemcpyHostToDevice, st));
+    const bool metrics = target_host && sums_host;
+    if (metrics) {
+        CUDA_TRY(h, cudaMemcpyAsync(tg, target_host, F * 63 * sizeof(float), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(h, cudaMemsetAsync(sums, 0, MMEGO_SUMS_LEN * sizeof(double), st));
+    }
+    int rc = mmego_pipeline_forward(h, imu, data, body, metrics ? tg : nullptr, pred, metrics ? reinterpret_cast<double*>(sums) : nullptr,
+                                    nullptr, nullptr, nullptr, nullptr, B, L, N, n_imu, body_index_mode, b_offset, B_global,
+                                    ws, ws_bytes + 256, st);
+    if (rc) return rc;
+    if (pred_host) CUDA_TRY(h, cudaMemcpyAsync(pred_host, pred, F * 63 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (metrics) CUDA_TRY(h, cudaMemcpyAsync(sums_host, sums, MMEGO_SUMS_LEN * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return MMEGO_OK;
+}
+
+int mmego_debug_tap(mmego_handle* h, const char* name, void* dst, size_t bytes) {
+    if (!h || !name) return MMEGO_EINVAL;
+    if (!dst) { h->taps.erase(name); return MMEGO_OK; }
+    h->taps[name] = {dst, bytes};
+    return MMEGO_OK;
+}
+
+long long mmego_launch_count(const mmego_handle* h) { return h ? g_launches : 0; }
+
+}  // extern "C"

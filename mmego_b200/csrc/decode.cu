@@ -1,0 +1,428 @@
+// decode.cu -- the HBM-bound "K4" kernels: 6D->rotation, forward kinematics, rigid transforms, IMU attention pooling,
+// result assembly and error metrics.  All are streaming kernels: tiles of frames are staged through shared memory
+// with coalesced 128-bit (or widest legal) accesses; per-frame math runs one frame per thread out of shared memory.
+#include "internal.h"
+
+namespace mmego {
+
+namespace {
+
+// skeleton tables (Config/config.py:37-55 of the reference)
+__constant__ int kSkelParent[20] = {20, 3, 2, 2, 2, 4, 5, 6, 8, 9, 10, 1, 0, 0, 12, 13, 14, 16, 17, 18};
+__constant__ int kSkelChild[20] = {3, 2, 1, 4, 8, 5, 6, 7, 9, 10, 11, 0, 12, 16, 13, 14, 15, 17, 18, 19};
+
+constexpr int kSumsLen = 44;   // == MMEGO_SUMS_LEN of the public header
+
+// upper-local index of a 21-joint id: upper_joint_map = [0..12, 16, 20]
+__host__ __device__ constexpr int upper_idx(int j) { return j <= 12 ? j : (j == 16 ? 13 : 14); }
+// lower-local index: lower_joint_map = [12..19]
+__host__ __device__ constexpr int lower_idx(int j) { return j - 12; }
+// rotation slot of a lower child joint: [13,14,15,17,18,19].index(c)
+__host__ __device__ constexpr int lower_rot_idx(int c) { return c <= 15 ? c - 13 : c - 14; }
+
+// Gram-Schmidt 6D -> rotation, columns (x, y, z); m is row-major 3x3.
+__device__ __forceinline__ void ortho6d(const float* a6, float eps, float* m) {
+    float ax = a6[0], ay = a6[1], az = a6[2];
+    const float bx = a6[3], by = a6[4], bz = a6[5];
+    float n = fmaxf(sqrtf(ax * ax + ay * ay + az * az), eps);
+    ax /= n; ay /= n; az /= n;
+    float zx = ay * bz - az * by, zy = az * bx - ax * bz, zz = ax * by - ay * bx;
+    n = fmaxf(sqrtf(zx * zx + zy * zy + zz * zz), eps);
+    zx /= n; zy /= n; zz /= n;
+    const float yx = zy * az - zz * ay, yy = zz * ax - zx * az, yz = zx * ay - zy * ax;
+    m[0] = ax; m[1] = yx; m[2] = zx;
+    m[3] = ay; m[4] = yy; m[5] = zy;
+    m[6] = az; m[7] = yz; m[8] = zz;
+}
+
+// cooperative tile copy global -> shared (n floats, base 16B-aligned when n_total is), vectorised where possible
+__device__ __forceinline__ void tile_load(float* dst, const float* src, int n, int tid, int nthreads) {
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int n4 = n >> 2;
+        for (int i = tid; i < n4; i += nthreads)
+            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+        for (int i = (n4 << 2) + tid; i < n; i += nthreads) dst[i] = src[i];
+    } else {
+        for (int i = tid; i < n; i += nthreads) dst[i] = src[i];
+    }
+}
+__device__ __forceinline__ void tile_store(float* dst, const float* src, int n, int tid, int nthreads) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const int n4 = n >> 2;
+        for (int i = tid; i < n4; i += nthreads)
+            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+        for (int i = (n4 << 2) + tid; i < n; i += nthreads) dst[i] = src[i];
+    } else {
+        for (int i = tid; i < n; i += nthreads) dst[i] = src[i];
+    }
+}
+
+constexpr int FPB = 64;     // frames per tile
+constexpr int DT = 128;     // threads per CTA
+
+// ------------------------------------------------------------------------------------------------
+// Upper decode: o [F,87] -> q [F,14,3,3], l [F,15,3]   (MLPHead tail Net/Upper_Net.py:355-364, ForKinematics :122-144,
+// Transform2R Utils.py:274-281)
+// ------------------------------------------------------------------------------------------------
+struct UpperDecodeSmem {
+    float in[FPB * 87];
+    float q[FPB * 126];
+    float l[FPB * 45];
+    float rt[FPB * 12];
+};
+
+__global__ void __launch_bounds__(DT) upper_decode_kernel(const float* __restrict__ o, const float* __restrict__ body,
+                                                          const float* __restrict__ R, const float* __restrict__ t,
+                                                          float* __restrict__ lout, float* __restrict__ qout,
+                                                          long long F, int L, int mode, long long row_offset,
+                                                          int B_global) {
+    MMEGO_DYN_SMEM(UpperDecodeSmem, sp);
+    UpperDecodeSmem& s = *sp;
+    const int tid = threadIdx.x;
+    const long long f0 = (long long)blockIdx.x * FPB;
+    const int nf = (int)((F - f0) < FPB ? (F - f0) : FPB);
+    tile_load(s.in, o + f0 * 87, nf * 87, tid, DT);
+    for (int i = tid; i < nf * 9; i += DT) s.rt[(i / 9) * 12 + i % 9] = R[f0 * 9 + i];
+    for (int i = tid; i < nf * 3; i += DT) s.rt[(i / 3) * 12 + 9 + i % 3] = t[f0 * 3 + i];
+    __syncthreads();
+    if (tid < nf) {
+        const long long r = row_offset + f0 + tid;
+        const long long bi = (mode == 0) ? (r % B_global) : (r / L);
+        const float* bd = body + bi * 60;
+        const float* in = s.in + tid * 87;
+        float* J = s.l + tid * 45;     // joints in the head frame; row stride 45 (odd) -> conflict-free
+        J[42] = in[84]; J[43] = in[85]; J[44] = in[86];
+        for (int i = 0; i < 14; ++i) {
+            const int ci = upper_idx(kSkelChild[i]), pi = upper_idx(kSkelParent[i]);
+            float m[9];
+            ortho6d(in + ci * 6, 1e-12f, m);
+            float* qd = s.q + tid * 126 + ci * 9;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) qd[k] = m[k];
+            const float bx = bd[i * 3], by = bd[i * 3 + 1], bz = bd[i * 3 + 2];
+            J[ci * 3] = J[pi * 3] + (m[0] * bx + m[1] * by + m[2] * bz);
+            J[ci * 3 + 1] = J[pi * 3 + 1] + (m[3] * bx + m[4] * by + m[5] * bz);
+            J[ci * 3 + 2] = J[pi * 3 + 2] + (m[6] * bx + m[7] * by + m[8] * bz);
+        }
+        const float* rt = s.rt + tid * 12;
+#pragma unroll
+        for (int j = 0; j < 15; ++j) {
+            float* ld = J + j * 3;
+            const float jx = ld[0], jy = ld[1], jz = ld[2];
+            ld[0] = rt[0] * jx + rt[3] * jy + rt[6] * jz + rt[9];
+            ld[1] = rt[1] * jx + rt[4] * jy + rt[7] * jz + rt[10];
+            ld[2] = rt[2] * jx + rt[5] * jy + rt[8] * jz + rt[11];
+        }
+    }
+    __syncthreads();
+    tile_store(lout + f0 * 45, s.l, nf * 45, tid, DT);
+    if (qout) tile_store(qout + f0 * 126, s.q, nf * 126, tid, DT);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lower decode: o [F,42] -> q [F,6,3,3], l [F,8,3]   (FusionModule tail Net/Lower_Net.py:126-135, ForKinematics :12-37)
+// ------------------------------------------------------------------------------------------------
+struct LowerDecodeSmem {
+    float in[FPB * 42];
+    float q[FPB * 54];
+    float l[FPB * 24];
+    float rt[FPB * 12];
+};
+
+__global__ void __launch_bounds__(DT) lower_decode_kernel(const float* __restrict__ o, const float* __restrict__ body,
+                                                          const float* __restrict__ R, const float* __restrict__ t,
+                                                          float* __restrict__ lout, float* __restrict__ qout,
+                                                          long long F, int L, int mode, long long row_offset,
+                                                          int B_global) {
+    MMEGO_DYN_SMEM(LowerDecodeSmem, sp);
+    LowerDecodeSmem& s = *sp;
+    const int tid = threadIdx.x;
+    const long long f0 = (long long)blockIdx.x * FPB;
+    const int nf = (int)((F - f0) < FPB ? (F - f0) : FPB);
+    tile_load(s.in, o + f0 * 42, nf * 42, tid, DT);
+    for (int i = tid; i < nf * 9; i += DT) s.rt[(i / 9) * 12 + i % 9] = R[f0 * 9 + i];
+    for (int i = tid; i < nf * 3; i += DT) s.rt[(i / 3) * 12 + 9 + i % 3] = t[f0 * 3 + i];
+    __syncthreads();
+    if (tid < nf) {
+        const long long r = row_offset + f0 + tid;
+        const long long bi = (mode == 0) ? (r % B_global) : (r / L);
+        const float* bd = body + bi * 60;
+        const float* in = s.in + tid * 42;
+        float* J = s.l + tid * 24;     // head-frame joints; 24-float rows: 2-way conflicts only, negligible here
+        J[0] = in[36]; J[1] = in[37]; J[2] = in[38];
+        J[12] = in[39]; J[13] = in[40]; J[14] = in[41];
+        for (int i = 0; i < 6; ++i) {
+            const int c = kSkelChild[14 + i], p = kSkelParent[14 + i];
+            const int ci = lower_idx(c), pi = lower_idx(p), qi = lower_rot_idx(c);
+            float m[9];
+            ortho6d(in + qi * 6, 1e-12f, m);
+            float* qd = s.q + tid * 54 + qi * 9;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) qd[k] = m[k];
+            const float bx = bd[(14 + i) * 3], by = bd[(14 + i) * 3 + 1], bz = bd[(14 + i) * 3 + 2];
+            J[ci * 3] = J[pi * 3] + (m[0] * bx + m[1] * by + m[2] * bz);
+            J[ci * 3 + 1] = J[pi * 3 + 1] + (m[3] * bx + m[4] * by + m[5] * bz);
+            J[ci * 3 + 2] = J[pi * 3 + 2] + (m[6] * bx + m[7] * by + m[8] * bz);
+        }
+        const float* rt = s.rt + tid * 12;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float* ld = J + j * 3;
+            const float jx = ld[0], jy = ld[1], jz = ld[2];
+            ld[0] = rt[0] * jx + rt[3] * jy + rt[6] * jz + rt[9];
+            ld[1] = rt[1] * jx + rt[4] * jy + rt[7] * jz + rt[10];
+            ld[2] = rt[2] * jx + rt[5] * jy + rt[8] * jz + rt[11];
+        }
+    }
+    __syncthreads();
+    tile_store(lout + f0 * 24, s.l, nf * 24, tid, DT);
+    if (qout) tile_store(qout + f0 * 54, s.q, nf * 54, tid, DT);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Assembly + metrics (Processor/Test/Demo_test.py:121-123, 64-69, 150-158)
+// ------------------------------------------------------------------------------------------------
+struct MetricsSmem {
+    float up[FPB * 45];
+    float lo[FPB * 24];
+    float tg[FPB * 63];
+    float pr[FPB * 63];
+    double acc[kSumsLen];
+};
+
+__global__ void __launch_bounds__(DT) assemble_metrics_kernel(const float* __restrict__ up, const float* __restrict__ lo,
+                                                              const float* __restrict__ tg, float* __restrict__ pred,
+                                                              double* __restrict__ sums, long long F) {
+    MMEGO_DYN_SMEM(MetricsSmem, sp);
+    MetricsSmem& s = *sp;
+    const int tid = threadIdx.x;
+    const long long f0 = (long long)blockIdx.x * FPB;
+    const int nf = (int)((F - f0) < FPB ? (F - f0) : FPB);
+    const bool do_metrics = tg != nullptr && sums != nullptr;
+    tile_load(s.up, up + f0 * 45, nf * 45, tid, DT);
+    tile_load(s.lo, lo + f0 * 24, nf * 24, tid, DT);
+    if (do_metrics) tile_load(s.tg, tg + f0 * 63, nf * 63, tid, DT);
+    if (tid < kSumsLen) s.acc[tid] = 0.0;
+    __syncthreads();
+    if (tid < nf) {
+        const float* u = s.up + tid * 45;
+        const float* l = s.lo + tid * 24;
+        float* p = s.pr + tid * 63;
+        // pred[:, :, upper_joint_map] = upper ; pred[:, :, lower_joint_map] = lower (lower wins on 12 and 16)
+#pragma unroll
+        for (int j = 0; j < 21; ++j) {
+            const float* src = (j >= 12 && j <= 19) ? (l + (j - 12) * 3) : (u + upper_idx(j) * 3);
+            p[j * 3] = src[0]; p[j * 3 + 1] = src[1]; p[j * 3 + 2] = src[2];
+        }
+    }
+    __syncthreads();
+    if (pred) tile_store(pred + f0 * 63, s.pr, nf * 63, tid, DT);
+    if (!do_metrics) return;
+    float vals[kSumsLen];
+#pragma unroll
+    for (int i = 0; i < kSumsLen; ++i) vals[i] = 0.f;
+    if (tid < nf) {
+        const float* p = s.pr + tid * 63;
+        const float* g = s.tg + tid * 63;
+        const float* u = s.up + tid * 45;
+        const float* l = s.lo + tid * 24;
+#pragma unroll
+        for (int j = 0; j < 21; ++j) {
+            const float dx = p[j * 3] - g[j * 3], dy = p[j * 3 + 1] - g[j * 3 + 1], dz = p[j * 3 + 2] - g[j * 3 + 2];
+            vals[j] = sqrtf(dx * dx + dy * dy + dz * dz);
+        }
+        float eu = 0.f, el = 0.f;
+#pragma unroll
+        for (int j = 0; j < 21; ++j) {
+            if (j <= 12 || j == 16 || j == 20) {
+                const int ui = upper_idx(j);
+                const float dx = u[ui * 3] - g[j * 3], dy = u[ui * 3 + 1] - g[j * 3 + 1], dz = u[ui * 3 + 2] - g[j * 3 + 2];
+                eu += sqrtf(dx * dx + dy * dy + dz * dz);
+            }
+            if (j >= 12 && j <= 19) {
+                const int li = j - 12;
+                const float dx = l[li * 3] - g[j * 3], dy = l[li * 3 + 1] - g[j * 3 + 1], dz = l[li * 3 + 2] - g[j * 3 + 2];
+                el += sqrtf(dx * dx + dy * dy + dz * dz);
+            }
+        }
+        vals[21] = eu;
+        vals[22] = el;
+#pragma unroll
+        for (int i = 0; i < 20; ++i) {
+            const int a = kSkelParent[i], b = kSkelChild[i];
+            const float px = p[b * 3] - p[a * 3], py = p[b * 3 + 1] - p[a * 3 + 1], pz = p[b * 3 + 2] - p[a * 3 + 2];
+            const float gx = g[b * 3] - g[a * 3], gy = g[b * 3 + 1] - g[a * 3 + 1], gz = g[b * 3 + 2] - g[a * 3 + 2];
+            // torch cosine_similarity: dot / max(|p| * |g|, eps) with eps = 1e-8
+            const float dot = px * gx + py * gy + pz * gz;
+            const float den = fmaxf(sqrtf((px * px + py * py + pz * pz) * (gx * gx + gy * gy + gz * gz)), 1e-8f);
+            float c = dot / den;
+            c = fminf(fmaxf(c, -1.0f), 1.0f);
+            vals[23 + i] = fabsf(acosf(c) / 3.14159265358f * 180.0f);
+        }
+        vals[43] = 1.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < kSumsLen; ++i) {
+        float v = vals[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0 && v != 0.f) atomicAdd(&s.acc[i], (double)v);
+    }
+    __syncthreads();
+    if (tid < kSumsLen && s.acc[tid] != 0.0) atomicAdd(&sums[tid], s.acc[tid]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// IMU_Net tail
+// ------------------------------------------------------------------------------------------------
+// attention pooling over the n samples of a frame (Net/IMU_Net.py:82-83): y [F,n,1024] -> s [F,1024]
+constexpr int PW = 256;
+__global__ void __launch_bounds__(PW) imu_pool_kernel(const float* __restrict__ y, const float* __restrict__ attn,
+                                                      float* __restrict__ out, long long F, int n) {
+    __shared__ float sc[64];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const long long f = blockIdx.x;
+    const float* yf = y + f * (long long)n * 1024;
+    float4 aw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) aw[i] = reinterpret_cast<const float4*>(attn)[i * 32 + lane];
+    const float ab = attn[1024];
+    for (int sidx = w; sidx < n; sidx += PW / 32) {
+        const float4* yp = reinterpret_cast<const float4*>(yf + (long long)sidx * 1024);
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = yp[i * 32 + lane];
+            a = fmaf(v.x, aw[i].x, a); a = fmaf(v.y, aw[i].y, a); a = fmaf(v.z, aw[i].z, a); a = fmaf(v.w, aw[i].w, a);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) sc[sidx] = a + ab;
+    }
+    __syncthreads();
+    float m = -INFINITY;
+    for (int i = 0; i < n; ++i) m = fmaxf(m, sc[i]);
+    float sum = 0.f;
+    for (int i = 0; i < n; ++i) sum += expf(sc[i] - m);
+    const float inv = 1.0f / sum;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < n; ++i) {
+        const float wgt = expf(sc[i] - m) * inv;
+        const float4 v = reinterpret_cast<const float4*>(yf + (long long)i * 1024)[tid];
+        acc.x = fmaf(wgt, v.x, acc.x); acc.y = fmaf(wgt, v.y, acc.y);
+        acc.z = fmaf(wgt, v.z, acc.z); acc.w = fmaf(wgt, v.w, acc.w);
+    }
+    reinterpret_cast<float4*>(out + f * 1024)[tid] = acc;
+}
+
+// fc2 + ortho6d (Net/IMU_Net.py:87-93, 7-47): g [F,1024] -> R [F,3,3], t [F,3]; one warp per frame
+__global__ void __launch_bounds__(256) imu_decode_kernel(const float* __restrict__ g, const float* __restrict__ fc2,
+                                                         float* __restrict__ R, float* __restrict__ t, long long F) {
+    const int lane = threadIdx.x & 31;
+    const long long f = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (f >= F) return;   // whole warp exits together; no block barrier below
+    float4 x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = reinterpret_cast<const float4*>(g + f * 1024)[i * 32 + lane];
+    float T9[9];
+#pragma unroll
+    for (int o = 0; o < 9; ++o) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 wv = reinterpret_cast<const float4*>(fc2 + o * 1024)[i * 32 + lane];
+            a = fmaf(wv.x, x[i].x, a); a = fmaf(wv.y, x[i].y, a); a = fmaf(wv.z, x[i].z, a); a = fmaf(wv.w, x[i].w, a);
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+        T9[o] = a + fc2[9 * 1024 + o];
+    }
+    if (lane == 0) {
+        float m[9];
+        ortho6d(T9, 1e-8f, m);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[f * 9 + k] = m[k];
+        t[f * 3] = T9[6]; t[f * 3 + 1] = T9[7]; t[f * 3 + 2] = T9[8];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rigid transforms (Utils.py:274-292) as standalone ops for the drop-in Util module
+// ------------------------------------------------------------------------------------------------
+__global__ void transform2h_kernel(float* __restrict__ pts, const float* __restrict__ R, const float* __restrict__ t,
+                                   long long total, int n, int D) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long f = i / n;
+    const float* r = R + f * 9;
+    const float* tt = t + f * 3;
+    float* p = pts + i * D;
+    const float dx = p[0] - tt[0], dy = p[1] - tt[1], dz = p[2] - tt[2];
+    p[0] = r[0] * dx + r[1] * dy + r[2] * dz;
+    p[1] = r[3] * dx + r[4] * dy + r[5] * dz;
+    p[2] = r[6] * dx + r[7] * dy + r[8] * dz;
+}
+__global__ void transform2r_kernel(const float* __restrict__ pts, const float* __restrict__ R,
+                                   const float* __restrict__ t, float* __restrict__ out, long long total, int n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long f = i / n;
+    const float* r = R + f * 9;
+    const float* tt = t + f * 3;
+    const float* p = pts + i * 3;
+    out[i * 3] = r[0] * p[0] + r[3] * p[1] + r[6] * p[2] + tt[0];
+    out[i * 3 + 1] = r[1] * p[0] + r[4] * p[1] + r[7] * p[2] + tt[1];
+    out[i * 3 + 2] = r[2] * p[0] + r[5] * p[1] + r[8] * p[2] + tt[2];
+}
+
+}  // namespace
+
+void launch_upper_decode(const float* o, const float* body, const float* R, const float* t, float* l, float* q,
+                         long long F, int L, int mode, long long row_offset, int B_global, cudaStream_t st) {
+    if (F <= 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(upper_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpperDecodeSmem));
+        attr_set = true;
+    }
+    MMEGO_LAUNCH(upper_decode_kernel, dim3((unsigned)((F + FPB - 1) / FPB)), dim3(DT), sizeof(UpperDecodeSmem), st, o,
+                 body, R, t, l, q, F, L, mode, row_offset, B_global);
+}
+void launch_lower_decode(const float* o, const float* body, const float* R, const float* t, float* l, float* q,
+                         long long F, int L, int mode, long long row_offset, int B_global, cudaStream_t st) {
+    if (F <= 0) return;
+    MMEGO_LAUNCH(lower_decode_kernel, dim3((unsigned)((F + FPB - 1) / FPB)), dim3(DT), sizeof(LowerDecodeSmem), st, o,
+                 body, R, t, l, q, F, L, mode, row_offset, B_global);
+}
+void launch_assemble_metrics(const float* up, const float* lo, const float* tg, float* pred, double* sums, long long F,
+                             cudaStream_t st) {
+    if (F <= 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(assemble_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MetricsSmem));
+        attr_set = true;
+    }
+    MMEGO_LAUNCH(assemble_metrics_kernel, dim3((unsigned)((F + FPB - 1) / FPB)), dim3(DT), sizeof(MetricsSmem), st, up,
+                 lo, tg, pred, sums, F);
+}
+void launch_imu_pool(const float* y, const float* attn, float* out, long long F, int n, cudaStream_t st) {
+    if (F <= 0) return;
+    MMEGO_LAUNCH(imu_pool_kernel, dim3((unsigned)F), dim3(PW), 0, st, y, attn, out, F, n);
+}
+void launch_imu_decode(const float* g, const float* fc2, float* R, float* t, long long F, cudaStream_t st) {
+    if (F <= 0) return;
+    MMEGO_LAUNCH(imu_decode_kernel, dim3((unsigned)((F + 7) / 8)), dim3(256), 0, st, g, fc2, R, t, F);
+}
+void launch_transform2h(float* pts, const float* R, const float* t, long long F, int n, int D, cudaStream_t st) {
+    const long long total = F * n;
+    if (total <= 0) return;
+    MMEGO_LAUNCH(transform2h_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, pts, R, t, total, n, D);
+}
+void launch_transform2r(const float* pts, const float* R, const float* t, float* out, long long F, int n,
+                        cudaStream_t st) {
+    const long long total = F * n;
+    if (total <= 0) return;
+    MMEGO_LAUNCH(transform2r_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, pts, R, t, out, total, n);
+}
+
+}  // namespace mmego

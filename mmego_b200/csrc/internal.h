@@ -1,0 +1,165 @@
+// internal.h -- shared declarations of libmmego_b200 (host side + kernel launchers).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "cuda_compat.h"
+
+namespace mmego {
+
+extern long long g_launches;   // kernels launched by this library (all handles)
+
+// ------------------------------------------------------------------------------------------------
+// model constants (Config/config.py:16-24 of the reference)
+// ------------------------------------------------------------------------------------------------
+constexpr int kJointsAll = 21, kJointsUpper = 15, kJointsLower = 8, kBones = 20;
+constexpr int kLowerPts = 64;        // Config.lower_pc_no
+constexpr int kImuFeat = 15, kImuH = 512;
+constexpr int kSmallH = 64;          // hidden size of grnn / rnn_pk
+constexpr int kGcnV = 15;
+
+// ------------------------------------------------------------------------------------------------
+// generic fused GEMM (gemm_ffma.cu):  C[M,N] = sum_seg A_seg[M,K_seg] * W[N, Kp]^T  (+ epilogue)
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxSeg = 10;
+struct GemmSeg {
+    const float* a;      // row-major activations
+    long long lda;       // row stride (floats)
+    int k;               // valid K of this segment
+    int kpad;            // K padded to a multiple of 16 (weight layout)
+    int shift;           // source row = row + shift (temporal taps of the ST-GCN)
+    int period;          // rows per snippet for the shift validity test (0 = no test)
+    int vec;             // 1 = float4 loads allowed (aligned base, lda%4==0, k%8==0)
+};
+enum GemmEpi { EPI_STORE = 0, EPI_LSTM = 1, EPI_F6 = 2 };
+struct GemmArgs {
+    GemmSeg seg[kMaxSeg];
+    int nseg;
+    const float* w;      // packed [N][ldw], ldw = sum kpad of ALL packed segments
+    int ldw;
+    int ktot;            // sum kpad of the segments used by this call (a prefix of the packed ones)
+    const float* bias;   // [N] or [rowmod][N]
+    float* c;
+    long long ldc;
+    int M, N;
+    int relu;
+    int rowmod;          // >0: bias row = row % rowmod
+    // EPI_LSTM
+    float* cstate;       // [M][ldcs], updated in place
+    long long ldcs;
+    int has_state;       // 0: c_prev = 0 (first step with zero init)
+    // EPI_F6: rows = b*period + pos; element (row, col) -> c[b*N*period + col*period + pos]
+    int f6_period;
+};
+struct GemmBatch {
+    GemmArgs g[2];
+};
+// bn: tile width (32, 64, 128); nz: 1 or 2 problems (blockIdx.z)
+void launch_gemm(const GemmBatch& b, int nz, int bn, int epi, cudaStream_t st);
+
+// other kernel launchers (one per .cu file)
+size_t upper_point_smem_bytes();
+void launch_upper_point(float* x, const float* R, const float* t, const float* wblob, float* g, float* gw, long long F,
+                        int N, int sm_count, cudaStream_t st);
+void launch_lstm_small(const float* gx, const float* whh, const float* h0, const float* c0, float* y, float* hn,
+                       float* cn, int S, int T, cudaStream_t st);
+size_t lower_frame_smem_bytes();
+int lower_frame_max_points();
+void launch_lower_frame(float* x, const float* R, const float* t, const float* kfeat, const float* wblob, float* ak,
+                        long long F, int N, int sm_count, cudaStream_t st);
+void launch_gcn_prep(const float* upper, const float* R, const float* t, const float* bn, float* uh, float* y0,
+                     long long F, cudaStream_t st);
+void launch_gcn_prep_raw(const float* x, const float* bn, float* y0, int B, int T, cudaStream_t st);
+void launch_gcn_agg(const float* y, const float* ahat, float* ya, long long F, int C, int sm_count, cudaStream_t st);
+void launch_upper_decode(const float* o, const float* body, const float* R, const float* t, float* l, float* q,
+                         long long F, int L, int mode, long long row_offset, int B_global, cudaStream_t st);
+void launch_lower_decode(const float* o, const float* body, const float* R, const float* t, float* l, float* q,
+                         long long F, int L, int mode, long long row_offset, int B_global, cudaStream_t st);
+void launch_assemble_metrics(const float* up, const float* lo, const float* tg, float* pred, double* sums, long long F,
+                             cudaStream_t st);
+void launch_imu_pool(const float* y, const float* attn, float* out, long long F, int n, cudaStream_t st);
+void launch_imu_decode(const float* g, const float* fc2, float* R, float* t, long long F, cudaStream_t st);
+void launch_transform2h(float* pts, const float* R, const float* t, long long F, int n, int D, cudaStream_t st);
+void launch_transform2r(const float* pts, const float* R, const float* t, float* out, long long F, int n,
+                        cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// packed weights
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    float* p = nullptr;
+    size_t n = 0;
+};
+struct PackedGemm {     // W [N][ldw] + bias
+    DevBuf w, bias;
+    int N = 0, ldw = 0, nseg = 0;
+    int k[kMaxSeg] = {0}, kpad[kMaxSeg] = {0};
+};
+struct PackedBigLstmLayer {   // one layer, both directions, H=512, gate-interleaved rows (tile of 32 units)
+    PackedGemm dir[2];
+};
+struct PackedSmallLstmLayer {  // H=64
+    PackedGemm ih;             // [512][In] both dirs, column order = recurrent-kernel thread order; bias = b_ih+b_hh
+    DevBuf whh;                // [2][256][64]  row = thread order
+    int in = 0;
+};
+struct ImuWeights {
+    bool ready = false;
+    PackedGemm fc1;
+    PackedBigLstmLayer fast[2], slow[2];
+    DevBuf attn;       // [1024] + [1] bias at the end
+    DevBuf fc2;        // [9][1024] + [9]
+};
+struct UpperWeights {
+    bool ready = false;
+    DevBuf point;      // folded per-point MLP blob (point_layout.h)
+    PackedSmallLstmLayer lstm[3];
+    PackedGemm fc1, fc2;
+};
+struct GcnLayerWeights {
+    DevBuf ahat;       // [2][15][15]
+    PackedGemm gconv;  // [C'][2C] (+ rowmod bias [15][C'])
+    PackedGemm tconv;  // [C'][9*C' + C]
+    int cin = 0, cout = 0;
+};
+struct LowerWeights {
+    bool ready = false;
+    DevBuf frame;      // folded per-point MLP + to_q/to_k/to_v blob (point_layout.h)
+    DevBuf data_bn;    // [45] scale, [45] offset
+    GcnLayerWeights gcn[3];
+    PackedGemm fcn;
+    PackedSmallLstmLayer lstm[3];
+    PackedGemm fc0, fc1, fc2;
+};
+
+// host-side packing (pack.cpp; pure C++, unit-tested on CPU)
+using HostSD = std::map<std::string, std::pair<const float*, long long>>;
+struct HostPackedGemm {
+    std::vector<float> w, bias;
+    int N = 0, ldw = 0, nseg = 0;
+    int k[kMaxSeg] = {0}, kpad[kMaxSeg] = {0};
+};
+inline int pad16(int k) { return (k + 15) / 16 * 16; }
+
+}  // namespace mmego
+
+struct mmego_handle {
+    int device = 0;
+    int sm_count = 148;
+    std::string err;
+    long long launches = 0;
+    long long imu_chunk = 512;
+    int imu_gemm = 0;
+    mmego::ImuWeights imu;
+    mmego::UpperWeights upper;
+    mmego::LowerWeights lower;
+    std::map<std::string, std::pair<void*, size_t>> taps;
+    std::vector<void*> owned;      // device allocations freed at destroy
+    // host-API staging
+    void* stage_dev = nullptr;
+    size_t stage_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+};

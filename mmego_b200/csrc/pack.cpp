@@ -1,0 +1,241 @@
+// pack.cpp -- host-side weight packing: BatchNorm folding, K-segment padding, LSTM gate interleaving.
+// Layout contracts are documented next to the kernels that consume them (gemm_ffma.cu, lstm_small.cu, point_layout.h).
+#include "pack.h"
+
+#include <cmath>
+#include <cstring>
+
+#include "point_layout.h"
+
+namespace mmego {
+
+BnAffine bn_affine(const StateDict& sd, const std::string& p, int C) {
+    const float* g = sd.get(p + ".weight", C);
+    const float* b = sd.get(p + ".bias", C);
+    const float* m = sd.get(p + ".running_mean", C);
+    const float* v = sd.get(p + ".running_var", C);
+    BnAffine r;
+    r.s.resize(C);
+    r.o.resize(C);
+    for (int c = 0; c < C; ++c) {
+        r.s[c] = g[c] / std::sqrt(v[c] + 1e-5f);
+        r.o[c] = b[c] - m[c] * r.s[c];
+    }
+    return r;
+}
+
+HostPackedGemm pack_linear(const float* W, const float* b, int N, const std::vector<int>& ksegs, const float* row_scale,
+                           const float* row_offset) {
+    HostPackedGemm g;
+    g.N = N;
+    g.nseg = (int)ksegs.size();
+    int ktot = 0, kp = 0;
+    for (int s = 0; s < g.nseg; ++s) {
+        g.k[s] = ksegs[s];
+        g.kpad[s] = pad16(ksegs[s]);
+        ktot += ksegs[s];
+        kp += g.kpad[s];
+    }
+    g.ldw = kp;
+    g.w.assign((size_t)N * kp, 0.f);
+    g.bias.assign(N, 0.f);
+    for (int n = 0; n < N; ++n) {
+        const float sc = row_scale ? row_scale[n] : 1.f;
+        int src = 0, dst = 0;
+        for (int s = 0; s < g.nseg; ++s) {
+            for (int k = 0; k < g.k[s]; ++k) g.w[(size_t)n * kp + dst + k] = sc * W[(size_t)n * ktot + src + k];
+            src += g.k[s];
+            dst += g.kpad[s];
+        }
+        g.bias[n] = sc * (b ? b[n] : 0.f) + (row_offset ? row_offset[n] : 0.f);
+    }
+    return g;
+}
+
+// H=512 LSTM layer, one GEMM per direction: rows gate-interleaved per tile of 32 hidden units
+//   packed row p = tile*128 + gate*32 + e   <->   torch row gate*H + tile*32 + e      (gates i,f,g,o)
+// K segments: [input (In) | recurrent (H)].
+HostBigLstm pack_big_lstm(const StateDict& sd, const std::string& prefix, int layer, int In, int H) {
+    HostBigLstm out;
+    const char* sfx[2] = {"", "_reverse"};
+    for (int d = 0; d < 2; ++d) {
+        const std::string k = "l" + std::to_string(layer) + sfx[d];
+        const float* wih = sd.get(prefix + "weight_ih_" + k, (long long)4 * H * In);
+        const float* whh = sd.get(prefix + "weight_hh_" + k, (long long)4 * H * H);
+        const float* bih = sd.get(prefix + "bias_ih_" + k, 4 * H);
+        const float* bhh = sd.get(prefix + "bias_hh_" + k, 4 * H);
+        HostPackedGemm& g = out.dir[d];
+        g.N = 4 * H;
+        g.nseg = 2;
+        g.k[0] = In; g.kpad[0] = pad16(In);
+        g.k[1] = H;  g.kpad[1] = pad16(H);
+        g.ldw = g.kpad[0] + g.kpad[1];
+        g.w.assign((size_t)g.N * g.ldw, 0.f);
+        g.bias.assign(g.N, 0.f);
+        const int TU = 32;
+        for (int p = 0; p < 4 * H; ++p) {
+            const int tile = p / (4 * TU), gate = (p % (4 * TU)) / TU, e = p % TU;
+            const int r = gate * H + tile * TU + e;
+            std::memcpy(&g.w[(size_t)p * g.ldw], wih + (size_t)r * In, sizeof(float) * In);
+            std::memcpy(&g.w[(size_t)p * g.ldw + g.kpad[0]], whh + (size_t)r * H, sizeof(float) * H);
+            g.bias[p] = bih[r] + bhh[r];
+        }
+    }
+    return out;
+}
+
+// H=64 LSTM layer: recurrent-kernel thread order tid = w*32 + gate*8 + e  <->  torch row gate*64 + w*8 + e
+HostSmallLstm pack_small_lstm(const StateDict& sd, const std::string& prefix, int layer, int In) {
+    const int H = kSmallH;
+    HostSmallLstm out;
+    out.in = In;
+    HostPackedGemm& g = out.ih;
+    g.N = 2 * 4 * H;
+    g.nseg = 1;
+    g.k[0] = In; g.kpad[0] = pad16(In);
+    g.ldw = g.kpad[0];
+    g.w.assign((size_t)g.N * g.ldw, 0.f);
+    g.bias.assign(g.N, 0.f);
+    out.whh.assign((size_t)2 * 4 * H * H, 0.f);
+    const char* sfx[2] = {"", "_reverse"};
+    for (int d = 0; d < 2; ++d) {
+        const std::string k = "l" + std::to_string(layer) + sfx[d];
+        const float* wih = sd.get(prefix + "weight_ih_" + k, (long long)4 * H * In);
+        const float* whh = sd.get(prefix + "weight_hh_" + k, (long long)4 * H * H);
+        const float* bih = sd.get(prefix + "bias_ih_" + k, 4 * H);
+        const float* bhh = sd.get(prefix + "bias_hh_" + k, 4 * H);
+        for (int tid = 0; tid < 4 * H; ++tid) {
+            const int w = tid / 32, gate = (tid % 32) / 8, e = tid % 8;
+            const int r = gate * H + w * 8 + e;
+            const int n = d * 4 * H + tid;
+            std::memcpy(&g.w[(size_t)n * g.ldw], wih + (size_t)r * In, sizeof(float) * In);
+            g.bias[n] = bih[r] + bhh[r];
+            std::memcpy(&out.whh[((size_t)d * 4 * H + tid) * H], whh + (size_t)r * H, sizeof(float) * H);
+        }
+    }
+    return out;
+}
+
+namespace {
+// conv1d(k=1) [Cout][Cin][1] + BN folded into W[rows][CinPad] + b[rows]
+void fold_conv_bn(const StateDict& sd, const std::string& conv, const std::string& bn, int Cin, int Cout, float* W,
+                  float* b, int cin_pad) {
+    const float* w = sd.get(conv + ".weight", (long long)Cout * Cin);
+    const float* bb = sd.get(conv + ".bias", Cout);
+    BnAffine a = bn_affine(sd, bn, Cout);
+    for (int o = 0; o < Cout; ++o) {
+        for (int c = 0; c < Cin; ++c) W[o * cin_pad + c] = a.s[o] * w[o * Cin + c];
+        b[o] = a.s[o] * bb[o] + a.o[o];
+    }
+}
+}  // namespace
+
+std::vector<float> pack_upper_point(const StateDict& sd) {
+    using UL = UpperPointLayout;
+    std::vector<float> v(UL::TOTAL, 0.f);
+    fold_conv_bn(sd, "module0.conv1", "module0.cb1", 6, 8, &v[UL::W1], &v[UL::B1], pad4(6));
+    fold_conv_bn(sd, "module0.conv2", "module0.cb2", 8, 16, &v[UL::W2], &v[UL::B2], pad4(8));
+    fold_conv_bn(sd, "module0.conv3", "module0.cb3", 16, 24, &v[UL::W3], &v[UL::B3], pad4(16));
+    fold_conv_bn(sd, "module1.gpointnet.conv1", "module1.gpointnet.cb1", 28, 32, &v[UL::W4], &v[UL::B4], pad4(28));
+    fold_conv_bn(sd, "module1.gpointnet.conv2", "module1.gpointnet.cb2", 32, 48, &v[UL::W5], &v[UL::B5], pad4(32));
+    fold_conv_bn(sd, "module1.gpointnet.conv3", "module1.gpointnet.cb3", 48, 64, &v[UL::W6], &v[UL::B6], pad4(48));
+    std::memcpy(&v[UL::WA], sd.get("module1.gpointnet.attn.weight", 64), sizeof(float) * 64);
+    v[UL::BA] = sd.get("module1.gpointnet.attn.bias", 1)[0];
+    return v;
+}
+
+std::vector<float> pack_lower_frame(const StateDict& sd) {
+    using LL = LowerFrameLayout;
+    std::vector<float> v(LL::TOTAL, 0.f);
+    const std::string p = "pointEncoder.module0.";
+    fold_conv_bn(sd, p + "conv1", p + "cb1", 6, 16, &v[LL::W1], &v[LL::B1], pad4(6));
+    fold_conv_bn(sd, p + "conv2", p + "cb2", 16, 32, &v[LL::W2], &v[LL::B2], pad4(16));
+    fold_conv_bn(sd, p + "conv3", p + "cb3", 32, 61, &v[LL::W3], &v[LL::B3], pad4(32));
+    const float* wq = sd.get("fusion.to_q.weight", 64 * 64);
+    std::memcpy(&v[LL::WQ], wq, sizeof(float) * 64 * 64);
+    std::memcpy(&v[LL::BQ], sd.get("fusion.to_q.bias", 64), sizeof(float) * 64);
+    const float* wk = sd.get("fusion.to_k.weight", 64 * 64);
+    const float* wv = sd.get("fusion.to_v.weight", 64 * 64);
+    for (int o = 0; o < 64; ++o)
+        for (int c = 0; c < 64; ++c) {   // transposed [c][o] for conflict-free per-output-channel reads
+            v[LL::WK + c * 64 + o] = wk[o * 64 + c];
+            v[LL::WV + c * 64 + o] = wv[o * 64 + c];
+        }
+    std::memcpy(&v[LL::BK], sd.get("fusion.to_k.bias", 64), sizeof(float) * 64);
+    std::memcpy(&v[LL::BV], sd.get("fusion.to_v.bias", 64), sizeof(float) * 64);
+    return v;
+}
+
+std::vector<float> pack_data_bn(const StateDict& sd, const std::string& gp) {
+    BnAffine a = bn_affine(sd, gp + "data_bn", 45);
+    std::vector<float> v(90);
+    for (int i = 0; i < 45; ++i) { v[i] = a.s[i]; v[45 + i] = a.o[i]; }
+    return v;
+}
+
+// One st_gcn block (Net/GCN.py:67-147) as two GEMMs on channel-last rows (f*15 + joint):
+//   gconv: U = relu( [Y Ahat_0 | Y Ahat_1] Wg^T + bias_w )                 K = 2*Cin, bias depends on the joint w
+//          Wg[c'][k*Cin + c] = s_a[c'] conv.weight[k*C' + c'][c]
+//          bias_w[w][c'] = s_a[c'] sum_k conv.bias[k*C'+c'] colsum_k[w] + o_a[c'],  colsum_k[w] = sum_v Ahat_k[v][w]
+//   tconv: Y' = relu( sum_tau U(l+tau-4) Wt_tau^T + Y Wr^T + bias )         K = 9*C' + Cin
+//          Wt_tau[c'][c] = s_b[c'] tcn.2.weight[c'][c][tau];  Wr = s_r residual.0.weight
+//          bias = s_b tcn.2.bias + o_b + s_r residual.0.bias + o_r
+HostGcnLayer pack_gcn_layer(const StateDict& sd, const std::string& gp, int layer, int Cin, int Cout) {
+    HostGcnLayer L;
+    L.cin = Cin;
+    L.cout = Cout;
+    const int V = kGcnV;
+    const float* A = sd.get(gp + "A", 2 * V * V);
+    const float* imp = sd.get(gp + "edge_importance." + std::to_string(layer), 2 * V * V);
+    L.ahat.resize(2 * V * V);
+    for (int i = 0; i < 2 * V * V; ++i) L.ahat[i] = A[i] * imp[i];
+    const std::string g = gp + "gcn_networks." + std::to_string(layer) + ".";
+    const float* cw = sd.get(g + "gcn.conv.weight", (long long)2 * Cout * Cin);
+    const float* cb = sd.get(g + "gcn.conv.bias", 2 * Cout);
+    BnAffine a = bn_affine(sd, g + "tcn.0", Cout);
+    // gconv
+    HostPackedGemm& gc = L.gconv;
+    gc.N = Cout;
+    gc.nseg = 1;
+    gc.k[0] = 2 * Cin; gc.kpad[0] = pad16(2 * Cin);
+    gc.ldw = gc.kpad[0];
+    gc.w.assign((size_t)Cout * gc.ldw, 0.f);
+    gc.bias.assign((size_t)V * Cout, 0.f);
+    for (int o = 0; o < Cout; ++o)
+        for (int k = 0; k < 2; ++k)
+            for (int c = 0; c < Cin; ++c)
+                gc.w[(size_t)o * gc.ldw + k * Cin + c] = a.s[o] * cw[(size_t)(k * Cout + o) * Cin + c];
+    for (int w = 0; w < V; ++w) {
+        float cs[2] = {0.f, 0.f};
+        for (int k = 0; k < 2; ++k)
+            for (int v = 0; v < V; ++v) cs[k] += L.ahat[k * V * V + v * V + w];
+        for (int o = 0; o < Cout; ++o)
+            gc.bias[(size_t)w * Cout + o] = a.s[o] * (cb[o] * cs[0] + cb[Cout + o] * cs[1]) + a.o[o];
+    }
+    // tconv
+    const float* tw = sd.get(g + "tcn.2.weight", (long long)Cout * Cout * 9);
+    const float* tb = sd.get(g + "tcn.2.bias", Cout);
+    BnAffine b = bn_affine(sd, g + "tcn.3", Cout);
+    const float* rw = sd.get(g + "residual.0.weight", (long long)Cout * Cin);
+    const float* rb = sd.get(g + "residual.0.bias", Cout);
+    BnAffine r = bn_affine(sd, g + "residual.1", Cout);
+    HostPackedGemm& tc = L.tconv;
+    tc.N = Cout;
+    tc.nseg = 10;
+    int kp = 0;
+    for (int s = 0; s < 9; ++s) { tc.k[s] = Cout; tc.kpad[s] = pad16(Cout); kp += tc.kpad[s]; }
+    tc.k[9] = Cin; tc.kpad[9] = pad16(Cin); kp += tc.kpad[9];
+    tc.ldw = kp;
+    tc.w.assign((size_t)Cout * kp, 0.f);
+    tc.bias.assign(Cout, 0.f);
+    for (int o = 0; o < Cout; ++o) {
+        for (int tau = 0; tau < 9; ++tau)
+            for (int c = 0; c < Cout; ++c)
+                tc.w[(size_t)o * kp + tau * tc.kpad[0] + c] = b.s[o] * tw[((size_t)o * Cout + c) * 9 + tau];
+        for (int c = 0; c < Cin; ++c) tc.w[(size_t)o * kp + 9 * tc.kpad[0] + c] = r.s[o] * rw[(size_t)o * Cin + c];
+        tc.bias[o] = b.s[o] * tb[o] + b.o[o] + r.s[o] * rb[o] + r.o[o];
+    }
+    return L;
+}
+
+}  // namespace mmego

@@ -1,0 +1,55 @@
+// pack.h -- host-side weight packing (pure C++; unit-tested on CPU through the mmego_pack_* test hooks).
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+namespace mmego {
+
+struct StateDict {
+    HostSD m;
+    const float* get(const std::string& name, long long numel) const {
+        auto it = m.find(name);
+        if (it == m.end()) throw std::runtime_error("missing state_dict tensor: " + name);
+        if (it->second.second != numel)
+            throw std::runtime_error("state_dict tensor " + name + " has " + std::to_string(it->second.second) +
+                                     " elements, expected " + std::to_string(numel));
+        return it->second.first;
+    }
+};
+
+struct BnAffine {
+    std::vector<float> s, o;
+};
+BnAffine bn_affine(const StateDict& sd, const std::string& prefix, int C);
+
+// W [N][sum(ksegs)] row-major -> segments padded to 16; optional per-row scale and bias transform
+HostPackedGemm pack_linear(const float* W, const float* b, int N, const std::vector<int>& ksegs,
+                           const float* row_scale = nullptr, const float* row_offset = nullptr);
+
+struct HostBigLstm {
+    HostPackedGemm dir[2];
+};
+HostBigLstm pack_big_lstm(const StateDict& sd, const std::string& prefix, int layer, int In, int H);
+
+struct HostSmallLstm {
+    HostPackedGemm ih;
+    std::vector<float> whh;
+    int in = 0;
+};
+HostSmallLstm pack_small_lstm(const StateDict& sd, const std::string& prefix, int layer, int In);
+
+std::vector<float> pack_upper_point(const StateDict& sd);
+std::vector<float> pack_lower_frame(const StateDict& sd);
+
+struct HostGcnLayer {
+    std::vector<float> ahat;
+    HostPackedGemm gconv, tconv;
+    int cin = 0, cout = 0;
+};
+HostGcnLayer pack_gcn_layer(const StateDict& sd, const std::string& gcn_prefix, int layer, int Cin, int Cout);
+std::vector<float> pack_data_bn(const StateDict& sd, const std::string& gcn_prefix);
+
+}  // namespace mmego
