@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- mmEgo inference frames/s on B200 (BASELINE.json metric) with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+N>1 is launched by torchrun (one rank per GPU, NCCL): snippets are independent, so every rank runs the whole pipeline
+on its own `--batch` snippets (weak scaling) and the only communication is the all-gather of predictions and the
+all-reduce of the error sums, inside the timed region.
+
+A step = one pass of the full pipeline (IMU_Net -> Upper_Net -> Lower_Net -> 21-joint assembly + error sums) over the
+batch, through the C ABI (`mmego_pipeline_forward`).  `value` times it with inputs resident in HBM; `e2e` times
+`mmego_infer_host` with pinned HOST buffers (H2D of the inputs and D2H of predictions + sums inside the timed region).
+Inputs per step are 350 MB at B=4096 -- larger than the 126 MB L2 -- so consecutive steps do not hit in L2.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mmEgo inference frames/s (IMU_Net+Upper_Net+Lower_Net/GCN+decode, fp32 parity mode)"
+UNIT = "frames/s"
+L, N_PTS, N_IMU = 20, 128, 20
+H = 512
+# algorithmic FLOPs (2*MAC) per frame, SURVEY.md section 8(d)
+FLOPS_PER_FRAME = dict(imu=444_962_816, upper=2_150_922, lower=9_267_786)
+FLOPS_PER_FRAME["total"] = sum(FLOPS_PER_FRAME.values())
+
+
+def lstm_step_flops(seqs: int, in_features: int) -> float:
+    """One timestep launch (both directions) of an H=512 LSTM layer: 2 dirs * 2 * M * 4H * (In + H)."""
+    return 2 * 2.0 * seqs * 4 * H * (in_features + H)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_pass(snippets: int, steps: int, warmup: int):
+    """The reference's algorithm on the host cores: the oracle port (oracle/mmego_oracle.py; the reference is pure
+    PyTorch-on-CPU and its repository does not travel to the GPU box), all threads, fp32."""
+    import torch
+    from oracle import mmego_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sb = O.synth_batch(snippets, seed=1234)
+    up = torch.load(os.path.join(ROOT, "Resource/Pretrained_model/Upper_Net/epoch451_batch20frame20lr3e-05.pth"),
+                    map_location="cpu", weights_only=True)
+    lo = torch.load(os.path.join(ROOT, "Resource/Pretrained_model/Lower_Net/epoch161_batch20frame20lr0.0003.pth"),
+                    map_location="cpu", weights_only=True)
+    imu_sd = O.synth_imu_state_dict(0)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.pipeline(imu_sd, up, lo, sb["imu"], sb["data"], sb["skl"])
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return snippets * L / dt, dt, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    snippets = args.cpu_snippets
+    fps, dt, cores = cpu_reference_pass(snippets, max(1, min(args.steps, 3)), 1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"full pipeline, B={args.batch}, L={L}, N={N_PTS}, n_imu={N_IMU} (config 3 of BASELINE.json)",
+                   "note": "each step is a bounded sample of that workload"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{snippets} snippets ({snippets * L} frames) of the same synthetic workload per step, "
+                                   "oracle port of the reference's PyTorch-CPU path, fp32, torch threads = all cores"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4096, help="snippets per GPU (config 3: 4096)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-snippets", type=int, default=256, help="snippets per CPU-baseline pass (bounded sample)")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from mmego_b200 import _capi, synth
+    from mmego_b200.pipeline import SUMS_LEN, MMEgoPipeline, ShardedRunner, report_from_sums
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    Bg = B * world                                   # weak scaling: every rank owns B snippets
+    pipe = MMEgoPipeline(dev, imu_state=None)
+    # this rank's shard of the global synthetic batch (seed depends on the rank; same distribution)
+    sb = synth.batch(B, L=L, N=N_PTS, n_imu=N_IMU, seed=1234 + rank)
+    imu_h, data_h, skl_h = sb["imu"].pin_memory(), sb["data"].pin_memory(), sb["skl"].pin_memory()
+    imu_d, data0_d, skl_d = imu_h.to(dev), data_h.to(dev), skl_h.to(dev)
+    data_d = torch.empty_like(data0_d)
+    sums_d = torch.zeros(SUMS_LEN, dtype=torch.float64, device=dev)
+    # synthetic ground truth: first prediction + 3 cm noise
+    data_d.copy_(data0_d)
+    pred0 = pipe.forward(imu_d, data_d, skl_d)
+    target_h = synth.target_like(pred0, seed=99 + rank).contiguous().pin_memory()
+    target_d = target_h.to(dev)
+    torch.cuda.synchronize()
+
+    def step_fn(lo, hi, Bglobal):
+        # the in-place Transform2H mutates the cloud: every step starts from a fresh copy of the resident input
+        data_d.copy_(data0_d)
+        sums_d.zero_()
+        pred = pipe.forward(imu_d, data_d, skl_d, target_d, sums_d)
+        return pred, sums_d
+
+    runner = ShardedRunner(lambda lo, hi, Bglobal: step_fn(lo, hi, Bglobal), world, rank)
+
+    def one_step():
+        # every rank holds exactly its own B snippets, so the shard bounds are (rank*B, (rank+1)*B)
+        return runner.run(Bg)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        pred, sums = one_step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    pipe.handle.profile_begin()
+    n0 = pipe.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        pred, sums = one_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = pipe.launch_count() - n0
+    prof = pipe.handle.profile_read()
+    pipe.handle.profile_end()
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    ms_per_step = ms / args.steps
+    frames = Bg * L
+    value = frames / (ms_per_step * 1e-3)
+    rep = report_from_sums(sums.cpu().numpy())
+
+    # ---- end to end through the host-buffer entry point (H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            pipe.infer_host(imu_h, data_h, skl_h, target_h)
+        barrier()
+        t0 = time.perf_counter()
+        k2 = max(2, min(args.steps, 5))
+        for _ in range(k2):
+            pred_h, sums_h = pipe.infer_host(imu_h, data_h, skl_h, target_h)
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / k2], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = sum(t.numel() * t.element_size() for t in (imu_h, data_h, skl_h, target_h))
+        d2h = pred_h.numel() * 4 + SUMS_LEN * 8
+        e2e = {"value": frames / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "ms_per_step": float(dt.item()) * 1e3, "steps": k2,
+               "api": "mmego_infer_host (pinned host buffers)"}
+
+    if rank == 0:
+        peaks = measured_peaks()
+        # dominant kernel: the H=512 LSTM timestep launch (recurrent GEMM + fused cell), 160 launches per chunk
+        steps_fast = 2 * N_IMU                      # per chunk: 2 layers x n_imu steps with M = chunk*L sequences
+        steps_slow = 2 * L                          # 2 layers x L steps with M = chunk sequences
+        chunk = min(B, 512)
+        nchunks = (B + chunk - 1) // chunk
+        fl = 0.0
+        for c in range(nchunks):
+            bc = min(chunk, B - c * chunk)
+            fl += N_IMU * (lstm_step_flops(bc * L, H) + lstm_step_flops(bc * L, 2 * H))
+            fl += L * 2 * lstm_step_flops(bc, 2 * H)
+        lst = prof.get("imu.lstm_step", dict(ms=0.0, launches=0))
+        per_launch_flops = fl * args.steps / max(1, lst["launches"])
+        per_launch_ms = lst["ms"] / max(1, lst["launches"])
+        ach = per_launch_flops / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
+        peak = peaks["bf16_sustained"]
+        roofline = {"bound": "tensor", "kernel": "gemm_ffma_kernel<128,EPI_LSTM> (H=512 LSTM timestep: [x_t|h_{t-1}] GEMM + fused cell)",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peaks["source"] + ", sustained dense bf16 (kernel timed inside a long step)",
+                    "avg_launch_ms": per_launch_ms, "launches": lst["launches"],
+                    "flops_per_launch": per_launch_flops,
+                    "share_of_step": lst["ms"] / ms if ms > 0 else None}
+        stage_ms = {k: round(v["ms"] / args.steps, 3) for k, v in prof.items()}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"full pipeline, B={B} snippets per GPU, L={L}, N={N_PTS}, n_imu={N_IMU} "
+                                   "(config 3 of BASELINE.json); IMU_Net weights: " + pipe.imu_weights,
+                       "global_batch": Bg, "frames_per_step": frames, "parallelism": f"dp{world}",
+                       "l2": "inputs per step (350 MB per GPU) exceed the 126 MB L2; no explicit flush"},
+            "clocks": clocks, "gpu_launches": launches,
+            "algorithmic_tflops": FLOPS_PER_FRAME["total"] * frames / (ms_per_step * 1e-3) / 1e12,
+            "stage_ms_per_step": stage_ms,
+            "mpjpe_vs_synthetic_target_cm": rep["mpjpe_cm"],
+            "roofline": roofline,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline and world == 1:
+            fps, dt_cpu, cores = cpu_reference_pass(args.cpu_snippets, 2, 1)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_snippets} snippets ({args.cpu_snippets * L} frames) of the same "
+                                              "synthetic workload, 1 warm-up + 2 timed passes of the oracle port "
+                                              "(PyTorch CPU fp32, all host threads)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

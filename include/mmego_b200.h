@@ -42,8 +42,9 @@ enum { MMEGO_BODY_REF = 0, MMEGO_BODY_PER_SNIPPET = 1 };
 
 /* Layout of the `sums` accumulator filled by mmego_assemble_metrics (all float64, ADDED to, never cleared):
  * [0..20] per-joint sum of ||pred-gt||, [21] upper-body sum (15 joints, UpperNet's own hips),
- * [22] lower-body sum (8 joints), [23..42] per-bone angle sum in degrees, [43] frame count. */
-#define MMEGO_SUMS_LEN 44
+ * [22] lower-body sum (8 joints), [23..42] per-bone angle sum in degrees, [43] frame count,
+ * [44] L1 sum |lower_l - gt| and [45] L1 sum over the 6 lower bone vectors (eval_loss / eval_loss_l, Demo_test.py:141-147). */
+#define MMEGO_SUMS_LEN 46
 
 typedef struct mmego_handle mmego_handle;
 
@@ -123,6 +124,16 @@ int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_h
 int mmego_debug_tap(mmego_handle* h, const char* name, void* dst, size_t bytes);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 long long mmego_launch_count(const mmego_handle* h);
+
+
+/* Measurement hooks (bench.py): between profile_begin and profile_end every named group of launches is bracketed by
+ * CUDA events on the launching stream.  profile_read synchronises on the recorded events and returns the summed
+ * duration, the number of kernel launches and the number of spans of `name`
+ * ("imu.fc1", "imu.lstm_step", "imu.pool", "imu.decode", "upper.point", "small_lstm", "upper.head_decode",
+ *  "lower.gcn", "lower.frame", "lower.head_decode", "assemble_metrics"). */
+int mmego_profile_begin(mmego_handle* h);
+int mmego_profile_read(mmego_handle* h, const char* name, double* total_ms, long long* launches, long long* spans);
+int mmego_profile_end(mmego_handle* h);
 
 #ifdef __cplusplus
 }

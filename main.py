@@ -1,0 +1,48 @@
+"""`python main.py --infer` -- same command line as the reference's main.py:5-73 for the inference path.
+Training (`--train_*`) and visualisation (`--vis`) are outside this repository's scope and say so."""
+import argparse
+import sys
+
+
+def main():
+    p = argparse.ArgumentParser(description="mmEgo inference on B200")
+    p.add_argument("--infer", action="store_true", help="evaluate on Resource/Sample_data (frozen tensors)")
+    p.add_argument("--vis", action="store_true", help="(reference flag) visualisation -- not implemented here")
+    p.add_argument("--train_IMU", action="store_true", help="(reference flag) not implemented here")
+    p.add_argument("--train_Upper", action="store_true", help="(reference flag) not implemented here")
+    p.add_argument("--train_Lower", action="store_true", help="(reference flag) not implemented here")
+    p.add_argument("--epochs", type=int)
+    p.add_argument("--lr", type=float)
+    p.add_argument("--device", type=str, help="cuda device, e.g. cuda:0")
+    p.add_argument("--batch_size", type=int, help="snippets per batch (the reference's eval loop hard-codes 1)")
+    p.add_argument("--log_dir", type=str)
+    p.add_argument("--load_IMU_path", type=str)
+    p.add_argument("--load_Upper_path", type=str)
+    p.add_argument("--load_Lower_path", type=str)
+    p.add_argument("--colab", action="store_true")
+    p.add_argument("--imu_surrogate", action="store_true",
+                   help="feed IMU_Net's training targets as (R, t) (needed while the IMU checkpoint is missing)")
+    a = p.parse_args()
+
+    from mmego_b200.Config.config import Config
+    if a.device:
+        Config.device = a.device
+    if a.batch_size:
+        Config.batch_size = a.batch_size
+    if a.load_IMU_path:
+        Config.model_IMU_path = a.load_IMU_path
+    if a.load_Upper_path:
+        Config.model_upper_path = a.load_Upper_path
+    if a.load_Lower_path:
+        Config.model_lower_path = a.load_Lower_path
+    if a.train_IMU or a.train_Upper or a.train_Lower or a.vis:
+        sys.exit("only --infer is implemented: training and visualisation are out of scope for the B200 inference path")
+    if not a.infer:
+        p.print_help()
+        return
+    from mmego_b200.Processor.Test.Demo_test import MMEgo
+    MMEgo(imu_surrogate=True if a.imu_surrogate else None).eval_model()
+
+
+if __name__ == "__main__":
+    main()

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libmmego_b200.so")
 NET_IMU, NET_UPPER, NET_LOWER = 0, 1, 2
 STAGE_IMU, STAGE_UPPER, STAGE_LOWER, STAGE_GCN, STAGE_PIPELINE = 0, 1, 2, 3, 4
 BODY_REF, BODY_PER_SNIPPET = 0, 1
-SUMS_LEN = 44
+SUMS_LEN = 46
 
 _vp, _i, _ll, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t
 
@@ -42,7 +42,13 @@ SIGNATURES = {
     "mmego_infer_host": (_i, [_vp] + [_vp] * 6 + [_i] * 7),
     "mmego_debug_tap": (_i, [_vp, C.c_char_p, _vp, _sz]),
     "mmego_launch_count": (_ll, [_vp]),
+    "mmego_profile_begin": (_i, [_vp]),
+    "mmego_profile_read": (_i, [_vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(_ll), C.POINTER(_ll)]),
+    "mmego_profile_end": (_i, [_vp]),
 }
+
+PROFILE_SPANS = ("imu.fc1", "imu.lstm_step", "imu.pool", "imu.decode", "upper.point", "small_lstm", "upper.head_decode",
+                 "lower.gcn", "lower.frame", "lower.head_decode", "assemble_metrics")
 
 
 class MMEgoError(RuntimeError):
@@ -163,6 +169,22 @@ class Handle:
 
     def launch_count(self) -> int:
         return int(self.lib.dll.mmego_launch_count(self._h))
+
+    def profile_begin(self):
+        self._ck(self.lib.dll.mmego_profile_begin(self._h), "profile_begin")
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        out = {}
+        for name in PROFILE_SPANS:
+            ms, n, k = C.c_double(), _ll(), _ll()
+            self._ck(self.lib.dll.mmego_profile_read(self._h, name.encode(), C.byref(ms), C.byref(n), C.byref(k)),
+                     "profile_read")
+            if k.value:
+                out[name] = dict(ms=ms.value, launches=int(n.value), spans=int(k.value))
+        return out
+
+    def profile_end(self):
+        self._ck(self.lib.dll.mmego_profile_end(self._h), "profile_end")
 
     def tap(self, name: str, dst: torch.Tensor):
         self._keep.append(dst)

@@ -125,6 +125,29 @@ void tap(mmego_handle* h, const char* name, const void* src, size_t bytes, cudaS
     h->taps.erase(it);
 }
 
+// CUDA-event span around a group of launches on the launching stream (enabled by mmego_profile_begin)
+struct Prof {
+    mmego_handle* h;
+    cudaStream_t st;
+    size_t idx = (size_t)-1;
+    long long l0 = 0;
+    Prof(mmego_handle* h_, const char* name, cudaStream_t st_) : h(h_), st(st_) {
+        if (!h->prof_on) return;
+        ProfSpan sp;
+        sp.name = name;
+        if (cudaEventCreate(&sp.e0) != cudaSuccess || cudaEventCreate(&sp.e1) != cudaSuccess) return;
+        cudaEventRecord(sp.e0, st);
+        l0 = g_launches;
+        h->prof.push_back(sp);
+        idx = h->prof.size() - 1;
+    }
+    ~Prof() {
+        if (idx == (size_t)-1) return;
+        cudaEventRecord(h->prof[idx].e1, st);
+        h->prof[idx].launches = g_launches - l0;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------- H=64 bi-LSTM stack
 struct SmallLstmWs {
     float* gx;       // [S*T, 512]
@@ -141,6 +164,7 @@ const float* run_small_lstm(mmego_handle* h, const PackedSmallLstmLayer* layers,
                             const SmallLstmWs& w, cudaStream_t st) {
     const float* cur = in;
     long long ld = in_ld;
+    Prof prof(h, "small_lstm", st);
     for (int l = 0; l < 3; ++l) {
         linear(h, layers[l].ih, cur, ld, w.gx, 512, S * T, 0, st);
         const size_t so = (size_t)l * 2 * S * kSmallH;
@@ -173,6 +197,7 @@ void plan_imu(Carver& c, long long Bc, int L, int n, ImuWs& w) {
 void run_big_lstm_layer(mmego_handle* h, const PackedBigLstmLayer& lw, const float* x, int In, float* y, float* cst,
                         long long S, int T, cudaStream_t st) {
     const int H = kImuH;
+    Prof prof(h, "imu.lstm_step", st);
     for (int step = 0; step < T; ++step) {
         GemmBatch b{};
         for (int d = 0; d < 2; ++d) {
@@ -196,17 +221,26 @@ int imu_chunk_forward(mmego_handle* h, const float* imu, float* R, float* t, lon
                       const ImuWs& w, cudaStream_t st) {
     const long long S = Bc * L;
     const ImuWeights& W = h->imu;
-    linear(h, W.fc1, imu, kImuFeat, w.u, kImuH, S * n, 1, st);                          // Net/IMU_Net.py:79
+    {
+        Prof p(h, "imu.fc1", st);
+        linear(h, W.fc1, imu, kImuFeat, w.u, kImuH, S * n, 1, st);                      // Net/IMU_Net.py:79
+    }
     tap(h, "imu.u", w.u, (size_t)S * n * kImuH * 4, st);
     run_big_lstm_layer(h, W.fast[0], w.u, kImuH, w.y0, w.cst, S, n, st);                 // :80
     run_big_lstm_layer(h, W.fast[1], w.y0, 2 * kImuH, w.y1, w.cst, S, n, st);
     tap(h, "imu.f", w.y1, (size_t)S * n * 2 * kImuH * 4, st);
-    launch_imu_pool(w.y1, W.attn.p, w.s, S, n, st);                                      // :82-83
+    {
+        Prof p(h, "imu.pool", st);
+        launch_imu_pool(w.y1, W.attn.p, w.s, S, n, st);                                  // :82-83
+    }
     tap(h, "imu.s", w.s, (size_t)S * 2 * kImuH * 4, st);
     run_big_lstm_layer(h, W.slow[0], w.s, 2 * kImuH, w.z0, w.cst, Bc, L, st);            // :85
     run_big_lstm_layer(h, W.slow[1], w.z0, 2 * kImuH, w.z1, w.cst, Bc, L, st);
     tap(h, "imu.g", w.z1, (size_t)S * 2 * kImuH * 4, st);
-    launch_imu_decode(w.z1, W.fc2.p, R, t, S, st);                                       // :87-93
+    {
+        Prof p(h, "imu.decode", st);
+        launch_imu_decode(w.z1, W.fc2.p, R, t, S, st);                                   // :87-93
+    }
     return MMEGO_OK;
 }
 
@@ -489,10 +523,14 @@ int mmego_upper_forward(mmego_handle* h, float* x, const float* h0, const float*
     UpperWs w;
     plan_upper(c, B, L, w);
     const UpperWeights& W = h->upper;
-    launch_upper_point(x, R, t, W.point.p, w.g, global_w, F, N, h->sm_count, st);       // Upper_Net.py:379-381 (+gpointnet)
+    {
+        Prof p(h, "upper.point", st);
+        launch_upper_point(x, R, t, W.point.p, w.g, global_w, F, N, h->sm_count, st);   // Upper_Net.py:379-381 (+gpointnet)
+    }
     tap(h, "upper.g", w.g, (size_t)F * 64 * 4, st);
     const float* hs = run_small_lstm(h, W.lstm, w.g, 64, h0, c0, hn, cn, B, L, w.lstm, st);   // :339
     tap(h, "upper.lstm", hs, (size_t)F * 128 * 4, st);
+    Prof p(h, "upper.head_decode", st);
     linear(h, W.fc1, hs, 128, w.h1, 128, F, 1, st);                                     // :351-353
     linear(h, W.fc2, w.h1, 128, w.o, 87, F, 0, st);
     tap(h, "upper.o", w.o, (size_t)F * 87 * 4, st);
@@ -524,12 +562,19 @@ int mmego_lower_forward(mmego_handle* h, const float* upper_l, float* x, const f
     float* y0 = w.y[1];   // layer 0 writes y[0], so y[1] is free to hold the 3-channel input
     launch_gcn_prep(upper_l, R, t, W.data_bn.p, w.uh, y0, F, st);                         // Lower_Net.py:229, GCN.py:339-344
     tap(h, "lower.uh", w.uh, (size_t)F * 45 * 4, st);
-    run_gcn(h, y0, B, L, w, st);
+    {
+        Prof p(h, "lower.gcn", st);
+        run_gcn(h, y0, B, L, w, st);
+    }
     tap(h, "lower.K", w.kf, (size_t)F * kGcnV * 64 * 4, st);
-    launch_lower_frame(x, R, t, w.kf, W.frame.p, w.ak, F, N, h->sm_count, st);           // :191-192, 216-227, 231, 104-116
+    {
+        Prof p(h, "lower.frame", st);
+        launch_lower_frame(x, R, t, w.kf, W.frame.p, w.ak, F, N, h->sm_count, st);       // :191-192, 216-227, 231, 104-116
+    }
     tap(h, "lower.ak", w.ak, (size_t)F * 192 * 4, st);
     const float* hs = run_small_lstm(h, W.lstm, w.ak, 192, nullptr, nullptr, nullptr, nullptr, B, L, w.lstm, st);   // :117
     tap(h, "lower.lstm", hs, (size_t)F * 128 * 4, st);
+    Prof p(h, "lower.head_decode", st);
     {
         GemmArgs a = gemm_begin(W.fc0, w.f0, 128, F, 1);                                  // :119-121
         gemm_seg(a, W.fc0, hs, 128);
@@ -589,6 +634,7 @@ int mmego_assemble_metrics(mmego_handle* h, const float* upper_l, const float* l
                            float* pred, double* sums, int B, int L, void* stream) {
     if (int rc = check_dims(h, B, L, 1)) return rc;
     if (!upper_l || !lower_l) return fail(h, MMEGO_EINVAL, "assemble_metrics: NULL argument");
+    Prof p(h, "assemble_metrics", static_cast<cudaStream_t>(stream));
     launch_assemble_metrics(upper_l, lower_l, target, pred, sums, (long long)B * L, static_cast<cudaStream_t>(stream));
     CUDA_TRY(h, cudaGetLastError());
     h->launches = g_launches;
@@ -686,5 +732,42 @@ int mmego_debug_tap(mmego_handle* h, const char* name, void* dst, size_t bytes) 
 }
 
 long long mmego_launch_count(const mmego_handle* h) { return h ? g_launches : 0; }
+
+int mmego_profile_begin(mmego_handle* h) {
+    if (!h) return MMEGO_EINVAL;
+    for (ProfSpan& sp : h->prof) {
+        if (sp.e0) cudaEventDestroy(sp.e0);
+        if (sp.e1) cudaEventDestroy(sp.e1);
+    }
+    h->prof.clear();
+    h->prof_on = true;
+    return MMEGO_OK;
+}
+
+int mmego_profile_read(mmego_handle* h, const char* name, double* total_ms, long long* launches, long long* spans) {
+    if (!h || !name) return MMEGO_EINVAL;
+    double ms = 0.0;
+    long long n = 0, k = 0;
+    for (ProfSpan& sp : h->prof) {
+        if (sp.name != name || !sp.e1) continue;
+        CUDA_TRY(h, cudaEventSynchronize(sp.e1));
+        float v = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&v, sp.e0, sp.e1));
+        ms += v;
+        n += sp.launches;
+        ++k;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = n;
+    if (spans) *spans = k;
+    return MMEGO_OK;
+}
+
+int mmego_profile_end(mmego_handle* h) {
+    if (!h) return MMEGO_EINVAL;
+    mmego_profile_begin(h);
+    h->prof_on = false;
+    return MMEGO_OK;
+}
 
 }  // extern "C"

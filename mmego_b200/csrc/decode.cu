@@ -11,7 +11,7 @@ namespace {
 __constant__ int kSkelParent[20] = {20, 3, 2, 2, 2, 4, 5, 6, 8, 9, 10, 1, 0, 0, 12, 13, 14, 16, 17, 18};
 __constant__ int kSkelChild[20] = {3, 2, 1, 4, 8, 5, 6, 7, 9, 10, 11, 0, 12, 16, 13, 14, 15, 17, 18, 19};
 
-constexpr int kSumsLen = 44;   // == MMEGO_SUMS_LEN of the public header
+constexpr int kSumsLen = 46;   // == MMEGO_SUMS_LEN of the public header
 
 // upper-local index of a 21-joint id: upper_joint_map = [0..12, 16, 20]
 __host__ __device__ constexpr int upper_idx(int j) { return j <= 12 ? j : (j == 16 ? 13 : 14); }
@@ -260,6 +260,19 @@ __global__ void __launch_bounds__(DT) assemble_metrics_kernel(const float* __res
             vals[23 + i] = fabsf(acosf(c) / 3.14159265358f * 180.0f);
         }
         vals[43] = 1.0f;
+        // L1 sums of the reference's eval_loss / eval_loss_l (Demo_test.py:141-147): lower joints and lower bone vectors
+        float l1 = 0.f, l1b = 0.f;
+#pragma unroll
+        for (int k = 0; k < 24; ++k) l1 += fabsf(l[k] - g[36 + k]);
+#pragma unroll
+        for (int i = 14; i < 20; ++i) {
+            const int a = kSkelParent[i] - 12, b = kSkelChild[i] - 12;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                l1b += fabsf((l[b * 3 + c] - l[a * 3 + c]) - (g[36 + b * 3 + c] - g[36 + a * 3 + c]));
+        }
+        vals[44] = l1;
+        vals[45] = l1b;
     }
 #pragma unroll
     for (int i = 0; i < kSumsLen; ++i) {
@@ -380,10 +393,9 @@ __global__ void transform2r_kernel(const float* __restrict__ pts, const float* _
 void launch_upper_decode(const float* o, const float* body, const float* R, const float* t, float* l, float* q,
                          long long F, int L, int mode, long long row_offset, int B_global, cudaStream_t st) {
     if (F <= 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};
+    if (first_use_on_device(attr_set)) {
         cudaFuncSetAttribute(upper_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpperDecodeSmem));
-        attr_set = true;
     }
     MMEGO_LAUNCH(upper_decode_kernel, dim3((unsigned)((F + FPB - 1) / FPB)), dim3(DT), sizeof(UpperDecodeSmem), st, o,
                  body, R, t, l, q, F, L, mode, row_offset, B_global);
@@ -397,10 +409,9 @@ void launch_lower_decode(const float* o, const float* body, const float* R, cons
 void launch_assemble_metrics(const float* up, const float* lo, const float* tg, float* pred, double* sums, long long F,
                              cudaStream_t st) {
     if (F <= 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};
+    if (first_use_on_device(attr_set)) {
         cudaFuncSetAttribute(assemble_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MetricsSmem));
-        attr_set = true;
     }
     MMEGO_LAUNCH(assemble_metrics_kernel, dim3((unsigned)((F + FPB - 1) / FPB)), dim3(DT), sizeof(MetricsSmem), st, up,
                  lo, tg, pred, sums, F);

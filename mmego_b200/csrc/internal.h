@@ -60,6 +60,15 @@ struct GemmBatch {
 // bn: tile width (32, 64, 128); nz: 1 or 2 problems (blockIdx.z)
 void launch_gemm(const GemmBatch& b, int nz, int bn, int epi, cudaStream_t st);
 
+// per-device one-shot flag (kernel attributes such as the dynamic shared memory limit are per device)
+inline bool first_use_on_device(bool* flags) {
+    int d = 0;
+    cudaGetDevice(&d);
+    if (flags[d & 63]) return false;
+    flags[d & 63] = true;
+    return true;
+}
+
 // other kernel launchers (one per .cu file)
 size_t upper_point_smem_bytes();
 void launch_upper_point(float* x, const float* R, const float* t, const float* wblob, float* g, float* gw, long long F,
@@ -146,7 +155,15 @@ inline int pad16(int k) { return (k + 15) / 16 * 16; }
 
 }  // namespace mmego
 
+struct ProfSpan {
+    std::string name;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    long long launches = 0;
+};
+
 struct mmego_handle {
+    bool prof_on = false;
+    std::vector<ProfSpan> prof;
     int device = 0;
     int sm_count = 148;
     std::string err;

@@ -218,10 +218,9 @@ int lower_frame_max_points() { return NMAX; }
 void launch_lower_frame(float* x, const float* R, const float* t, const float* kfeat, const float* wblob, float* ak,
                         long long F, int N, int sm_count, cudaStream_t st) {
     if (F <= 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};
+    if (first_use_on_device(attr_set)) {
         cudaFuncSetAttribute(lower_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        attr_set = true;
     }
     long long grid = F < (long long)sm_count * 2 ? F : (long long)sm_count * 2;
     MMEGO_LAUNCH(lower_frame_kernel, dim3((unsigned)grid), dim3(NT), sizeof(Smem), st, x, R, t, kfeat, wblob, ak, F, N);

@@ -149,11 +149,10 @@ size_t upper_point_smem_bytes() { return (size_t)(UL::TOTAL + 64 * RED_LD + 128 
 void launch_upper_point(float* x, const float* R, const float* t, const float* wblob, float* g, float* gw,
                         long long F, int N, int sm_count, cudaStream_t st) {
     if (F <= 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};
+    if (first_use_on_device(attr_set)) {
         cudaFuncSetAttribute(upper_point_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)upper_point_smem_bytes());
-        attr_set = true;
     }
     long long grid = F < (long long)sm_count * 3 ? F : (long long)sm_count * 3;
     MMEGO_LAUNCH(upper_point_kernel, dim3((unsigned)grid), dim3(PT), upper_point_smem_bytes(), st, x, R, t, wblob, g,

@@ -1,0 +1,69 @@
+"""Per-device library handles and the nn.Module base shared by the drop-in networks."""
+from __future__ import annotations
+
+import time
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import _capi
+from ._capi import MMEgoError
+
+_HANDLES: Dict[int, "_capi.Handle"] = {}
+
+
+def get_handle(device) -> "_capi.Handle":
+    """One mmego_handle per GPU, created on first use.  Raises when CUDA or the library is unavailable."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise MMEgoError(f"mmego_b200 runs on CUDA devices only (got '{device}'); there is no CPU fallback")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    h = _HANDLES.get(idx)
+    if h is None:
+        h = _capi.Handle(torch.device("cuda", idx))
+        _HANDLES[idx] = h
+    return h
+
+
+class NativeNet(nn.Module):
+    """Parameters live in ordinary nn.Parameters/buffers (checkpoint-compatible); compute lives in the library.
+    The packed device copies owned by the handle are refreshed whenever the module's tensors change."""
+
+    _net_id: int = -1
+
+    def __init__(self):
+        super().__init__()
+        self._packed_key = None
+        self._packed_handle = None
+
+    def _weights_key(self):
+        return tuple((id(t), t._version, t.data_ptr()) for t in self.state_dict(keep_vars=True).values())
+
+    def _sync(self, device) -> "_capi.Handle":
+        h = get_handle(device)
+        key = self._weights_key()
+        if self._packed_handle is not h or key != self._packed_key:
+            h.set_weights(self._net_id, self.state_dict())
+            self._packed_key, self._packed_handle = key, h
+        return h
+
+    @staticmethod
+    def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+        if not torch.is_tensor(t):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if not t.is_cuda:
+            raise MMEgoError(f"{name} is on '{t.device}': mmego_b200 has no CPU path, move the batch to the B200")
+        if t.dtype != torch.float32:
+            raise MMEgoError(f"{name} must be float32 (got {t.dtype})")
+        return t
+
+    # -- same persistence surface as the reference classes (Net/IMU_Net.py:96-114 etc.)
+    def save(self, name=None):
+        if name is None:
+            name = time.strftime("checkpoints/" + "%m%d_%H_%M_%S.pth")
+        torch.save(self.state_dict(), name)
+        return name
+
+    def load(self, pathname):
+        self.load_state_dict(torch.load(pathname, map_location="cpu", weights_only=True))

@@ -1,0 +1,120 @@
+"""The chained inference pass of Processor/Test/Demo_test.py:106-123 as one object: IMUNet -> UpperNet -> LowerNet ->
+21-joint assembly (+ error sums), for device-resident batches (`forward`) and for host batches (`infer_host`).
+Multi-GPU: one process per GPU, snippets sharded contiguously on dim 0, predictions all-gathered and error sums
+all-reduced (`ShardedRunner`)."""
+from __future__ import annotations
+
+import os
+from typing import Dict, Mapping, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _capi, synth
+from .Config.config import Config
+from .Net.IMU_Net import IMUNet
+from .Net.Lower_Net import LowerNet
+from .Net.Upper_Net import UpperNet
+from .engine import MMEgoError
+
+SUMS_LEN = _capi.SUMS_LEN
+
+
+def load_checkpoint(path: str) -> Dict[str, torch.Tensor]:
+    return torch.load(path, map_location="cpu", weights_only=True)
+
+
+def report_from_sums(sums) -> Dict[str, object]:
+    """The five printed quantities of Demo_test.py:176-180 from the device-accumulated sums (layout: mmego_b200.h)."""
+    s = np.asarray(sums, dtype=np.float64)
+    F_ = s[43]
+    return dict(frames=int(F_),
+                mpjpe_cm=float(s[0:21].sum() / (F_ * 21) * 100.0),
+                upper_cm=float(s[21] / (F_ * 15) * 100.0),
+                lower_cm=float(s[22] / (F_ * 8) * 100.0),
+                angle_deg=float((s[23:43] / F_).mean()),
+                per_joint_cm=s[0:21] / F_ * 100.0,
+                angle_bone_deg=s[23:43] / F_,
+                eval_loss=float(s[44] / F_),
+                eval_loss_l=np.asarray([s[44] / F_ / 8.0, s[45] / F_]))
+
+
+class MMEgoPipeline:
+    def __init__(self, device="cuda", imu_state: Optional[Mapping[str, torch.Tensor]] = None,
+                 upper_state: Optional[Mapping[str, torch.Tensor]] = None,
+                 lower_state: Optional[Mapping[str, torch.Tensor]] = None, body_index_mode: str = "ref"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise MMEgoError("MMEgoPipeline needs a CUDA device; there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.imu_net = IMUNet(15, 9, 512, 2, True, 0.1)
+        self.upper_net = UpperNet()
+        self.lower_net = LowerNet(64)
+        self.imu_weights = "checkpoint"
+        if imu_state is None:
+            if os.path.exists(Config.model_IMU_path):
+                imu_state = load_checkpoint(Config.model_IMU_path)
+            else:
+                imu_state = synth.imu_state_dict(0)        # the blob is missing from the reference mount
+                self.imu_weights = "seeded-random(0)"
+        self.imu_net.load_state_dict(imu_state)
+        self.upper_net.load_state_dict(upper_state if upper_state is not None else load_checkpoint(Config.model_upper_path))
+        self.lower_net.load_state_dict(lower_state if lower_state is not None else load_checkpoint(Config.model_lower_path))
+        for m in (self.imu_net, self.upper_net, self.lower_net):
+            m.to(self.device).eval()
+        self.body_mode = _capi.BODY_REF if body_index_mode == "ref" else _capi.BODY_PER_SNIPPET
+        self.handle = None
+        self._sync()
+
+    def _sync(self):
+        for m in (self.imu_net, self.upper_net, self.lower_net):
+            self.handle = m._sync(self.device)
+
+    def launch_count(self) -> int:
+        return self.handle.launch_count()
+
+    def forward(self, imu, data, skl, target=None, sums=None, b_offset: int = 0, B_global: Optional[int] = None,
+                outs: Optional[Dict[str, torch.Tensor]] = None, want_pred: bool = True):
+        """Device tensors in, pred [B,L,21,3] out.  `data` is transformed in place twice, as the reference does.
+        When `target` and `sums` (float64[SUMS_LEN], device) are given the batch's error sums are ADDED to `sums`."""
+        self._sync()
+        return self.handle.pipeline_forward(imu, data, skl, target, sums, self.body_mode, b_offset, B_global, outs,
+                                            want_pred)
+
+    def infer_host(self, imu, data, skl, target=None, b_offset: int = 0, B_global: Optional[int] = None):
+        """Host tensors in, (pred, sums) host tensors out; copies are part of the call."""
+        self._sync()
+        return self.handle.infer_host(imu, data, skl, target, self.body_mode, b_offset, B_global)
+
+
+def shard_bounds(B: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous split of the snippet dimension; the first B % world ranks take one extra snippet."""
+    base, rem = divmod(B, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ShardedRunner:
+    """Data-parallel wrapper: each rank runs `step_fn` on its contiguous shard; predictions are all-gathered and the
+    float64 error sums all-reduced.  Snippets are independent, so this is the only communication of the path."""
+
+    def __init__(self, step_fn, world: int, rank: int, group=None):
+        self.step_fn, self.world, self.rank, self.group = step_fn, world, rank, group
+
+    def run(self, B: int, *step_args):
+        import torch.distributed as dist
+        lo, hi = shard_bounds(B, self.world, self.rank)
+        pred, sums = self.step_fn(lo, hi, B, *step_args)      # pred [hi-lo, L, 21, 3], sums float64[SUMS_LEN]
+        if self.world == 1:
+            return pred, sums
+        sizes = [shard_bounds(B, self.world, r) for r in range(self.world)]
+        rows = max(h - l for l, h in sizes)                    # uneven shards: pad to the largest, trim after
+        mine = pred.contiguous()
+        if mine.shape[0] < rows:
+            mine = torch.cat((mine, mine.new_zeros((rows - mine.shape[0],) + tuple(mine.shape[1:]))), dim=0)
+        gathered = torch.empty((self.world * rows,) + tuple(pred.shape[1:]), dtype=pred.dtype, device=pred.device)
+        dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+        parts = [gathered[r * rows:r * rows + (h - l)] for r, (l, h) in enumerate(sizes)]
+        return torch.cat(parts, dim=0), sums

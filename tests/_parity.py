@@ -1,0 +1,172 @@
+"""Parity checks shared by the emulator suite (CPU, `not gpu`) and the B200 suite (`-m gpu`).  Each check drives the
+library through its C ABI (mmego_b200._capi.Handle) and compares with the oracle / the reference-generated goldens.
+
+Tolerances (fp32 mode): BASELINE.json asks for joint positions within 1e-3 cm = 1e-5 m and angles within 1e-3 deg.
+The oracle and the library are two fp32 evaluation orders of the same math (noise floor ~4e-7 m)."""
+import os
+
+import numpy as np
+import torch
+
+from mmego_b200 import _capi
+from oracle import mmego_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+POS_TOL = 1e-5          # metres  (= 1e-3 cm)
+ROT_TOL = 2e-5          # rotation-matrix entries (1e-3 deg = 1.7e-5 rad)
+
+
+def golden(name):
+    return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, name)).items()}
+
+
+def checkpoints():
+    base = os.path.join(ROOT, "Resource", "Pretrained_model")
+    up = torch.load(os.path.join(base, "Upper_Net", "epoch451_batch20frame20lr3e-05.pth"), map_location="cpu", weights_only=True)
+    lo = torch.load(os.path.join(base, "Lower_Net", "epoch161_batch20frame20lr0.0003.pth"), map_location="cpu", weights_only=True)
+    return up, lo
+
+
+def maxerr(a, b):
+    return float((torch.as_tensor(a).detach().cpu().double() - torch.as_tensor(b).detach().cpu().double()).abs().max())
+
+
+def make_handle(lib=None, require_cuda=True, imu_seed=0, with_imu=True):
+    h = _capi.Handle(lib=lib, require_cuda=require_cuda)
+    up, lo = checkpoints()
+    h.set_weights(_capi.NET_UPPER, up)
+    h.set_weights(_capi.NET_LOWER, lo)
+    if with_imu:
+        h.set_weights(_capi.NET_IMU, O.synth_imu_state_dict(imu_seed))
+    return h
+
+
+def dev(h, t):
+    return t.to(h.device).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------- checks
+def check_upper_lower_golden(h, name, sl=None):
+    """Upper_Net and Lower_Net against the vectors produced by the REFERENCE's own classes."""
+    g = golden(name)
+    B = g["data"].shape[0]
+    one_call = name == "synth3.npz"
+    chunks = [slice(0, B)] if one_call else ([slice(i, i + 1) for i in range(B)] if sl is None else sl)
+    up_sd, lo_sd = checkpoints()
+    for s in chunks:
+        b = g["data"][s].shape[0]
+        x = dev(h, g["data"][s].clone())
+        h0 = torch.zeros(6, b, 64, device=h.device)
+        skl, R, t = dev(h, g["skl"][s]), dev(h, g["R"][s]), dev(h, g["t"][s])
+        l, q, gw, hn, cn = h.upper_forward(x, h0, h0.clone(), skl, R, t)
+        assert maxerr(l, g["upper_l"][s]) < POS_TOL
+        assert maxerr(q, g["q_upper"][s]) < ROT_TOL
+        assert maxerr(gw.reshape(b, 20, -1), g["gw"][s]) < 1e-5
+        assert maxerr(hn.permute(1, 0, 2), g["hn"][s]) < 2e-5
+        assert maxerr(cn.permute(1, 0, 2), g["cn"][s]) < 5e-5
+        assert maxerr(x, g["x1"][s]) < 2e-6                      # the in-place Transform2H side effect (F5)
+        assert torch.equal(x[..., 3:].cpu(), g["data"][s][..., 3:])
+        # lower stage fed with the reference's own upper_l and once-transformed cloud
+        x = dev(h, g["x1"][s].clone())
+        ul = dev(h, g["upper_l"][s])
+        ul_before = ul.clone()
+        ll, ql = h.lower_forward(ul, x, skl, R, t)
+        assert torch.equal(ul, ul_before)                        # upper_l is not modified
+        assert maxerr(x, g["x2"][s]) < 5e-6                      # second in-place transform
+        # ties in the top-64 key exist in the real data (distinct points, identical xyz): the reference's unstable
+        # sort picks arbitrarily; the library's rule (lowest slot wins) is checked exactly against the oracle
+        lo_o, ql_o, _ = O.lower_forward(lo_sd, g["upper_l"][s], g["x1"][s], g["skl"][s], g["R"][s], g["t"][s])
+        assert maxerr(ll, lo_o) < POS_TOL
+        assert maxerr(ql, ql_o) < ROT_TOL * 2
+        assert maxerr(ll, g["lower_l"][s]) < (POS_TOL if one_call else 5e-3)
+        pred = h.assemble_metrics(l, ll)
+        assert maxerr(pred, O.assemble(l.cpu(), ll.cpu())) == 0.0
+
+
+def check_gcn_golden(h):
+    g = golden("gcn2.npz")
+    out = h.gcn_extract_feature(dev(h, g["x"]))
+    assert out.shape == g["out"].shape
+    assert maxerr(out, g["out"]) < 2e-5 * float(g["out"].abs().max())
+
+
+def check_imu_golden(h, tag="synth", nb=1):
+    g = golden("imu_seed0.npz")
+    R, t = h.imu_forward(dev(h, g["imu_" + tag][:nb]))
+    assert maxerr(R, g["R_" + tag][:nb]) < ROT_TOL
+    assert maxerr(t, g["t_" + tag][:nb]) < POS_TOL
+
+
+def check_transforms(h, F=37, n=15):
+    gen = torch.Generator().manual_seed(1)
+    sb = O.synth_batch(2, L=F // 2 + 1, seed=3)
+    R = sb["R"].reshape(-1, 3, 3)[:F].contiguous()
+    t = sb["t"].reshape(-1, 3)[:F].contiguous()
+    p = torch.randn(F, n, 6, generator=gen)
+    want = p.clone()
+    want[:, :, :3] = O.transform2h(p[:, :, :3], R, t)
+    got = h.transform2h_(dev(h, p.clone()), dev(h, R), dev(h, t))
+    assert maxerr(got, want) < 2e-6
+    p3 = torch.randn(F, n, 3, generator=gen)
+    assert maxerr(h.transform2r(dev(h, p3), dev(h, R), dev(h, t)), O.transform2r(p3, R, t)) < 2e-6
+
+
+def check_metrics(h):
+    g = golden("sample16.npz")
+    sums = torch.zeros(_capi.SUMS_LEN, dtype=torch.float64, device=h.device)
+    pred = h.assemble_metrics(dev(h, g["upper_l"]), dev(h, g["lower_l"]), dev(h, g["target"]), sums)
+    assert maxerr(pred, g["pred"]) == 0.0
+    s = O.metric_sums(g["pred"], g["upper_l"], g["lower_l"], g["target"])
+    got = sums.cpu().numpy().copy()
+    assert got[43] == 16 * 20
+    assert np.allclose(got[0:21], s["err_joint"], rtol=1e-6)
+    assert abs(got[21] - s["err_upper"]) < 1e-6 * s["err_upper"]
+    assert abs(got[22] - s["err_lower"]) < 1e-6 * s["err_lower"]
+    # acos amplifies fp32 noise near 0 deg; the SUM over 320 frames is compared at 1e-3 deg per frame on average
+    assert np.abs(got[23:43] - s["angle_bone"]).max() / 320 < 1e-3
+    lower_t = g["target"][:, :, O.LOWER_JOINT_MAP]
+    assert abs(got[44] - float((g["lower_l"] - lower_t).abs().double().sum())) < 1e-4
+    # accumulation: a second call adds
+    h.assemble_metrics(dev(h, g["upper_l"]), dev(h, g["lower_l"]), dev(h, g["target"]), sums, want_pred=False)
+    assert np.allclose(sums.cpu().numpy(), 2 * got, rtol=1e-12)
+
+
+def check_pipeline_vs_oracle(h, B=2, L=20, N=128, n_imu=20, seed=11, distinct=True, imu_seed=0):
+    """Whole chain on synthetic snippets vs the oracle pipeline (IMU_Net with the seeded stand-in weights)."""
+    sb = O.synth_batch(B, L=L, N=N, n_imu=n_imu, seed=seed, distinct_skeletons=distinct)
+    up_sd, lo_sd = checkpoints()
+    ref = O.pipeline(O.synth_imu_state_dict(imu_seed), up_sd, lo_sd, sb["imu"], sb["data"], sb["skl"])
+    x = dev(h, sb["data"].clone())
+    outs = dict(R=torch.empty(B, L, 3, 3, device=h.device), t=torch.empty(B, L, 3, device=h.device),
+                upper_l=torch.empty(B, L, 15, 3, device=h.device), lower_l=torch.empty(B, L, 8, 3, device=h.device))
+    tg = dev(h, ref["pred"] + 0.03)
+    sums = torch.zeros(_capi.SUMS_LEN, dtype=torch.float64, device=h.device)
+    pred = h.pipeline_forward(dev(h, sb["imu"]), x, dev(h, sb["skl"]), tg, sums, outs=outs)
+    assert maxerr(outs["R"], ref["R"]) < ROT_TOL
+    assert maxerr(outs["t"], ref["t"]) < POS_TOL
+    assert maxerr(outs["upper_l"], ref["upper_l"]) < POS_TOL
+    assert maxerr(x, ref["x_after_lower"]) < 1e-5
+    assert maxerr(outs["lower_l"], ref["lower_l"]) < POS_TOL
+    assert maxerr(pred, ref["pred"]) < POS_TOL
+    assert sums.cpu().numpy()[43] == B * L
+    return pred
+
+
+def check_errors(h):
+    """Error behaviour of the boundary: bad shapes / missing weights raise, nothing crashes."""
+    import pytest
+    g = golden("synth3.npz")
+    x = dev(h, g["data"][:1, :, :32].clone())                   # N=32 < 64 points: Lower_Net cannot select its top-64
+    with pytest.raises(_capi.MMEgoError):
+        h.lower_forward(dev(h, g["upper_l"][:1]), x, dev(h, g["skl"][:1]), dev(h, g["R"][:1]), dev(h, g["t"][:1]))
+    with pytest.raises(_capi.MMEgoError):
+        h.imu_forward(torch.zeros(1, 2, 3, 14, device=h.device))
+    with pytest.raises(_capi.MMEgoError):
+        h.set_option("no_such_option", 1)
+    h2 = _capi.Handle(lib=h.lib, require_cuda=h.require_cuda)
+    with pytest.raises(_capi.MMEgoError, match="never set"):
+        h2.imu_forward(torch.zeros(1, 2, 3, 15, device=h.device))
+    with pytest.raises(_capi.MMEgoError, match="missing state_dict tensor"):
+        h2.set_weights(_capi.NET_UPPER, {"module0.conv1.weight": torch.zeros(8, 6, 1)})
+    h2.close()
