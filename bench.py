@@ -27,6 +27,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "mmEgo inference frames/s (IMU_Net+Upper_Net+Lower_Net/GCN+decode, fp32 parity mode)"
+KERNEL_NAMES = {0: "gemm_ffma_kernel<128,EPI_LSTM> (fp32 FFMA GEMM + fused LSTM cell)",
+                1: "lstm_tc_step_kernel<3> (tcgen05 fp16x3 split-precision GEMM, TMEM partial sums drained to fp32 registers, fused LSTM cell)",
+                2: "lstm_tc_step_kernel<1> (tcgen05 fp16 GEMM, fused LSTM cell)"}
 UNIT = "frames/s"
 L, N_PTS, N_IMU = 20, 128, 20
 H = 512
@@ -149,6 +152,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-snippets", type=int, default=256, help="snippets per CPU-baseline pass (bounded sample)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-half", action="store_true", help="skip the extra pass in single-pass fp16 mode")
+    ap.add_argument("--imu-gemm", type=int, default=None, help="0 fp32 FFMA, 1 tcgen05 fp16x3, 2 tcgen05 fp16 (default: library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -172,6 +177,8 @@ def main():
     B = args.batch
     Bg = B * world                                   # weak scaling: every rank owns B snippets
     pipe = MMEgoPipeline(dev, imu_state=None)
+    if args.imu_gemm is not None:
+        pipe.handle.set_option("imu_gemm", args.imu_gemm)
     # this rank's shard of the global synthetic batch (seed depends on the rank; same distribution)
     sb = synth.batch(B, L=L, N=N_PTS, n_imu=N_IMU, seed=1234 + rank)
     imu_h, data_h, skl_h = sb["imu"].pin_memory(), sb["data"].pin_memory(), sb["skl"].pin_memory()
@@ -203,31 +210,35 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        pred, sums = one_step()
-    barrier()
+    def timed_pass(steps, warmup):
+        """W untimed + K timed steps; returns (ms max over ranks, launches, per-span profile, clocks, sums)."""
+        for _ in range(warmup):
+            pred, sums = one_step()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        pipe.handle.profile_begin()
+        n0 = pipe.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            pred, sums = one_step()
+        e1.record()
+        barrier()
+        ms_ = e0.elapsed_time(e1)
+        launches_ = pipe.launch_count() - n0
+        prof_ = pipe.handle.profile_read()
+        pipe.handle.profile_end()
+        clocks_ = sampler.stop() if rank == 0 else None
+        t_ms = torch.tensor([ms_], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        return float(t_ms.item()), launches_, prof_, clocks_, sums
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    pipe.handle.profile_begin()
-    n0 = pipe.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        pred, sums = one_step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = pipe.launch_count() - n0
-    prof = pipe.handle.profile_read()
-    pipe.handle.profile_end()
-    clocks = sampler.stop() if rank == 0 else None
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms = float(t_ms.item())
+    mode = args.imu_gemm if args.imu_gemm is not None else 1
+    ms, launches, prof, clocks, sums = timed_pass(args.steps, args.warmup)
     ms_per_step = ms / args.steps
     frames = Bg * L
     value = frames / (ms_per_step * 1e-3)
@@ -253,6 +264,12 @@ def main():
                "d2h_bytes_per_step": d2h * world, "ms_per_step": float(dt.item()) * 1e3, "steps": k2,
                "api": "mmego_infer_host (pinned host buffers)"}
 
+    half = None
+    if mode == 1 and not args.no_half:
+        pipe.handle.set_option("imu_gemm", 2)
+        half = timed_pass(args.steps, 2)
+        pipe.handle.set_option("imu_gemm", 1)
+
     if rank == 0:
         peaks = measured_peaks()
         # dominant kernel: the H=512 LSTM timestep launch (recurrent GEMM + fused cell), 160 launches per chunk
@@ -265,22 +282,31 @@ def main():
             bc = min(chunk, B - c * chunk)
             fl += N_IMU * (lstm_step_flops(bc * L, H) + lstm_step_flops(bc * L, 2 * H))
             fl += L * 2 * lstm_step_flops(bc, 2 * H)
-        lst = prof.get("imu.lstm_step", dict(ms=0.0, launches=0))
-        per_launch_flops = fl * args.steps / max(1, lst["launches"])
-        per_launch_ms = lst["ms"] / max(1, lst["launches"])
-        ach = per_launch_flops / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
         peak = peaks["bf16_sustained"]
-        roofline = {"bound": "tensor", "kernel": "gemm_ffma_kernel<128,EPI_LSTM> (H=512 LSTM timestep: [x_t|h_{t-1}] GEMM + fused cell)",
+
+        def lstm_roofline(prof_, ms_, steps_, mode_):
+            lst = prof_.get("imu.lstm_step", dict(ms=0.0, launches=0))
+            per_launch_flops = fl * steps_ / max(1, lst["launches"])
+            per_launch_ms = lst["ms"] / max(1, lst["launches"])
+            ach = per_launch_flops / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
+            passes = 3 if mode_ == 1 else 1
+            return {"bound": "tensor", "kernel": "H=512 LSTM timestep launch: " + KERNEL_NAMES[mode_],
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                     "peak_source": peaks["source"] + ", sustained dense bf16 (kernel timed inside a long step)",
-                    "avg_launch_ms": per_launch_ms, "launches": lst["launches"],
-                    "flops_per_launch": per_launch_flops,
-                    "share_of_step": lst["ms"] / ms if ms > 0 else None}
+                    "avg_launch_ms": per_launch_ms, "launches": lst["launches"], "flops_per_launch": per_launch_flops,
+                    "mma_passes": passes, "tensor_pipe_tflops_issued": ach * passes,
+                    "note": ("fp32-grade results need 3 fp16 tensor-core products per algorithmic multiply; "
+                             "`achieved` counts algorithmic FLOPs once, `tensor_pipe_tflops_issued` is the MMA work done")
+                            if passes == 3 else "single-pass fp16",
+                    "share_of_step": lst["ms"] / ms_ if ms_ > 0 else None}
+
+        roofline = lstm_roofline(prof, ms, args.steps, mode)
         stage_ms = {k: round(v["ms"] / args.steps, 3) for k, v in prof.items()}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": {0: "f32", 1: "f32 (fp16x3 split products, fp32 accumulate)", 2: "f16 (fp32 accumulate)"}[mode],
+            "data": "synthetic",
             "config": {"workload": f"full pipeline, B={B} snippets per GPU, L={L}, N={N_PTS}, n_imu={N_IMU} "
                                    "(config 3 of BASELINE.json); IMU_Net weights: " + pipe.imu_weights,
                        "global_batch": Bg, "frames_per_step": frames, "parallelism": f"dp{world}",
@@ -291,6 +317,14 @@ def main():
             "mpjpe_vs_synthetic_target_cm": rep["mpjpe_cm"],
             "roofline": roofline,
         }
+        if half:
+            ms2, _, prof2, _, _ = half
+            line["half_mode"] = {
+                "what": "same workload with imu_gemm=2 (single-pass fp16 tensor-core LSTM); tolerance vs the fp32 oracle: "
+                        "R 2e-3, t 1e-4 m, joints 3e-3 m with the seeded stand-in weights (tests/_parity.py IMU_MODE_TOL)",
+                "value": frames / (ms2 / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms2 / args.steps,
+                "roofline": lstm_roofline(prof2, ms2, args.steps, 2),
+                "stage_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in prof2.items()}}
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:

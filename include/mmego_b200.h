@@ -56,8 +56,11 @@ int mmego_destroy(mmego_handle* h);
 /* Text of the last error on this handle (or of the last failed mmego_create when h is NULL). */
 const char* mmego_last_error(const mmego_handle* h);
 
-/* Options: "imu_chunk" (snippets per IMU_Net workspace chunk, default 512),
- *          "imu_gemm"  (0 = fp32 FFMA recurrent GEMM, 1 = tcgen05 fp16x3 split-precision tensor-core GEMM). */
+/* Options: "imu_chunk"   (snippets per IMU_Net workspace chunk, default 2048),
+ *          "imu_gemm"    (IMU_Net's H=512 LSTMs: 1 = tcgen05 fp16x3 split-precision tensor-core GEMM, fp32-grade, the
+ *                         default; 2 = tcgen05 single-pass fp16, fastest, tolerance reported separately;
+ *                         0 = fp32 FFMA GEMM),
+ *          "tc_kb_chunk" (imu_gemm=1: K blocks of 64 accumulated in TMEM before draining into fp32 registers, default 2). */
 int mmego_set_option(mmego_handle* h, const char* key, long long value);
 
 /* Replaces IMUNet.load / UpperNet.load / LowerNet.load (Net/IMU_Net.py:106-114, Net/Upper_Net.py:400-404,

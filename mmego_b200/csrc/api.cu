@@ -244,6 +244,76 @@ int imu_chunk_forward(mmego_handle* h, const float* imu, float* R, float* t, lon
     return MMEGO_OK;
 }
 
+#ifndef MMEGO_EMUL
+// ---------------------------------------------------------------------------------------------- IMU_Net on tensor cores
+// Activations are fp16 hi/lo planes (see lstm_tc.cu); one plane of n elements takes n/2 floats of workspace.
+struct ImuTcWs {
+    void *u[2], *y0[2], *y1[2], *s[2], *z0[2], *z1[2];
+    float* cst;
+    long long Spad;
+};
+void plan_imu_tc(Carver& c, long long Bc, int L, int n, ImuTcWs& w) {
+    const size_t S = (size_t)Bc * L;
+    auto plane = [&](size_t elems) { return static_cast<void*>(c.f((elems + 1) / 2)); };
+    for (int k = 0; k < 2; ++k) {
+        w.u[k] = plane(S * n * kImuH);
+        w.y0[k] = plane(S * n * 2 * kImuH);
+        w.y1[k] = plane(S * n * 2 * kImuH);
+        w.s[k] = plane(S * 2 * kImuH);
+        w.z0[k] = plane(S * 2 * kImuH);
+        w.z1[k] = plane(S * 2 * kImuH);
+    }
+    w.Spad = (long long)((S + 127) / 128 * 128);
+    w.cst = c.f((size_t)2 * kImuH * w.Spad);
+}
+
+int imu_chunk_forward_tc(mmego_handle* h, const float* imu, float* R, float* t, long long Bc, int L, int n,
+                         const ImuTcWs& w, cudaStream_t st) {
+    const long long S = Bc * L;
+    const ImuWeights& W = h->imu;
+    const int npass = h->imu_gemm == 1 ? 3 : 1;
+    void* const nolo = nullptr;
+    auto lo = [&](void* const* planes) { return npass == 3 ? planes[1] : nolo; };
+    {
+        Prof p(h, "imu.fc1", st);
+        tc_imu_fc1(imu, W.fc1, w.u[0], lo(w.u), S * n, st);                               // Net/IMU_Net.py:79
+    }
+    auto tap_split = [&](const char* name, void* const* planes, long long elems) {
+        auto it = h->taps.find(name);
+        if (it == h->taps.end()) return;
+        tc_unsplit(planes[0], lo(planes), static_cast<float*>(it->second.first),
+                   std::min<long long>(elems, (long long)(it->second.second / 4)), st);
+        h->taps.erase(it);
+    };
+    tap_split("imu.u", w.u, S * n * kImuH);
+    int rc = 0;
+    {
+        Prof p(h, "imu.lstm_step", st);
+        rc |= tc_lstm_layer(h, W.tc_fast[0], w.u[0], lo(w.u), w.y0[0], lo(w.y0), w.cst, S, w.Spad, n, npass, st);   // :80
+        tap_split("imu.y0", w.y0, S * n * 2 * kImuH);
+        rc |= tc_lstm_layer(h, W.tc_fast[1], w.y0[0], lo(w.y0), w.y1[0], lo(w.y1), w.cst, S, w.Spad, n, npass, st);
+    }
+    tap_split("imu.f", w.y1, S * n * 2 * kImuH);
+    {
+        Prof p(h, "imu.pool", st);
+        tc_imu_pool(w.y1[0], lo(w.y1), W.attn.p, w.s[0], lo(w.s), S, n, st);              // :82-83
+    }
+    tap_split("imu.s", w.s, S * 2 * kImuH);
+    {
+        Prof p(h, "imu.lstm_step", st);
+        rc |= tc_lstm_layer(h, W.tc_slow[0], w.s[0], lo(w.s), w.z0[0], lo(w.z0), w.cst, Bc, w.Spad, L, npass, st);  // :85
+        rc |= tc_lstm_layer(h, W.tc_slow[1], w.z0[0], lo(w.z0), w.z1[0], lo(w.z1), w.cst, Bc, w.Spad, L, npass, st);
+    }
+    tap_split("imu.g", w.z1, S * 2 * kImuH);
+    {
+        Prof p(h, "imu.decode", st);
+        tc_imu_decode(w.z1[0], lo(w.z1), W.fc2.p, R, t, S, st);                           // :87-93
+    }
+    if (rc) return fail(h, MMEGO_ECUDA, "imu_forward: cuTensorMapEncodeTiled failed");
+    return MMEGO_OK;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------- Upper_Net schedule
 struct UpperWs {
     float* g;        // [F,64]
@@ -308,7 +378,20 @@ void run_gcn(mmego_handle* h, const float* y0, int B, int L, const LowerWs& w, c
     run_gemm(h, a, EPI_F6, st, 64);
 }
 
-bool is_stream_ok(void*) { return true; }
+size_t imu_ws_bytes(const mmego_handle* h, long long Bc, int L, int n) {
+    Carver s(nullptr);
+#ifndef MMEGO_EMUL
+    if (h->imu_gemm != 0) {
+        ImuTcWs w;
+        plan_imu_tc(s, Bc, L, n, w);
+        return s.off;
+    }
+#endif
+    ImuWs w;
+    plan_imu(s, Bc, L, n, w);
+    (void)h;
+    return s.off;
+}
 
 int check_dims(mmego_handle* h, int B, int L, int N) {
     if (!h) return MMEGO_EINVAL;
@@ -338,6 +421,11 @@ int mmego_create(mmego_handle** out, int device) {
     mmego_handle* h = new mmego_handle();
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
+#ifdef MMEGO_EMUL
+    h->imu_gemm = 0;
+#else
+    h->imu_gemm = tc_supported() ? 1 : 0;      // default: tcgen05 fp16x3 (fp32-grade); 0 = FFMA fp32; 2 = tcgen05 fp16
+#endif
     *out = h;
     return MMEGO_OK;
 }
@@ -362,8 +450,23 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
         return MMEGO_OK;
     }
     if (!strcmp(key, "imu_gemm")) {
-        if (value != 0) return fail(h, MMEGO_EINVAL, "imu_gemm=%lld is not available in this build", value);
+        if (value < 0 || value > 2) return fail(h, MMEGO_EINVAL, "imu_gemm must be 0 (fp32 FFMA), 1 (tcgen05 fp16x3) or 2 (tcgen05 fp16)");
+#ifdef MMEGO_EMUL
+        if (value != 0) return fail(h, MMEGO_EINVAL, "imu_gemm=%lld needs the sm_100a build", value);
+#else
+        if (value != 0 && !tc_supported()) return fail(h, MMEGO_EARCH, "imu_gemm=%lld: cuTensorMapEncodeTiled is not available from this driver", value);
+        if (value != 0 && h->imu.ready && !h->imu.tc_ready) return fail(h, MMEGO_ESTATE, "imu_gemm=%lld: tensor-core weight packing failed at set_weights", value);
+#endif
         h->imu_gemm = (int)value;
+        return MMEGO_OK;
+    }
+    if (!strcmp(key, "tc_kb_chunk")) {
+        if (value < 0 || value > 64) return fail(h, MMEGO_EINVAL, "tc_kb_chunk must be in 0..64");
+        h->tc_kb_chunk = (int)value;
+        return MMEGO_OK;
+    }
+    if (!strcmp(key, "tc_precise_act")) {
+        h->tc_precise_act = value != 0;
         return MMEGO_OK;
     }
     return fail(h, MMEGO_EINVAL, "unknown option '%s'", key);
@@ -402,6 +505,18 @@ int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const 
             memcpy(fc2.data() + 9 * 2 * H, sd.get("fc2.bias", 9), sizeof(float) * 9);
             ok &= upload(h, fc2, W.fc2);
             W.ready = ok;
+            W.tc_ready = false;
+#ifndef MMEGO_EMUL
+            if (ok && tc_supported()) {
+                bool t = true;
+                for (int l = 0; l < 2; ++l) {
+                    t = t && tc_pack_layer(h, sd, "rnn_fast.", l, l == 0 ? H : 2 * H, W.tc_fast[l]);
+                    t = t && tc_pack_layer(h, sd, "rnn_slow.", l, 2 * H, W.tc_slow[l]);
+                }
+                W.tc_ready = t;
+            }
+            if (h->imu_gemm != 0 && !W.tc_ready) return fail(h, MMEGO_ESTATE, "set_weights: tensor-core packing of IMU_Net failed");
+#endif
         } else if (net == MMEGO_NET_UPPER) {
             UpperWeights& W = h->upper;
             W.ready = false;
@@ -453,8 +568,7 @@ size_t mmego_workspace_bytes(const mmego_handle* h, int stage, int B, int L, int
     Carver c(nullptr);
     const long long Bc = B < h->imu_chunk ? B : h->imu_chunk;
     if (stage == MMEGO_STAGE_IMU) {
-        ImuWs w;
-        plan_imu(c, Bc, L, n_imu, w);
+        c.off = imu_ws_bytes(h, Bc, L, n_imu);
     } else if (stage == MMEGO_STAGE_UPPER) {
         UpperWs w;
         plan_upper(c, B, L, w);
@@ -466,9 +580,7 @@ size_t mmego_workspace_bytes(const mmego_handle* h, int stage, int B, int L, int
         const size_t F = (size_t)B * L;
         c.f(F * 9); c.f(F * 3); c.f(F * 45); c.f(F * 24);
         size_t best = 0;
-        {
-            Carver s(nullptr); ImuWs w; plan_imu(s, Bc, L, n_imu, w); best = std::max(best, s.off);
-        }
+        best = std::max(best, imu_ws_bytes(h, Bc, L, n_imu));
         {
             Carver s(nullptr); UpperWs w; plan_upper(s, B, L, w); best = std::max(best, s.off);
         }
@@ -493,6 +605,22 @@ int mmego_imu_forward(mmego_handle* h, const float* imu, float* R, float* t, int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long Bc = B < h->imu_chunk ? B : h->imu_chunk;
     Carver c(ws);
+#ifndef MMEGO_EMUL
+    if (h->imu_gemm != 0) {
+        if (!h->imu.tc_ready) return fail(h, MMEGO_ESTATE, "imu_forward: tensor-core weights are not packed");
+        ImuTcWs w;
+        plan_imu_tc(c, Bc, L, n_imu, w);
+        for (long long b0 = 0; b0 < B; b0 += Bc) {
+            const long long nb = (B - b0) < Bc ? (B - b0) : Bc;
+            if (int rc = imu_chunk_forward_tc(h, imu + (size_t)b0 * L * n_imu * kImuFeat, R + (size_t)b0 * L * 9,
+                                              t + (size_t)b0 * L * 3, nb, L, n_imu, w, st))
+                return rc;
+        }
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches = g_launches;
+        return MMEGO_OK;
+    }
+#endif
     ImuWs w;
     plan_imu(c, Bc, L, n_imu, w);
     for (long long b0 = 0; b0 < B; b0 += Bc) {

@@ -8,6 +8,8 @@
 
 #include "cuda_compat.h"
 
+struct mmego_handle;
+
 namespace mmego {
 
 extern long long g_launches;   // kernels launched by this library (all handles)
@@ -98,6 +100,8 @@ void launch_transform2r(const float* pts, const float* R, const float* t, float*
 // ------------------------------------------------------------------------------------------------
 // packed weights
 // ------------------------------------------------------------------------------------------------
+struct TcLstmLayer;
+struct PackedGemm;
 struct DevBuf {
     float* p = nullptr;
     size_t n = 0;
@@ -115,8 +119,21 @@ struct PackedSmallLstmLayer {  // H=64
     DevBuf whh;                // [2][256][64]  row = thread order
     int in = 0;
 };
+// H=512 layer packed for the tcgen05 path (lstm_tc.cu): fp16 hi/lo planes [2 dirs * 2048 rows][In + 512], scaled by 2^e
+struct TcLstmLayer {
+    alignas(64) unsigned char map_hi[128];
+    alignas(64) unsigned char map_lo[128];
+    void* whi = nullptr;
+    void* wlo = nullptr;
+    float* bias = nullptr;     // [2][2048] packed row order
+    int in_features = 0, K = 0;
+    float out_scale = 1.f;     // 2^-e
+};
+
 struct ImuWeights {
     bool ready = false;
+    bool tc_ready = false;
+    TcLstmLayer tc_fast[2], tc_slow[2];
     PackedGemm fc1;
     PackedBigLstmLayer fast[2], slow[2];
     DevBuf attn;       // [1024] + [1] bias at the end
@@ -153,6 +170,20 @@ struct HostPackedGemm {
 };
 inline int pad16(int k) { return (k + 15) / 16 * 16; }
 
+#ifndef MMEGO_EMUL
+// tcgen05 path (lstm_tc.cu; nvcc only)
+struct StateDict;
+bool tc_supported();
+bool tc_pack_layer(mmego_handle* h, const StateDict& sd, const std::string& prefix, int layer, int In, TcLstmLayer& out);
+int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const void* xlo, void* yhi, void* ylo,
+                  float* cstate, long long S, long long Spad, int T, int npass, cudaStream_t st);
+void tc_imu_fc1(const float* imu, const PackedGemm& fc1, void* uhi, void* ulo, long long rows, cudaStream_t st);
+void tc_imu_pool(const void* yhi, const void* ylo, const float* attn, void* shi, void* slo, long long F, int n,
+                 cudaStream_t st);
+void tc_imu_decode(const void* ghi, const void* glo, const float* fc2, float* R, float* t, long long F, cudaStream_t st);
+void tc_unsplit(const void* hi, const void* lo, float* out, long long n, cudaStream_t st);
+#endif
+
 }  // namespace mmego
 
 struct ProfSpan {
@@ -168,8 +199,10 @@ struct mmego_handle {
     int sm_count = 148;
     std::string err;
     long long launches = 0;
-    long long imu_chunk = 512;
-    int imu_gemm = 0;
+    long long imu_chunk = 2048;
+    int imu_gemm = -1;        // -1: pick at first use (1 when the tcgen05 path is available, else 0)
+    int tc_precise_act = 0;
+    int tc_kb_chunk = 2;      // fp16x3 mode: K blocks (of 64) per TMEM partial accumulation
     mmego::ImuWeights imu;
     mmego::UpperWeights upper;
     mmego::LowerWeights lower;

@@ -1,0 +1,641 @@
+// lstm_tc.cu -- IMU_Net's H=512 bidirectional LSTMs (Net/IMU_Net.py:58-62, 80, 85; 97.5 % of the pipeline's FLOPs) on
+// the 5th-generation tensor cores: one persistent, warp-specialised tcgen05 kernel per timestep.
+//
+//   gates[M, 4H] = [x_t | h_{t-1}] [M, In+H] * W^T            M = sequences (81,920 at B=4096), 4H = 2048
+//
+// * CTA tile 128 sequences x 256 gate columns (= 64 hidden units x {i,f,g,o}: the weight rows are packed
+//   gate-interleaved so that one tile holds all four gates of its units), K in blocks of 64.
+// * warp 0 = TMA producer (operand tiles -> 128B-swizzled shared memory, mbarrier ring),
+//   warp 1 = MMA issuer (tcgen05.mma, fp32 accumulators in TMEM, double buffered: 2 x 256 columns),
+//   warps 2..17 = epilogue (tcgen05.ld of partial sums -> fp32 register accumulation -> bias, sigmoid/tanh, cell update,
+//   h written back as the next step's operand).
+// * persistent: grid = #SMs, static round-robin over (sequence tile, direction, unit tile) with the unit tile fastest,
+//   so the CTAs that share an activation tile run together and hit it in L2.
+// * precision: activations and weights are stored as fp16 hi/lo pairs.  NPASS = 3 evaluates
+//   a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi (weights pre-scaled by 2^e so that w_lo stays a normal fp16) with fp32
+//   accumulation -- ~2^-22 relative, i.e. fp32-grade, which is what the 1e-3 cm parity target needs; NPASS = 1 uses the
+//   hi parts only (plain fp16 tensor-core GEMM, reported with its own tolerance).
+// * the recurrent operand of step t is read straight from the layer's own output tensor at t-1 (no separate h buffer);
+//   the cell state is fp32, laid out [direction][unit][sequence] so that the epilogue's accesses are coalesced.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstring>
+
+#include "internal.h"
+#include "pack.h"
+#include "tc_common.cuh"
+
+namespace mmego {
+
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int kUnitsPerTile = BN / 4;            // 64
+constexpr int kNTiles = 4 * kImuH / BN;          // 8
+constexpr int kEpiWarps = 16;
+constexpr int kUnitsPerEpiWarp = kUnitsPerTile / (kEpiWarps / 4);   // 16
+constexpr int kThreads = 128 + kEpiWarps * 32;   // 640: warpgroup 0 = {TMA, MMA, 2 idle warps}, warpgroups 1..4 = epilogue
+constexpr int A_TILE = BM * BK * 2;              // 16 KB
+constexpr int W_TILE = BN * BK * 2;              // 32 KB
+constexpr uint32_t kTmemCols = 512;
+// Activation planes hold 2^8 * value: with |h| <= 1 (and |u| up to ~250) the hi part stays far below the fp16 maximum,
+// while the lo part (residual, ~2^-12 of the value) stays a NORMAL fp16 for |value| >= 1e-3 -- unscaled, the residual of
+// a typical h ~ 0.05 would be a denormal and lose most of its 11 bits.
+constexpr float kActScale = 256.0f, kActInv = 1.0f / 256.0f;
+
+template <int NPASS>
+struct Cfg {
+    static constexpr int PLANES = NPASS == 3 ? 2 : 1;
+    static constexpr int STAGE_BYTES = PLANES * (A_TILE + W_TILE);          // 96 KB / 48 KB
+    static constexpr int STAGES = NPASS == 3 ? 2 : 4;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct StepParams {
+    int S;               // sequences
+    int m_tiles;
+    int kb_in, kb_rec;   // K blocks of the input segment / of the recurrent segment (0 on the first step)
+    int in_features;     // column of W where the recurrent block starts
+    int tt0, tt1, tp0, tp1;   // per direction: time index of this step, and of the previous one (no arrays: dynamic
+                         // indexing of kernel parameters would force a local-memory copy)
+    int T;
+    const float* bias;   // [2][2048], packed row order
+    float* cstate;       // [2][512][Spad]
+    long long Spad;
+    __half* out_hi;      // [S][T][1024]
+    __half* out_lo;      // may be null (NPASS == 1)
+    float out_scale;     // 2^-e
+    int kb_chunk;        // K blocks accumulated in TMEM before the partial sum is drained into registers
+};
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
+template <int NPASS>
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtensorMap mXlo,
+                    const __grid_constant__ CUtensorMap mYhi, const __grid_constant__ CUtensorMap mYlo,
+                    const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo,
+                    const StepParams p) {
+    using C = Cfg<NPASS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + C::STAGES;
+    uint64_t* tfull = bars + 2 * C::STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.m_tiles * 2 * kNTiles;
+    const int kb_total = p.kb_in + p.kb_rec;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&mXhi);
+        prefetch_tensormap(&mYhi);
+        prefetch_tensormap(&mWhi);
+        if (NPASS == 3) {
+            prefetch_tensormap(&mXlo);
+            prefetch_tensormap(&mYlo);
+            prefetch_tensormap(&mWlo);
+        }
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], kEpiWarps);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_holder, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    // register re-balancing: the control warpgroup keeps 32 registers per thread (the CTA pool must balance: 128 x (96-32) = 512 x (112-96)), the 16 epilogue warps (64 fp32
+    // accumulators per thread) grow to 112
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+      if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % kNTiles, dir = (tile / kNTiles) & 1, m = tile / (2 * kNTiles);
+                const int wrow = dir * 4 * kImuH + nt * BN;
+                const int tt = dir ? p.tt1 : p.tt0, tp = dir ? p.tp1 : p.tp0;
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                    uint8_t* sw = sa + C::PLANES * A_TILE;
+                    int wcol;
+                    if (kb < p.kb_in) {
+                        tma_load_3d(sa, &mXhi, &full[stage], kb * BK, tt, m * BM);
+                        if (NPASS == 3) tma_load_3d(sa + A_TILE, &mXlo, &full[stage], kb * BK, tt, m * BM);
+                        wcol = kb * BK;
+                    } else {
+                        const int kr = kb - p.kb_in;
+                        tma_load_3d(sa, &mYhi, &full[stage], dir * kImuH + kr * BK, tp, m * BM);
+                        if (NPASS == 3)
+                            tma_load_3d(sa + A_TILE, &mYlo, &full[stage], dir * kImuH + kr * BK, tp, m * BM);
+                        wcol = p.in_features + kr * BK;
+                    }
+                    tma_load_2d(sw, &mWhi, &full[stage], wcol, wrow);
+                    if (NPASS == 3) tma_load_2d(sw + W_TILE, &mWlo, &full[stage], wcol, wrow);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+      } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        // The tensor core's fp32 accumulator loses low-order bits on every accumulate (measured: errors grow with the
+        // length of the accumulation chain and are biased, so they compound through the recurrence).  The K loop is
+        // therefore cut into chunks of p.kb_chunk K-blocks: each chunk accumulates into one of the two TMEM buffers
+        // from zero, and the epilogue warps drain finished chunks into fp32 registers (round-to-nearest adds) while
+        // the next chunk is being multiplied.
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0 /*fp16*/);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t cc = 0;      // running chunk counter (same sequence in the epilogue warps)
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int c0 = 0; c0 < kb_total; c0 += p.kb_chunk, ++cc) {
+                    const uint32_t buf = cc & 1, bph = (cc >> 1) & 1;
+                    mbar_wait(&tempty[buf], bph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * BN;
+                    const int c1 = min(kb_total, c0 + p.kb_chunk);
+                    for (int kb = c0; kb < c1; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+                        const uint32_t a_lo = a_hi + A_TILE;
+                        const uint32_t w_hi = a_hi + C::PLANES * A_TILE;
+                        const uint32_t w_lo = w_hi + W_TILE;
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t da_hi = make_sw128_kmajor_desc(a_hi + k * 32);
+                            const uint64_t dw_hi = make_sw128_kmajor_desc(w_hi + k * 32);
+                            if (NPASS == 3) {
+                                // small correction terms first, the large term last
+                                const uint64_t da_lo = make_sw128_kmajor_desc(a_lo + k * 32);
+                                const uint64_t dw_lo = make_sw128_kmajor_desc(w_lo + k * 32);
+                                mma_f16_ss(d_tmem, da_hi, dw_lo, idesc, (kb > c0) || (k > 0));
+                                mma_f16_ss(d_tmem, da_lo, dw_hi, idesc, 1);
+                                mma_f16_ss(d_tmem, da_hi, dw_hi, idesc, 1);
+                            } else {
+                                mma_f16_ss(d_tmem, da_hi, dw_hi, idesc, (kb > c0) || (k > 0));
+                            }
+                        }
+                        mma_commit(&empty[stage]);      // frees the smem slot when these MMAs have read it
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    mma_commit(&tfull[buf]);            // partial accumulator complete -> epilogue
+                }
+            }
+        }
+        __syncwarp();
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        // ===================================================================== epilogue (16 warps)
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int part = (warp - 4) >> 2;       // which 16 of the tile's 64 hidden units
+        const int u0 = part * kUnitsPerEpiWarp;
+        uint32_t cc = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % kNTiles, dir = (tile / kNTiles) & 1, m = tile / (2 * kNTiles);
+            float acc[4][kUnitsPerEpiWarp];     // i, f, g, o pre-activations (scaled) of this thread's row
+            for (int c0 = 0; c0 < kb_total; c0 += p.kb_chunk, ++cc) {
+                const uint32_t buf = cc & 1, bph = (cc >> 1) & 1;
+                mbar_wait(&tfull[buf], bph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + u0);
+#pragma unroll
+                for (int g2 = 0; g2 < 2; ++g2) {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld_x16(taddr + (2 * g2) * kUnitsPerTile, r0);
+                    tmem_ld_x16(taddr + (2 * g2 + 1) * kUnitsPerTile, r1);
+                    tmem_ld_wait();
+                    if (c0 == 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            acc[2 * g2][j] = __uint_as_float(r0[j]);
+                            acc[2 * g2 + 1][j] = __uint_as_float(r1[j]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            acc[2 * g2][j] += __uint_as_float(r0[j]);
+                            acc[2 * g2 + 1][j] += __uint_as_float(r1[j]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);
+            }
+            // ---- LSTM cell on the register-resident pre-activations
+            const long long row = (long long)m * BM + q * 32 + lane;
+            const bool ok = row < p.S;
+            const float* bias = p.bias + dir * 4 * kImuH + nt * BN + u0;
+            const bool has_state = p.kb_rec > 0;
+            float hv[kUnitsPerEpiWarp];
+            float* cbase = p.cstate + ((long long)(dir * kImuH + nt * kUnitsPerTile + u0)) * p.Spad + row;
+#pragma unroll
+            for (int j = 0; j < kUnitsPerEpiWarp; ++j) {
+                if ((j & 3) == 0) asm volatile("" ::: "memory");   // keep the bias / cell-state loads from being hoisted en bloc
+                const float pi = fmaf(acc[0][j], p.out_scale, __ldg(bias + j));
+                const float pf = fmaf(acc[1][j], p.out_scale, __ldg(bias + kUnitsPerTile + j));
+                const float pg = fmaf(acc[2][j], p.out_scale, __ldg(bias + 2 * kUnitsPerTile + j));
+                const float po = fmaf(acc[3][j], p.out_scale, __ldg(bias + 3 * kUnitsPerTile + j));
+                const float cprev = (has_state && ok) ? cbase[(long long)j * p.Spad] : 0.f;
+                const float cn = sigmoid_fast(pf) * cprev + sigmoid_fast(pi) * tanh_fast(pg);
+                hv[j] = sigmoid_fast(po) * tanh_fast(cn);
+                if (ok) cbase[(long long)j * p.Spad] = cn;
+            }
+            if (ok) {
+                const long long o = (row * p.T + (dir ? p.tt1 : p.tt0)) * (2 * kImuH) + dir * kImuH + nt * kUnitsPerTile + u0;
+                uint32_t ph[8], pl[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float v0 = hv[2 * j] * kActScale, v1 = hv[2 * j + 1] * kActScale;
+                    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+                    const __half l0 = __float2half_rn(v0 - __half2float(h0));
+                    const __half l1 = __float2half_rn(v1 - __half2float(h1));
+                    ph[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                    pl[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                }
+                uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
+                dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                if (p.out_lo) {
+                    uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
+                    dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- small split-fp16 kernels
+__device__ __forceinline__ void store_split(__half* hi, __half* lo, long long i, float v) {
+    v = fminf(fmaxf(v * kActScale, -65000.f), 65000.f);
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2half_rn(v - __half2float(h));
+}
+
+// fc1 + ReLU (Net/IMU_Net.py:79): imu [rows,15] -> u [rows,512] as fp16 hi/lo planes.  HBM-bound (writes 2 KB per row).
+constexpr int FC1_ROWS = 16;
+__global__ void __launch_bounds__(256) imu_fc1_split_kernel(const float* __restrict__ imu, const float* __restrict__ w,
+                                                            const float* __restrict__ b, int ldw,
+                                                            __half* __restrict__ uhi, __half* __restrict__ ulo,
+                                                            long long rows) {
+    __shared__ float xs[FC1_ROWS][16];
+    const int tid = threadIdx.x;
+    const long long r0 = (long long)blockIdx.x * FC1_ROWS;
+    {
+        const int r = tid / 16, c = tid % 16;
+        xs[r][c] = (c < kImuFeat && (r0 + r) < rows) ? imu[(r0 + r) * kImuFeat + c] : 0.f;
+    }
+    float w0[kImuFeat], w1[kImuFeat];
+#pragma unroll
+    for (int k = 0; k < kImuFeat; ++k) {
+        w0[k] = w[(2 * tid) * ldw + k];
+        w1[k] = w[(2 * tid + 1) * ldw + k];
+    }
+    const float b0 = b[2 * tid], b1 = b[2 * tid + 1];
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < FC1_ROWS; ++r) {
+        if (r0 + r >= rows) break;
+        float a0 = b0, a1 = b1;
+#pragma unroll
+        for (int k = 0; k < kImuFeat; ++k) {
+            a0 = fmaf(w0[k], xs[r][k], a0);
+            a1 = fmaf(w1[k], xs[r][k], a1);
+        }
+        a0 = fminf(fmaxf(a0, 0.f) * kActScale, 65000.f);
+        a1 = fminf(fmaxf(a1, 0.f) * kActScale, 65000.f);
+        const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
+        const long long o = (r0 + r) * kImuH + 2 * tid;
+        *reinterpret_cast<__half2*>(uhi + o) = __halves2half2(h0, h1);
+        if (ulo)
+            *reinterpret_cast<__half2*>(ulo + o) =
+                __halves2half2(__float2half_rn(a0 - __half2float(h0)), __float2half_rn(a1 - __half2float(h1)));
+    }
+}
+
+__device__ __forceinline__ void load8(const __half* hi, const __half* lo, long long i, float* v) {
+    const uint4 a = *reinterpret_cast<const uint4*>(hi + i);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(ah[k]);
+        v[2 * k] = f.x;
+        v[2 * k + 1] = f.y;
+    }
+    if (lo) {
+        const uint4 b = *reinterpret_cast<const uint4*>(lo + i);
+        const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(bh[k]);
+            v[2 * k] += f.x;
+            v[2 * k + 1] += f.y;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] *= kActInv;
+}
+
+// attention pooling over the n samples of a frame (Net/IMU_Net.py:82-83) on split planes: y [F,n,1024] -> s [F,1024]
+__global__ void __launch_bounds__(128) imu_pool_split_kernel(const __half* __restrict__ yhi, const __half* __restrict__ ylo,
+                                                             const float* __restrict__ attn, __half* __restrict__ shi,
+                                                             __half* __restrict__ slo, long long F, int n) {
+    __shared__ float sc[64];
+    __shared__ float part[4][64];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const long long f = blockIdx.x;
+    const long long base = f * (long long)n * 1024;
+    float aw[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) aw[k] = attn[tid * 8 + k];
+    // thread owns channels [8 tid, 8 tid + 8) of every sample; scores need a block reduction per sample
+    for (int s0 = 0; s0 < n; ++s0) {
+        float v[8];
+        load8(yhi, ylo, base + (long long)s0 * 1024 + tid * 8, v);
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a = fmaf(v[k], aw[k], a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) part[w][s0] = a;
+    }
+    __syncthreads();
+    if (tid < n) sc[tid] = part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid] + attn[1024];
+    __syncthreads();
+    float m = -INFINITY;
+    for (int i = 0; i < n; ++i) m = fmaxf(m, sc[i]);
+    float sum = 0.f;
+    for (int i = 0; i < n; ++i) sum += expf(sc[i] - m);
+    const float inv = 1.0f / sum;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < n; ++i) {
+        const float wgt = expf(sc[i] - m) * inv;
+        float v[8];
+        load8(yhi, ylo, base + (long long)i * 1024 + tid * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) store_split(shi, slo, f * 1024 + tid * 8 + k, acc[k]);
+}
+
+__device__ __forceinline__ void ortho6d_cols(const float* a6, float eps, float* m) {
+    float ax = a6[0], ay = a6[1], az = a6[2];
+    const float bx = a6[3], by = a6[4], bz = a6[5];
+    float n = fmaxf(sqrtf(ax * ax + ay * ay + az * az), eps);
+    ax /= n; ay /= n; az /= n;
+    float zx = ay * bz - az * by, zy = az * bx - ax * bz, zz = ax * by - ay * bx;
+    n = fmaxf(sqrtf(zx * zx + zy * zy + zz * zz), eps);
+    zx /= n; zy /= n; zz /= n;
+    const float yx = zy * az - zz * ay, yy = zz * ax - zx * az, yz = zx * ay - zy * ax;
+    m[0] = ax; m[1] = yx; m[2] = zx;
+    m[3] = ay; m[4] = yy; m[5] = zy;
+    m[6] = az; m[7] = yz; m[8] = zz;
+}
+
+// fc2 + ortho6d (Net/IMU_Net.py:87-93) on split planes; one warp per frame
+__global__ void __launch_bounds__(256) imu_decode_split_kernel(const __half* __restrict__ ghi, const __half* __restrict__ glo,
+                                                               const float* __restrict__ fc2, float* __restrict__ R,
+                                                               float* __restrict__ t, long long F) {
+    const int lane = threadIdx.x & 31;
+    const long long f = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (f >= F) return;
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) load8(ghi, glo, f * 1024 + i * 256 + lane * 8, x + i * 8);
+    float T9[9];
+#pragma unroll
+    for (int o = 0; o < 9; ++o) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a = fmaf(fc2[o * 1024 + i * 256 + lane * 8 + k], x[i * 8 + k], a);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+        T9[o] = a + fc2[9 * 1024 + o];
+    }
+    if (lane == 0) {
+        float m[9];
+        ortho6d_cols(T9, 1e-8f, m);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[f * 9 + k] = m[k];
+        t[f * 3] = T9[6]; t[f * 3 + 1] = T9[7]; t[f * 3 + 2] = T9[8];
+    }
+}
+
+// test hook: split planes -> fp32
+__global__ void unsplit_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ out,
+                               long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (__half2float(hi[i]) + (lo ? __half2float(lo[i]) : 0.f)) * kActInv;
+}
+
+// ---------------------------------------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        if (q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// activations [S][T][C] fp16; box = 64 channels x 1 step x 128 sequences
+bool make_act_map(CUtensorMap* m, const void* base, long long S, int T, int C) {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)S};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2};
+    cuuint32_t box[3] = {BK, 1, BM};
+    cuuint32_t es[3] = {1, 1, 1};
+    return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// weights [rows][K] fp16; box = 64 x 256
+bool make_w_map(CUtensorMap* m, const void* base, int rows, int K) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {BK, BN};
+    cuuint32_t es[2] = {1, 1};
+    return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// ================================================================================================ host interface
+bool tc_supported() { return encode_fn() != nullptr; }
+
+// Packs one bidirectional H=512 layer: rows gate-interleaved per tile of 64 units
+//   packed row p = dir*2048 + tile*256 + gate*64 + e   <->   torch row gate*512 + tile*64 + e   (gates i,f,g,o)
+// columns [W_ih (In) | W_hh (512)], scaled by 2^e and split into fp16 hi/lo.
+bool tc_pack_layer(mmego_handle* h, const StateDict& sd, const std::string& prefix, int layer, int In, TcLstmLayer& out) {
+    const int H = kImuH, K = In + H, rows = 2 * 4 * H;
+    std::vector<float> w((size_t)rows * K), bias(rows);
+    const char* sfx[2] = {"", "_reverse"};
+    float wmax = 0.f;
+    for (int d = 0; d < 2; ++d) {
+        const std::string k = "l" + std::to_string(layer) + sfx[d];
+        const float* wih = sd.get(prefix + "weight_ih_" + k, (long long)4 * H * In);
+        const float* whh = sd.get(prefix + "weight_hh_" + k, (long long)4 * H * H);
+        const float* bih = sd.get(prefix + "bias_ih_" + k, 4 * H);
+        const float* bhh = sd.get(prefix + "bias_hh_" + k, 4 * H);
+        for (int pr = 0; pr < 4 * H; ++pr) {
+            const int tile = pr / BN, gate = (pr % BN) / kUnitsPerTile, e = pr % kUnitsPerTile;
+            const int r = gate * H + tile * kUnitsPerTile + e;
+            float* dst = &w[((size_t)d * 4 * H + pr) * K];
+            std::memcpy(dst, wih + (size_t)r * In, sizeof(float) * In);
+            std::memcpy(dst + In, whh + (size_t)r * H, sizeof(float) * H);
+            bias[(size_t)d * 4 * H + pr] = bih[r] + bhh[r];
+        }
+    }
+    for (float v : w) wmax = std::max(wmax, std::fabs(v));
+    int e = 11;
+    while (e > 0 && wmax * std::ldexp(1.0f, e) > 30000.f) --e;
+    const float scale = std::ldexp(1.0f, e);
+    std::vector<__half> hi(w.size()), lo(w.size());
+    for (size_t i = 0; i < w.size(); ++i) {
+        const float v = w[i] * scale;
+        const __half a = __float2half_rn(v);
+        hi[i] = a;
+        lo[i] = __float2half_rn(v - __half2float(a));
+    }
+    cudaSetDevice(h->device);
+    auto up = [&](const void* src, size_t bytes, void** dst) {
+        if (cudaMalloc(dst, bytes) != cudaSuccess) return false;
+        h->owned.push_back(*dst);
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    void *dhi = nullptr, *dlo = nullptr, *db = nullptr;
+    if (!up(hi.data(), hi.size() * 2, &dhi) || !up(lo.data(), lo.size() * 2, &dlo) || !up(bias.data(), bias.size() * 4, &db))
+        return false;
+    out.whi = dhi;
+    out.wlo = dlo;
+    out.bias = static_cast<float*>(db);
+    out.in_features = In;
+    out.K = K;
+    out.out_scale = kActInv / scale;
+    static_assert(sizeof(CUtensorMap) == sizeof(out.map_hi), "tensor map storage size");
+    return make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_hi), dhi, rows, K) &&
+           make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_lo), dlo, rows, K);
+}
+
+// One bidirectional layer: x planes [S][T][In] -> y planes [S][T][1024]; cstate [2][512][Spad] fp32 scratch.
+int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const void* xlo, void* yhi, void* ylo,
+                  float* cstate, long long S, long long Spad, int T, int npass, cudaStream_t st) {
+    CUtensorMap mXhi, mXlo, mYhi, mYlo;
+    const int In = lw.in_features;
+    if (!make_act_map(&mXhi, xhi, S, T, In) || !make_act_map(&mYhi, yhi, S, T, 2 * kImuH)) return -1;
+    if (npass == 3) {
+        if (!make_act_map(&mXlo, xlo, S, T, In) || !make_act_map(&mYlo, ylo, S, T, 2 * kImuH)) return -1;
+    } else {
+        mXlo = mXhi;
+        mYlo = mYhi;
+    }
+    static bool attr_set[64] = {false};
+    if (first_use_on_device(attr_set)) {
+        cudaFuncSetAttribute(lstm_tc_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::SMEM_BYTES);
+        cudaFuncSetAttribute(lstm_tc_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES);
+    }
+    const CUtensorMap& mWhi = *reinterpret_cast<const CUtensorMap*>(&lw.map_hi);
+    const CUtensorMap& mWlo = *reinterpret_cast<const CUtensorMap*>(&lw.map_lo);
+    StepParams p{};
+    p.S = (int)S;
+    p.m_tiles = (int)((S + BM - 1) / BM);
+    p.kb_in = In / BK;
+    p.in_features = In;
+    p.T = T;
+    p.bias = lw.bias;
+    p.cstate = cstate;
+    p.Spad = Spad;
+    p.out_hi = static_cast<__half*>(yhi);
+    p.out_lo = npass == 3 ? static_cast<__half*>(ylo) : nullptr;
+    p.out_scale = lw.out_scale;
+    const int chunk_opt = h->tc_kb_chunk;
+    const int total = p.m_tiles * 2 * kNTiles;
+    const int grid = total < h->sm_count ? total : h->sm_count;
+    for (int step = 0; step < T; ++step) {
+        p.kb_rec = step > 0 ? kImuH / BK : 0;
+        p.kb_chunk = (npass == 3 && chunk_opt > 0) ? chunk_opt : (p.kb_in + p.kb_rec);
+        p.tt0 = step;
+        p.tt1 = T - 1 - step;
+        p.tp0 = step > 0 ? step - 1 : 0;
+        p.tp1 = step > 0 ? p.tt1 + 1 : p.tt1;
+        ++g_launches;
+        if (npass == 3)
+            lstm_tc_step_kernel<3><<<grid, kThreads, Cfg<3>::SMEM_BYTES, st>>>(mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
+        else
+            lstm_tc_step_kernel<1><<<grid, kThreads, Cfg<1>::SMEM_BYTES, st>>>(mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
+    }
+    return 0;
+}
+
+void tc_imu_fc1(const float* imu, const PackedGemm& fc1, void* uhi, void* ulo, long long rows, cudaStream_t st) {
+    if (rows <= 0) return;
+    ++g_launches;
+    imu_fc1_split_kernel<<<(unsigned)((rows + FC1_ROWS - 1) / FC1_ROWS), 256, 0, st>>>(
+        imu, fc1.w.p, fc1.bias.p, fc1.ldw, static_cast<__half*>(uhi), static_cast<__half*>(ulo), rows);
+}
+void tc_imu_pool(const void* yhi, const void* ylo, const float* attn, void* shi, void* slo, long long F, int n,
+                 cudaStream_t st) {
+    if (F <= 0) return;
+    ++g_launches;
+    imu_pool_split_kernel<<<(unsigned)F, 128, 0, st>>>(static_cast<const __half*>(yhi), static_cast<const __half*>(ylo),
+                                                       attn, static_cast<__half*>(shi), static_cast<__half*>(slo), F, n);
+}
+void tc_imu_decode(const void* ghi, const void* glo, const float* fc2, float* R, float* t, long long F, cudaStream_t st) {
+    if (F <= 0) return;
+    ++g_launches;
+    imu_decode_split_kernel<<<(unsigned)((F + 7) / 8), 256, 0, st>>>(static_cast<const __half*>(ghi),
+                                                                     static_cast<const __half*>(glo), fc2, R, t, F);
+}
+void tc_unsplit(const void* hi, const void* lo, float* out, long long n, cudaStream_t st) {
+    if (n <= 0) return;
+    ++g_launches;
+    unsplit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<const __half*>(hi),
+                                                                static_cast<const __half*>(lo), out, n);
+}
+
+}  // namespace mmego

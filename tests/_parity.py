@@ -91,11 +91,26 @@ def check_gcn_golden(h):
     assert maxerr(out, g["out"]) < 2e-5 * float(g["out"].abs().max())
 
 
-def check_imu_golden(h, tag="synth", nb=1):
+# IMU_Net precision modes of the library ("imu_gemm" option) and their tolerances on (R entries, t metres, joint metres).
+# 0 = fp32 FFMA, 1 = tcgen05 fp16x3 (default; fp32-grade), 2 = tcgen05 single-pass fp16 (the "reduced precision" mode that
+# BASELINE.json asks to be reported separately).  The seeded stand-in IMU weights produce 6D vectors of norm ~0.05, so the
+# Gram-Schmidt normalisation amplifies upstream error ~20x; a trained checkpoint (norm ~1) would sit far below these.
+IMU_MODE_TOL = {0: (ROT_TOL, POS_TOL, POS_TOL), 1: (ROT_TOL, POS_TOL, POS_TOL), 2: (2e-3, 1e-4, 3e-3)}
+
+
+def check_imu_golden(h, tag="synth", nb=1, mode=None):
     g = golden("imu_seed0.npz")
-    R, t = h.imu_forward(dev(h, g["imu_" + tag][:nb]))
-    assert maxerr(R, g["R_" + tag][:nb]) < ROT_TOL
-    assert maxerr(t, g["t_" + tag][:nb]) < POS_TOL
+    rt, tt, _ = IMU_MODE_TOL[1 if mode is None else mode]
+    if mode is not None:
+        h.set_option("imu_gemm", mode)
+    try:
+        R, t = h.imu_forward(dev(h, g["imu_" + tag][:nb]))
+    finally:
+        if mode is not None:
+            h.set_option("imu_gemm", 1 if h.require_cuda else 0)
+    er, et = maxerr(R, g["R_" + tag][:nb]), maxerr(t, g["t_" + tag][:nb])
+    assert er < rt and et < tt, (er, et)
+    return er, et
 
 
 def check_transforms(h, F=37, n=15):
@@ -132,7 +147,7 @@ def check_metrics(h):
     assert np.allclose(sums.cpu().numpy(), 2 * got, rtol=1e-12)
 
 
-def check_pipeline_vs_oracle(h, B=2, L=20, N=128, n_imu=20, seed=11, distinct=True, imu_seed=0):
+def check_pipeline_vs_oracle(h, B=2, L=20, N=128, n_imu=20, seed=11, distinct=True, imu_seed=0, mode=None):
     """Whole chain on synthetic snippets vs the oracle pipeline (IMU_Net with the seeded stand-in weights)."""
     sb = O.synth_batch(B, L=L, N=N, n_imu=n_imu, seed=seed, distinct_skeletons=distinct)
     up_sd, lo_sd = checkpoints()
@@ -142,15 +157,27 @@ def check_pipeline_vs_oracle(h, B=2, L=20, N=128, n_imu=20, seed=11, distinct=Tr
                 upper_l=torch.empty(B, L, 15, 3, device=h.device), lower_l=torch.empty(B, L, 8, 3, device=h.device))
     tg = dev(h, ref["pred"] + 0.03)
     sums = torch.zeros(_capi.SUMS_LEN, dtype=torch.float64, device=h.device)
-    pred = h.pipeline_forward(dev(h, sb["imu"]), x, dev(h, sb["skl"]), tg, sums, outs=outs)
-    assert maxerr(outs["R"], ref["R"]) < ROT_TOL
-    assert maxerr(outs["t"], ref["t"]) < POS_TOL
-    assert maxerr(outs["upper_l"], ref["upper_l"]) < POS_TOL
-    assert maxerr(x, ref["x_after_lower"]) < 1e-5
-    assert maxerr(outs["lower_l"], ref["lower_l"]) < POS_TOL
-    assert maxerr(pred, ref["pred"]) < POS_TOL
+    rt, tt, pt = IMU_MODE_TOL[1 if mode is None else mode]
+    if mode is not None:
+        h.set_option("imu_gemm", mode)
+    try:
+        pred = h.pipeline_forward(dev(h, sb["imu"]), x, dev(h, sb["skl"]), tg, sums, outs=outs)
+    finally:
+        if mode is not None:
+            h.set_option("imu_gemm", 1 if h.require_cuda else 0)
+    errs = dict(R=maxerr(outs["R"], ref["R"]), t=maxerr(outs["t"], ref["t"]), upper=maxerr(outs["upper_l"], ref["upper_l"]),
+                lower=maxerr(outs["lower_l"], ref["lower_l"]), pred=maxerr(pred, ref["pred"]),
+                x=maxerr(x, ref["x_after_lower"]))
+    assert errs["R"] < rt and errs["t"] < tt, errs
+    assert errs["upper"] < pt and errs["pred"] < pt, errs
+    # the cloud left behind in x went through R(R(p - t) - t) with |p| up to ~3 m, so it carries up to ~2 |p| times the
+    # error of R; it is a side effect, not a joint position, and gets the correspondingly scaled bound
+    assert errs["x"] < 6 * max(rt, errs["R"]), errs
+    # a point whose x-key sits within the mode's error of the 64th/65th boundary may swap in the top-64 set; in the
+    # fp32-grade modes that must not happen on these seeds
+    assert errs["lower"] < (pt if (mode is None or mode < 2) else 10 * pt), errs
     assert sums.cpu().numpy()[43] == B * L
-    return pred
+    return pred, errs
 
 
 def check_errors(h):

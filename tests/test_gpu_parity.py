@@ -46,13 +46,43 @@ def test_metrics(handle):
     P.check_metrics(handle)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("tag", ["synth", "real"])
-def test_imu_golden(handle, tag):
-    P.check_imu_golden(handle, tag, 2)
+def test_imu_golden(handle, tag, mode):
+    """IMU_Net against the reference-generated vectors in all three precision modes (see _parity.IMU_MODE_TOL)."""
+    er, et = P.check_imu_golden(handle, tag, 2, mode=mode)
+    print(f"imu_gemm={mode} {tag}: max|dR|={er:.2e} max|dt|={et:.2e}")
+
+
+def test_default_mode_is_tensor_core_fp16x3(handle):
+    # the default must be the tcgen05 path; flipping the option changes the kernels that run
+    sb = P.O.synth_batch(1, seed=3)
+    n0 = handle.launch_count()
+    handle.imu_forward(sb["imu"].cuda())
+    n_tc = handle.launch_count() - n0
+    handle.set_option("imu_gemm", 0)
+    n0 = handle.launch_count()
+    handle.imu_forward(sb["imu"].cuda())
+    n_ffma = handle.launch_count() - n0
+    handle.set_option("imu_gemm", 1)
+    assert n_tc == 83 and n_ffma == 83          # fc1 + 4 layers x 20 steps + pool + decode
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_pipeline_other_precision_modes(handle, mode):
+    _, errs = P.check_pipeline_vs_oracle(handle, B=4, seed=11, mode=mode)
+    print(f"imu_gemm={mode}: {errs}")
 
 
 def test_pipeline_config_shape(handle):
-    P.check_pipeline_vs_oracle(handle, B=4, L=20, N=128, n_imu=20, seed=11)
+    _, errs = P.check_pipeline_vs_oracle(handle, B=4, L=20, N=128, n_imu=20, seed=11)
+    print(errs)
+
+
+def test_pipeline_larger_batch_multi_tile(handle):
+    # 200 snippets = 4000 sequences: 32 sequence tiles per step in the tcgen05 kernel, last tile ragged
+    _, errs = P.check_pipeline_vs_oracle(handle, B=200, seed=12)
+    print(errs)
 
 
 @pytest.mark.parametrize("B,L,N,n", [(3, 5, 70, 3), (1, 1, 64, 1), (2, 40, 256, 20), (5, 20, 512, 7)])
