@@ -159,6 +159,9 @@ def main():
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)
 
+    # the JSON line must be the only thing on stdout: NCCL's version banner (NCCL_DEBUG=VERSION) goes there too
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     from mmego_b200 import _capi, synth

@@ -309,7 +309,7 @@ __device__ __forceinline__ void store_split(__half* hi, __half* lo, long long i,
 }
 
 // fc1 + ReLU (Net/IMU_Net.py:79): imu [rows,15] -> u [rows,512] as fp16 hi/lo planes.  HBM-bound (writes 2 KB per row).
-constexpr int FC1_ROWS = 16;
+constexpr int FC1_ROWS = 128;
 __global__ void __launch_bounds__(256) imu_fc1_split_kernel(const float* __restrict__ imu, const float* __restrict__ w,
                                                             const float* __restrict__ b, int ldw,
                                                             __half* __restrict__ uhi, __half* __restrict__ ulo,
@@ -317,10 +317,11 @@ __global__ void __launch_bounds__(256) imu_fc1_split_kernel(const float* __restr
     __shared__ float xs[FC1_ROWS][16];
     const int tid = threadIdx.x;
     const long long r0 = (long long)blockIdx.x * FC1_ROWS;
-    {
-        const int r = tid / 16, c = tid % 16;
+    for (int i = tid; i < FC1_ROWS * 16; i += 256) {
+        const int r = i / 16, c = i % 16;
         xs[r][c] = (c < kImuFeat && (r0 + r) < rows) ? imu[(r0 + r) * kImuFeat + c] : 0.f;
     }
+    // thread owns output channels 2*tid, 2*tid+1 of every row of the tile; its 30 weights stay in registers
     float w0[kImuFeat], w1[kImuFeat];
 #pragma unroll
     for (int k = 0; k < kImuFeat; ++k) {
@@ -329,9 +330,9 @@ __global__ void __launch_bounds__(256) imu_fc1_split_kernel(const float* __restr
     }
     const float b0 = b[2 * tid], b1 = b[2 * tid + 1];
     __syncthreads();
+    const int nr = (int)((rows - r0) < FC1_ROWS ? (rows - r0) : FC1_ROWS);
 #pragma unroll 4
-    for (int r = 0; r < FC1_ROWS; ++r) {
-        if (r0 + r >= rows) break;
+    for (int r = 0; r < nr; ++r) {
         float a0 = b0, a1 = b1;
 #pragma unroll
         for (int k = 0; k < kImuFeat; ++k) {
