@@ -332,15 +332,28 @@ void plan_upper(Carver& c, long long B, int L, UpperWs& w) {
 // ---------------------------------------------------------------------------------------------- Lower_Net schedule
 struct LowerWs {
     float *uh, *ya, *u, *y[2], *kf, *ak, *f0, *f1, *o;
+    void *p_y0[2], *p_ya[2], *p_u[2], *p_y[2][2];     // tensor-core path: fp16 hi/lo planes
     SmallLstmWs lstm;
 };
-void plan_lower(Carver& c, long long B, int L, LowerWs& w) {
+void plan_lower(Carver& c, long long B, int L, LowerWs& w, bool tc) {
     const size_t F = (size_t)B * L, FV = F * kGcnV;
     w.uh = c.f(F * 45);
-    w.ya = c.f(FV * 128);       // aggregated input of the widest layer: 2 * 64
-    w.u = c.f(FV * 128);        // graph-conv output of the widest layer
-    w.y[0] = c.f(FV * 128);
-    w.y[1] = c.f(FV * 128);
+    if (tc) {
+        auto plane = [&](size_t elems) { return static_cast<void*>(c.f((elems + 1) / 2)); };
+        for (int k = 0; k < 2; ++k) {
+            w.p_y0[k] = plane(FV * 8);
+            w.p_ya[k] = plane(FV * 128);
+            w.p_u[k] = plane(FV * 128);
+            w.p_y[0][k] = plane(FV * 128);
+            w.p_y[1][k] = plane(FV * 128);
+        }
+        w.ya = w.u = w.y[0] = w.y[1] = nullptr;
+    } else {
+        w.ya = c.f(FV * 128);       // aggregated input of the widest layer: 2 * 64
+        w.u = c.f(FV * 128);        // graph-conv output of the widest layer
+        w.y[0] = c.f(FV * 128);
+        w.y[1] = c.f(FV * 128);
+    }
     w.kf = c.f(FV * 64);
     w.ak = c.f(F * 192);
     plan_small_lstm(c, B, L, w.lstm);
@@ -376,6 +389,45 @@ void run_gcn(mmego_handle* h, const float* y0, int B, int L, const LowerWs& w, c
     gemm_seg(a, W.fcn, y, 128);
     a.f6_period = L * kGcnV;
     run_gemm(h, a, EPI_F6, st, 64);
+}
+
+#ifndef MMEGO_EMUL
+// ST-GCN on tensor cores: y0 planes [F*15][8] (data_bn applied) -> kf fp32 [B][64][L*15]
+int run_gcn_tc(mmego_handle* h, int B, int L, const LowerWs& w, cudaStream_t st) {
+    const LowerWeights& W = h->lower;
+    const long long F = (long long)B * L, FV = F * kGcnV;
+    const int RP = L * kGcnV;
+    void* const* y = w.p_y0;
+    int ystride = 8, creal = 3;
+    int rc = 0;
+    for (int i = 0; i < 3; ++i) {
+        const int cout = W.gcn[i].cout;
+        const int os = i == 0 ? 8 : 2 * creal;
+        if (i == 0) {   // channels 6, 7 of the 8-wide aggregated rows are padding
+            cudaMemsetAsync(w.p_ya[0], 0, (size_t)FV * 8 * 2, st);
+            cudaMemsetAsync(w.p_ya[1], 0, (size_t)FV * 8 * 2, st);
+        }
+        tc_gcn_agg(y[0], y[1], W.gcn[i].ahat.p, w.p_ya[0], w.p_ya[1], F, creal, ystride, os, h->sm_count, st);
+        rc |= tc_gcn_gemm(h, W.tc_gconv[i], w.p_ya[0], w.p_ya[1], os, 1, nullptr, nullptr, 0, kGcnV, 1, w.p_u[0], w.p_u[1],
+                          nullptr, B, RP, st);
+        void* const* out = w.p_y[i & 1];
+        rc |= tc_gcn_gemm(h, W.tc_tconv[i], w.p_u[0], w.p_u[1], cout, 9, y[0], y[1], ystride, 0, 1, out[0], out[1], nullptr,
+                          B, RP, st);
+        y = out;
+        ystride = creal = cout;
+    }
+    rc |= tc_gcn_gemm(h, W.tc_fcn, y[0], y[1], 128, 1, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, w.kf, B, RP, st);
+    return rc;
+}
+#endif
+
+bool use_gcn_tc(const mmego_handle* h) {
+#ifdef MMEGO_EMUL
+    (void)h;
+    return false;
+#else
+    return h->gcn_gemm != 0;
+#endif
 }
 
 size_t imu_ws_bytes(const mmego_handle* h, long long Bc, int L, int n) {
@@ -425,6 +477,7 @@ int mmego_create(mmego_handle** out, int device) {
     h->imu_gemm = 0;
 #else
     h->imu_gemm = tc_supported() ? 1 : 0;      // default: tcgen05 fp16x3 (fp32-grade); 0 = FFMA fp32; 2 = tcgen05 fp16
+    h->gcn_gemm = tc_supported() ? 1 : 0;
 #endif
     *out = h;
     return MMEGO_OK;
@@ -458,6 +511,16 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
         if (value != 0 && h->imu.ready && !h->imu.tc_ready) return fail(h, MMEGO_ESTATE, "imu_gemm=%lld: tensor-core weight packing failed at set_weights", value);
 #endif
         h->imu_gemm = (int)value;
+        return MMEGO_OK;
+    }
+    if (!strcmp(key, "gcn_gemm")) {
+        if (value < 0 || value > 1) return fail(h, MMEGO_EINVAL, "gcn_gemm must be 0 (fp32 FFMA) or 1 (tcgen05 fp16x3)");
+#ifdef MMEGO_EMUL
+        if (value != 0) return fail(h, MMEGO_EINVAL, "gcn_gemm=1 needs the sm_100a build");
+#else
+        if (value != 0 && !tc_supported()) return fail(h, MMEGO_EARCH, "gcn_gemm=1: cuTensorMapEncodeTiled is not available");
+#endif
+        h->gcn_gemm = (int)value;
         return MMEGO_OK;
     }
     if (!strcmp(key, "tc_kb_chunk")) {
@@ -532,6 +595,9 @@ int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const 
         } else if (net == MMEGO_NET_LOWER) {
             LowerWeights& W = h->lower;
             W.ready = false;
+            W.tc_ready = false;
+            bool tc_ok = true;
+            (void)tc_ok;
             ok &= upload(h, pack_lower_frame(sd), W.frame);
             const std::string gp = "keyEncoder.gcn.";
             ok &= upload(h, pack_data_bn(sd, gp), W.data_bn);
@@ -541,8 +607,16 @@ int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const 
                 ok &= upload(h, L.ahat, W.gcn[i].ahat) && upload(h, L.gconv, W.gcn[i].gconv) && upload(h, L.tconv, W.gcn[i].tconv);
                 W.gcn[i].cin = L.cin;
                 W.gcn[i].cout = L.cout;
+#ifndef MMEGO_EMUL
+                if (tc_supported()) tc_ok = tc_ok && tc_pack_gemm(h, L.gconv, W.tc_gconv[i]) && tc_pack_gemm(h, L.tconv, W.tc_tconv[i]);
+#endif
             }
-            ok &= upload(h, pack_linear(sd.get(gp + "fcn.weight", 64 * 128), sd.get(gp + "fcn.bias", 64), 64, {128}), W.fcn);
+            HostPackedGemm fcn = pack_linear(sd.get(gp + "fcn.weight", 64 * 128), sd.get(gp + "fcn.bias", 64), 64, {128});
+            ok &= upload(h, fcn, W.fcn);
+#ifndef MMEGO_EMUL
+            if (tc_supported()) tc_ok = tc_ok && tc_pack_gemm(h, fcn, W.tc_fcn);
+            W.tc_ready = tc_supported() && tc_ok;
+#endif
             for (int l = 0; l < 3; ++l) {
                 HostSmallLstm s = pack_small_lstm(sd, "fusion.rnn_pk.", l, l == 0 ? 192 : 128);
                 ok &= upload(h, s.ih, W.lstm[l].ih) && upload(h, s.whh, W.lstm[l].whh);
@@ -574,7 +648,7 @@ size_t mmego_workspace_bytes(const mmego_handle* h, int stage, int B, int L, int
         plan_upper(c, B, L, w);
     } else if (stage == MMEGO_STAGE_LOWER || stage == MMEGO_STAGE_GCN) {
         LowerWs w;
-        plan_lower(c, B, L, w);
+        plan_lower(c, B, L, w, use_gcn_tc(h));
     } else if (stage == MMEGO_STAGE_PIPELINE) {
         // R, t, upper_l, lower_l + the largest stage workspace (stages run back to back and reuse it)
         const size_t F = (size_t)B * L;
@@ -585,7 +659,7 @@ size_t mmego_workspace_bytes(const mmego_handle* h, int stage, int B, int L, int
             Carver s(nullptr); UpperWs w; plan_upper(s, B, L, w); best = std::max(best, s.off);
         }
         {
-            Carver s(nullptr); LowerWs w; plan_lower(s, B, L, w); best = std::max(best, s.off);
+            Carver s(nullptr); LowerWs w; plan_lower(s, B, L, w, use_gcn_tc(h)); best = std::max(best, s.off);
         }
         c.f(best / sizeof(float) + 64);
     } else {
@@ -685,15 +759,23 @@ int mmego_lower_forward(mmego_handle* h, const float* upper_l, float* x, const f
     const long long F = (long long)B * L;
     Carver c(ws);
     LowerWs w;
-    plan_lower(c, B, L, w);
+    const bool gtc = use_gcn_tc(h);
+    plan_lower(c, B, L, w, gtc);
     const LowerWeights& W = h->lower;
-    float* y0 = w.y[1];   // layer 0 writes y[0], so y[1] is free to hold the 3-channel input
-    launch_gcn_prep(upper_l, R, t, W.data_bn.p, w.uh, y0, F, st);                         // Lower_Net.py:229, GCN.py:339-344
-    tap(h, "lower.uh", w.uh, (size_t)F * 45 * 4, st);
-    {
+    if (gtc) {
+#ifndef MMEGO_EMUL
+        if (!W.tc_ready) return fail(h, MMEGO_ESTATE, "lower_forward: tensor-core ST-GCN weights are not packed");
         Prof p(h, "lower.gcn", st);
+        tc_gcn_prep(upper_l, R, t, W.data_bn.p, w.uh, w.p_y0[0], w.p_y0[1], F, st);       // Lower_Net.py:229, GCN.py:339-344
+        if (run_gcn_tc(h, B, L, w, st)) return fail(h, MMEGO_ECUDA, "lower_forward: tensor-core ST-GCN launch failed");
+#endif
+    } else {
+        float* y0 = w.y[1];   // layer 0 writes y[0], so y[1] is free to hold the 3-channel input
+        Prof p(h, "lower.gcn", st);
+        launch_gcn_prep(upper_l, R, t, W.data_bn.p, w.uh, y0, F, st);                     // Lower_Net.py:229, GCN.py:339-344
         run_gcn(h, y0, B, L, w, st);
     }
+    tap(h, "lower.uh", w.uh, (size_t)F * 45 * 4, st);
     tap(h, "lower.K", w.kf, (size_t)F * kGcnV * 64 * 4, st);
     {
         Prof p(h, "lower.frame", st);
@@ -728,10 +810,19 @@ int mmego_gcn_extract_feature(mmego_handle* h, const float* x, float* out, int B
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Carver c(ws);
     LowerWs w;
-    plan_lower(c, B, T, w);
-    float* y0 = w.y[1];
-    launch_gcn_prep_raw(x, h->lower.data_bn.p, y0, B, T, st);
-    run_gcn(h, y0, B, T, w, st);
+    const bool gtc = use_gcn_tc(h);
+    plan_lower(c, B, T, w, gtc);
+    if (gtc) {
+#ifndef MMEGO_EMUL
+        if (!h->lower.tc_ready) return fail(h, MMEGO_ESTATE, "gcn_extract_feature: tensor-core weights are not packed");
+        tc_gcn_prep_raw(x, h->lower.data_bn.p, w.p_y0[0], w.p_y0[1], B, T, st);
+        if (run_gcn_tc(h, B, T, w, st)) return fail(h, MMEGO_ECUDA, "gcn_extract_feature: tensor-core launch failed");
+#endif
+    } else {
+        float* y0 = w.y[1];
+        launch_gcn_prep_raw(x, h->lower.data_bn.p, y0, B, T, st);
+        run_gcn(h, y0, B, T, w, st);
+    }
     CUDA_TRY(h, cudaMemcpyAsync(out, w.kf, (size_t)B * T * kGcnV * 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(h, cudaGetLastError());
     h->launches = g_launches;

@@ -1,0 +1,502 @@
+// gemm_tc.cu -- the ST-GCN key encoder of Lower_Net (Net/GCN.py:332-355, Net/Lower_Net.py:149-167) on the tensor cores.
+//
+// Activations are channel-last rows (snippet b, row r = frame*15 + joint) stored as fp16 hi/lo planes [B][RP][C]
+// (RP = L*15 rows per snippet) of 2^4 * value.  Every convolution of the network is a row GEMM:
+//   graph conv   U  = relu( [Y A_0 | Y A_1] Wg^T + bias[joint] )            (aggregation = gcn_agg_split_kernel)
+//   temporal     Y' = relu( sum_tau U[row + (tau-4)*15] Wt_tau^T + Y Wr^T + b )   (9 row-shifted K segments + residual)
+//   fcn          E  = Y Wf^T + b, stored as the reference's raw [64][L*15] block (Net/GCN.py:352-353)
+// One persistent tcgen05 kernel serves all of them: CTA tile = 128 rows of ONE snippet x all N <= 128 output channels,
+// operands by TMA from a 3-D tensor map (channel, row-in-snippet, snippet): a shifted row window that leaves the snippet
+// is zero-filled by the TMA unit, which is exactly the (9,1) convolution's temporal zero padding; channels beyond C
+// (C = 8 or 32 < the 64-wide K block) are zero-filled the same way.  Precision scheme and warp roles are those of
+// lstm_tc.cu (fp16x3 split products, K chunks accumulated in TMEM and drained into fp32 registers).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstring>
+
+#include "internal.h"
+#include "pack.h"
+#include "tc_common.cuh"
+
+namespace mmego {
+
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128, BK = 64;
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = 128 + kEpiWarps * 32;   // 640
+constexpr int A_TILE = BM * BK * 2;              // 16 KB per plane
+constexpr float kGcnActScale = 16.0f, kGcnActInv = 1.0f / 16.0f;
+
+template <int BN>
+struct Cfg {
+    static constexpr int W_TILE = BN * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * (A_TILE + W_TILE);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;    // 64, 128, 256: powers of two
+    static constexpr int COLS_PER_THREAD = BN / 4;                       // 8, 16, 32
+};
+
+struct GemmTcParams {
+    int B, RP, rtiles;       // snippets, rows per snippet, row tiles per snippet
+    int n0, kb0, kb1;        // # of A0 segments (1 or 9), K blocks per A0 segment, K blocks of the A1 segment (0 = none)
+    int shift_step;          // rows between consecutive A0 segments (15 = one frame); segment s is shifted (s - n0/2)*step
+    int kb_chunk;
+    const float* bias;       // [N] or [rowmod][N]
+    int rowmod;
+    int relu;
+    int N;                   // == BN
+    float out_scale;         // 1 / (weight scale * activation scale)
+    __half* out_hi;          // planes [B][RP][N] (epilogue 0)
+    __half* out_lo;
+    float* out_f6;           // fp32 [B][N][RP] (epilogue 1), used when out_hi == nullptr
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant__ CUtensorMap mA0lo,
+               const __grid_constant__ CUtensorMap mA1hi, const __grid_constant__ CUtensorMap mA1lo,
+               const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, const GemmTcParams p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + C::STAGES;
+    uint64_t* tfull = bars + 2 * C::STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.B * p.rtiles;
+    const int kb_a0 = p.n0 * p.kb0;
+    const int kb_total = kb_a0 + p.kb1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&mA0hi);
+        prefetch_tensormap(&mA0lo);
+        prefetch_tensormap(&mWhi);
+        prefetch_tensormap(&mWlo);
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], kEpiWarps);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_holder, C::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+      if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int b = tile / p.rtiles, r0 = (tile % p.rtiles) * BM;
+                for (int kbi = 0; kbi < kb_total; ++kbi) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                    uint8_t* sw = sa + 2 * A_TILE;
+                    if (kbi < kb_a0) {
+                        const int seg = kbi / p.kb0, kb = kbi - seg * p.kb0;
+                        const int shift = (seg - p.n0 / 2) * p.shift_step;
+                        tma_load_3d(sa, &mA0hi, &full[stage], kb * BK, r0 + shift, b);
+                        tma_load_3d(sa + A_TILE, &mA0lo, &full[stage], kb * BK, r0 + shift, b);
+                    } else {
+                        const int kb = kbi - kb_a0;
+                        tma_load_3d(sa, &mA1hi, &full[stage], kb * BK, r0, b);
+                        tma_load_3d(sa + A_TILE, &mA1lo, &full[stage], kb * BK, r0, b);
+                    }
+                    tma_load_2d(sw, &mWhi, &full[stage], kbi * BK, 0);
+                    tma_load_2d(sw + C::W_TILE, &mWlo, &full[stage], kbi * BK, 0);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+      } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0 /*fp16*/);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t cc = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int c0 = 0; c0 < kb_total; c0 += p.kb_chunk, ++cc) {
+                    const uint32_t buf = cc & 1, bph = (cc >> 1) & 1;
+                    mbar_wait(&tempty[buf], bph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * BN;
+                    const int c1 = min(kb_total, c0 + p.kb_chunk);
+                    for (int kb = c0; kb < c1; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+                        const uint32_t a_lo = a_hi + A_TILE;
+                        const uint32_t w_hi = a_hi + 2 * A_TILE;
+                        const uint32_t w_lo = w_hi + C::W_TILE;
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t da_hi = make_sw128_kmajor_desc(a_hi + k * 32);
+                            const uint64_t dw_hi = make_sw128_kmajor_desc(w_hi + k * 32);
+                            const uint64_t da_lo = make_sw128_kmajor_desc(a_lo + k * 32);
+                            const uint64_t dw_lo = make_sw128_kmajor_desc(w_lo + k * 32);
+                            mma_f16_ss(d_tmem, da_hi, dw_lo, idesc, (kb > c0) || (k > 0));
+                            mma_f16_ss(d_tmem, da_lo, dw_hi, idesc, 1);
+                            mma_f16_ss(d_tmem, da_hi, dw_hi, idesc, 1);
+                        }
+                        mma_commit(&empty[stage]);
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    mma_commit(&tfull[buf]);
+                }
+            }
+        }
+        __syncwarp();
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        // ===================================================================== epilogue (16 warps)
+        constexpr int CPT = C::COLS_PER_THREAD;
+        const int q = warp & 3;
+        const int part = (warp - 4) >> 2;
+        const int col0 = part * CPT;
+        uint32_t cc = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int b = tile / p.rtiles, r0 = (tile % p.rtiles) * BM;
+            float acc[CPT];
+            for (int c0 = 0; c0 < kb_total; c0 += p.kb_chunk, ++cc) {
+                const uint32_t buf = cc & 1, bph = (cc >> 1) & 1;
+                mbar_wait(&tfull[buf], bph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col0);
+#pragma unroll
+                for (int g = 0; g < CPT / 8; ++g) {
+                    uint32_t r[8];
+                    tmem_ld_x8(taddr + g * 8, r);
+                    tmem_ld_wait();
+                    if (c0 == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[g * 8 + j] = __uint_as_float(r[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[g * 8 + j] += __uint_as_float(r[j]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);
+            }
+            const int r = r0 + q * 32 + lane;          // row inside the snippet
+            if (r < p.RP) {
+                const float* bias = p.bias + (p.rowmod > 0 ? (r % p.rowmod) * p.N : 0) + col0;
+                float v[CPT];
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    float x = fmaf(acc[j], p.out_scale, __ldg(bias + j));
+                    v[j] = p.relu ? fmaxf(x, 0.f) : x;
+                }
+                if (p.out_hi) {
+                    const long long o = ((long long)b * p.RP + r) * p.N + col0;
+#pragma unroll
+                    for (int g = 0; g < CPT / 8; ++g) {
+                        uint32_t ph[4], pl[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float v0 = fminf(v[g * 8 + 2 * j] * kGcnActScale, 65000.f);
+                            const float v1 = fminf(v[g * 8 + 2 * j + 1] * kGcnActScale, 65000.f);
+                            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+                            const __half l0 = __float2half_rn(v0 - __half2float(h0));
+                            const __half l1 = __float2half_rn(v1 - __half2float(h1));
+                            ph[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                            pl[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                        }
+                        *reinterpret_cast<uint4*>(p.out_hi + o + g * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                        *reinterpret_cast<uint4*>(p.out_lo + o + g * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    }
+                } else {
+                    float* dst = p.out_f6 + ((long long)b * p.N + col0) * p.RP + r;
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) dst[(long long)j * p.RP] = v[j];
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- memory-bound glue
+// Lower_Net front (Net/Lower_Net.py:229, Net/GCN.py:339-344): Transform2H of the upper-body joints + data_bn.
+//   upper [F,15,3] -> uh [F,45] fp32 (also the 45 extra inputs of fusion.fc0), y0 planes [F*15][8] (3 channels + zeros)
+__global__ void gcn_prep_split_kernel(const float* __restrict__ upper, const float* __restrict__ R,
+                                      const float* __restrict__ t, const float* __restrict__ bn, float* __restrict__ uh,
+                                      __half* __restrict__ yhi, __half* __restrict__ ylo, long long F) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (frame, joint)
+    if (i >= F * kGcnV) return;
+    const long long f = i / kGcnV;
+    const int v = (int)(i % kGcnV);
+    const float* r = R + f * 9;
+    const float* tt = t + f * 3;
+    const float* p = upper + i * 3;
+    const float dx = p[0] - tt[0], dy = p[1] - tt[1], dz = p[2] - tt[2];
+    float h[3];
+    h[0] = r[0] * dx + r[1] * dy + r[2] * dz;
+    h[1] = r[3] * dx + r[4] * dy + r[5] * dz;
+    h[2] = r[6] * dx + r[7] * dy + r[8] * dz;
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float val = 0.f;
+        if (c < 3) {
+            uh[i * 3 + c] = h[c];
+            val = (h[c] * bn[v * 3 + c] + bn[45 + v * 3 + c]) * kGcnActScale;
+        }
+        hi[c] = __float2half_rn(val);
+        lo[c] = __float2half_rn(val - __half2float(hi[c]));
+    }
+    *reinterpret_cast<uint4*>(yhi + i * 8) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(ylo + i * 8) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// standalone GCN.Model.extract_feature entry: x [B,3,T,15] -> y0 planes with data_bn applied
+__global__ void gcn_prep_raw_split_kernel(const float* __restrict__ x, const float* __restrict__ bn,
+                                          __half* __restrict__ yhi, __half* __restrict__ ylo, int B, int T) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, t, v)
+    const long long total = (long long)B * T * kGcnV;
+    if (i >= total) return;
+    const int v = (int)(i % kGcnV);
+    const long long bt = i / kGcnV;
+    const int tt = (int)(bt % T);
+    const long long b = bt / T;
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float val = 0.f;
+        if (c < 3) val = (x[((b * 3 + c) * T + tt) * kGcnV + v] * bn[v * 3 + c] + bn[45 + v * 3 + c]) * kGcnActScale;
+        hi[c] = __float2half_rn(val);
+        lo[c] = __float2half_rn(val - __half2float(hi[c]));
+    }
+    *reinterpret_cast<uint4*>(yhi + i * 8) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(ylo + i * 8) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// neighbourhood aggregation (einsum of Net/GCN.py:62, commuted in front of the 1x1 conv):
+//   ya[(f,w)][k*C + c] = sum_v y[(f,v)][c] * Ahat[k][v][w];   y planes have row stride CS, ya planes row stride OS
+__global__ void gcn_agg_split_kernel(const __half* __restrict__ yhi, const __half* __restrict__ ylo,
+                                     const float* __restrict__ ahat, __half* __restrict__ ohi, __half* __restrict__ olo,
+                                     long long F, int C, int CS, int OS) {
+    __shared__ float sa[2 * kGcnV * kGcnV];
+    for (int i = threadIdx.x; i < 2 * kGcnV * kGcnV; i += blockDim.x) sa[i] = ahat[i];
+    __syncthreads();
+    const long long total = F * kGcnV * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long long fw = i / C;
+        const int w = (int)(fw % kGcnV);
+        const long long f = fw / kGcnV;
+        const long long base = f * kGcnV * CS + c;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int v = 0; v < kGcnV; ++v) {
+            const float val = __half2float(yhi[base + v * CS]) + __half2float(ylo[base + v * CS]);
+            a0 = fmaf(val, sa[v * kGcnV + w], a0);
+            a1 = fmaf(val, sa[kGcnV * kGcnV + v * kGcnV + w], a1);
+        }
+        const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);     // values already carry the 2^4 scale
+        ohi[fw * OS + c] = h0;
+        olo[fw * OS + c] = __float2half_rn(a0 - __half2float(h0));
+        ohi[fw * OS + C + c] = h1;
+        olo[fw * OS + C + c] = __float2half_rn(a1 - __half2float(h1));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        if (q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// planes [B][RP][C] fp16; box = 64 channels x 128 rows x 1 snippet
+bool make_rows_map(CUtensorMap* m, const void* base, int B, int RP, int C) {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)RP, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)RP * C * 2};
+    cuuint32_t box[3] = {BK, BM, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool make_w_map(CUtensorMap* m, const void* base, int rows, int K) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {BK, (cuuint32_t)rows};
+    cuuint32_t es[2] = {1, 1};
+    return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN>
+void launch_gemm_tc(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l,
+                    const CUtensorMap& wh, const CUtensorMap& wl, const GemmTcParams& p, int sm_count, cudaStream_t st) {
+    static bool attr_set[64] = {false};
+    if (first_use_on_device(attr_set))
+        cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+    const int total = p.B * p.rtiles;
+    const int grid = total < sm_count ? total : sm_count;
+    ++g_launches;
+    gemm_tc_kernel<BN><<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(a0h, a0l, a1h, a1l, wh, wl, p);
+}
+
+}  // namespace
+
+// ================================================================================================ host interface
+// Re-packs a host GEMM (segments padded to 16) into fp16 hi/lo planes with every segment padded to 64 columns.
+bool tc_pack_gemm(mmego_handle* h, const HostPackedGemm& g, TcGemmW& out) {
+    int K64 = 0;
+    for (int s = 0; s < g.nseg; ++s) K64 += (g.k[s] + 63) / 64 * 64;
+    std::vector<float> w((size_t)g.N * K64, 0.f);
+    float wmax = 0.f;
+    for (int n = 0; n < g.N; ++n) {
+        int src = 0, dst = 0;
+        for (int s = 0; s < g.nseg; ++s) {
+            for (int k = 0; k < g.k[s]; ++k) {
+                const float v = g.w[(size_t)n * g.ldw + src + k];
+                w[(size_t)n * K64 + dst + k] = v;
+                wmax = std::max(wmax, std::fabs(v));
+            }
+            src += g.kpad[s];
+            dst += (g.k[s] + 63) / 64 * 64;
+        }
+    }
+    int e = 11;
+    while (e > 0 && wmax * std::ldexp(1.0f, e) > 30000.f) --e;
+    const float scale = std::ldexp(1.0f, e);
+    std::vector<__half> hi(w.size()), lo(w.size());
+    for (size_t i = 0; i < w.size(); ++i) {
+        const float v = w[i] * scale;
+        const __half a = __float2half_rn(v);
+        hi[i] = a;
+        lo[i] = __float2half_rn(v - __half2float(a));
+    }
+    cudaSetDevice(h->device);
+    auto up = [&](const void* src, size_t bytes, void** dst) {
+        if (cudaMalloc(dst, bytes) != cudaSuccess) return false;
+        h->owned.push_back(*dst);
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    void *dhi = nullptr, *dlo = nullptr, *db = nullptr;
+    if (!up(hi.data(), hi.size() * 2, &dhi) || !up(lo.data(), lo.size() * 2, &dlo) ||
+        !up(g.bias.data(), g.bias.size() * 4, &db))
+        return false;
+    out.whi = dhi;
+    out.wlo = dlo;
+    out.bias = static_cast<float*>(db);
+    out.N = g.N;
+    out.K64 = K64;
+    out.out_scale = 1.0f / scale;
+    return make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_hi), dhi, g.N, K64) &&
+           make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_lo), dlo, g.N, K64);
+}
+
+// One GEMM of the chain.  a0: planes [B][RP][c0] read through n0 shifted windows; a1 (optional): planes [B][RP][c1].
+int tc_gcn_gemm(mmego_handle* h, const TcGemmW& w, const void* a0hi, const void* a0lo, int c0, int n0, const void* a1hi,
+                const void* a1lo, int c1, int rowmod, int relu, void* outhi, void* outlo, float* out_f6, int B, int RP,
+                cudaStream_t st) {
+    CUtensorMap m0h, m0l, m1h, m1l;
+    if (!make_rows_map(&m0h, a0hi, B, RP, c0) || !make_rows_map(&m0l, a0lo, B, RP, c0)) return -1;
+    if (a1hi) {
+        if (!make_rows_map(&m1h, a1hi, B, RP, c1) || !make_rows_map(&m1l, a1lo, B, RP, c1)) return -1;
+    } else {
+        m1h = m0h;
+        m1l = m0l;
+    }
+    GemmTcParams p{};
+    p.B = B;
+    p.RP = RP;
+    p.rtiles = (RP + BM - 1) / BM;
+    p.n0 = n0;
+    p.kb0 = (c0 + BK - 1) / BK;
+    p.kb1 = a1hi ? (c1 + BK - 1) / BK : 0;
+    p.shift_step = kGcnV;
+    p.kb_chunk = h->tc_kb_chunk > 0 ? h->tc_kb_chunk : (p.n0 * p.kb0 + p.kb1);
+    p.bias = w.bias;
+    p.rowmod = rowmod;
+    p.relu = relu;
+    p.N = w.N;
+    p.out_scale = w.out_scale * kGcnActInv;
+    p.out_hi = static_cast<__half*>(outhi);
+    p.out_lo = static_cast<__half*>(outlo);
+    p.out_f6 = out_f6;
+    if ((p.n0 * p.kb0 + p.kb1) * BK != w.K64) return -2;
+    const CUtensorMap& wh = *reinterpret_cast<const CUtensorMap*>(&w.map_hi);
+    const CUtensorMap& wl = *reinterpret_cast<const CUtensorMap*>(&w.map_lo);
+    if (w.N == 128) launch_gemm_tc<128>(m0h, m0l, m1h, m1l, wh, wl, p, h->sm_count, st);
+    else if (w.N == 64) launch_gemm_tc<64>(m0h, m0l, m1h, m1l, wh, wl, p, h->sm_count, st);
+    else if (w.N == 32) launch_gemm_tc<32>(m0h, m0l, m1h, m1l, wh, wl, p, h->sm_count, st);
+    else return -3;
+    return 0;
+}
+
+void tc_gcn_prep(const float* upper, const float* R, const float* t, const float* bn, float* uh, void* yhi, void* ylo,
+                 long long F, cudaStream_t st) {
+    const long long total = F * kGcnV;
+    if (total <= 0) return;
+    ++g_launches;
+    gcn_prep_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(upper, R, t, bn, uh, static_cast<__half*>(yhi),
+                                                                           static_cast<__half*>(ylo), F);
+}
+void tc_gcn_prep_raw(const float* x, const float* bn, void* yhi, void* ylo, int B, int T, cudaStream_t st) {
+    const long long total = (long long)B * T * kGcnV;
+    if (total <= 0) return;
+    ++g_launches;
+    gcn_prep_raw_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, bn, static_cast<__half*>(yhi),
+                                                                               static_cast<__half*>(ylo), B, T);
+}
+void tc_gcn_agg(const void* yhi, const void* ylo, const float* ahat, void* ohi, void* olo, long long F, int C, int CS,
+                int OS, int sm_count, cudaStream_t st) {
+    const long long total = F * kGcnV * C;
+    if (total <= 0) return;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    ++g_launches;
+    gcn_agg_split_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __half*>(yhi), static_cast<const __half*>(ylo),
+                                                           ahat, static_cast<__half*>(ohi), static_cast<__half*>(olo), F,
+                                                           C, CS, OS);
+}
+
+}  // namespace mmego

@@ -130,6 +130,17 @@ struct TcLstmLayer {
     float out_scale = 1.f;     // 2^-e
 };
 
+// a GEMM weight packed for gemm_tc.cu: fp16 hi/lo planes [N][K64] of 2^e W, every K segment padded to 64
+struct TcGemmW {
+    alignas(64) unsigned char map_hi[128];
+    alignas(64) unsigned char map_lo[128];
+    void* whi = nullptr;
+    void* wlo = nullptr;
+    float* bias = nullptr;
+    int N = 0, K64 = 0;
+    float out_scale = 1.f;
+};
+
 struct ImuWeights {
     bool ready = false;
     bool tc_ready = false;
@@ -153,6 +164,8 @@ struct GcnLayerWeights {
 };
 struct LowerWeights {
     bool ready = false;
+    bool tc_ready = false;
+    TcGemmW tc_gconv[3], tc_tconv[3], tc_fcn;
     DevBuf frame;      // folded per-point MLP + to_q/to_k/to_v blob (point_layout.h)
     DevBuf data_bn;    // [45] scale, [45] offset
     GcnLayerWeights gcn[3];
@@ -182,6 +195,16 @@ void tc_imu_pool(const void* yhi, const void* ylo, const float* attn, void* shi,
                  cudaStream_t st);
 void tc_imu_decode(const void* ghi, const void* glo, const float* fc2, float* R, float* t, long long F, cudaStream_t st);
 void tc_unsplit(const void* hi, const void* lo, float* out, long long n, cudaStream_t st);
+// ST-GCN on tensor cores (gemm_tc.cu)
+bool tc_pack_gemm(mmego_handle* h, const HostPackedGemm& g, TcGemmW& out);
+int tc_gcn_gemm(mmego_handle* h, const TcGemmW& w, const void* a0hi, const void* a0lo, int c0, int n0, const void* a1hi,
+                const void* a1lo, int c1, int rowmod, int relu, void* outhi, void* outlo, float* out_f6, int B, int RP,
+                cudaStream_t st);
+void tc_gcn_prep(const float* upper, const float* R, const float* t, const float* bn, float* uh, void* yhi, void* ylo,
+                 long long F, cudaStream_t st);
+void tc_gcn_prep_raw(const float* x, const float* bn, void* yhi, void* ylo, int B, int T, cudaStream_t st);
+void tc_gcn_agg(const void* yhi, const void* ylo, const float* ahat, void* ohi, void* olo, long long F, int C, int CS,
+                int OS, int sm_count, cudaStream_t st);
 #endif
 
 }  // namespace mmego
@@ -202,6 +225,7 @@ struct mmego_handle {
     long long imu_chunk = 2048;
     int imu_gemm = -1;        // -1: pick at first use (1 when the tcgen05 path is available, else 0)
     int tc_precise_act = 0;
+    int gcn_gemm = 0;         // ST-GCN GEMMs: 0 = fp32 FFMA, 1 = tcgen05 fp16x3 (default when available)
     int tc_kb_chunk = 2;      // fp16x3 mode: K blocks (of 64) per TMEM partial accumulation
     mmego::ImuWeights imu;
     mmego::UpperWeights upper;

@@ -33,8 +33,19 @@ def test_upper_lower_real_sample16(handle):
     P.check_upper_lower_golden(handle, "sample16.npz")
 
 
-def test_gcn(handle):
-    P.check_gcn_golden(handle)
+@pytest.mark.parametrize("gcn_gemm", [0, 1])
+def test_gcn(handle, gcn_gemm):
+    """GCN.Model.extract_feature vs the reference-generated vector: fp32 FFMA GEMMs and the tcgen05 fp16x3 kernel."""
+    err = P.check_gcn_golden(handle, gcn_gemm)
+    print(f"gcn_gemm={gcn_gemm}: relative max error {err:.2e}")
+
+
+def test_lower_with_ffma_gcn(handle):
+    handle.set_option("gcn_gemm", 0)
+    try:
+        P.check_upper_lower_golden(handle, "synth3.npz")
+    finally:
+        handle.set_option("gcn_gemm", 1)
 
 
 def test_transforms(handle):
