@@ -60,6 +60,8 @@ const char* mmego_last_error(const mmego_handle* h);
  *          "imu_gemm"    (IMU_Net's H=512 LSTMs: 1 = tcgen05 fp16x3 split-precision tensor-core GEMM, fp32-grade, the
  *                         default; 2 = tcgen05 single-pass fp16, fastest, tolerance reported separately;
  *                         0 = fp32 FFMA GEMM),
+ *          "gcn_gemm"    (ST-GCN GEMMs: 1 = tcgen05 fp16x3, default; 0 = fp32 FFMA),
+ *          "host_chunk"  (mmego_infer_host: snippets per stage of its H2D / compute / D2H pipeline, default 1024),
  *          "tc_kb_chunk" (imu_gemm=1: K blocks of 64 accumulated in TMEM before draining into fp32 registers, default 2). */
 int mmego_set_option(mmego_handle* h, const char* key, long long value);
 
@@ -117,8 +119,9 @@ int mmego_pipeline_forward(mmego_handle* h, const float* imu, float* x, const fl
                            size_t ws_bytes, void* stream);
 
 /* Same chain with HOST buffers (the call a reference-side binding makes per batch): copies imu/data/skeleton/target
- * to the device, runs the pipeline, copies pred [B,L,21,3] and sums back.  Device staging is owned by the handle and
- * grows on demand.  data_host is NOT modified.  Synchronous on return. */
+ * to the device, runs the pipeline, copies pred [B,L,21,3] and sums back -- chunk-pipelined on three streams so that the
+ * copies of chunk i+1 / i-1 overlap the compute of chunk i.  Device staging is owned by the handle and grows on demand.
+ * data_host is NOT modified.  Synchronous on return.  Host buffers should be pinned for the copies to overlap. */
 int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_host, const float* initial_body_host,
                      const float* target_host, float* pred_host, double* sums_host, int B, int L, int N, int n_imu,
                      int body_index_mode, int b_offset, int B_global);

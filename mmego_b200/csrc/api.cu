@@ -489,6 +489,9 @@ int mmego_destroy(mmego_handle* h) {
     for (void* p : h->owned) cudaFree(p);
     if (h->stage_dev) cudaFree(h->stage_dev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    for (cudaEvent_t e : h->host_events) cudaEventDestroy(e);
     delete h;
     return MMEGO_OK;
 }
@@ -511,6 +514,11 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
         if (value != 0 && h->imu.ready && !h->imu.tc_ready) return fail(h, MMEGO_ESTATE, "imu_gemm=%lld: tensor-core weight packing failed at set_weights", value);
 #endif
         h->imu_gemm = (int)value;
+        return MMEGO_OK;
+    }
+    if (!strcmp(key, "host_chunk")) {
+        if (value <= 0) return fail(h, MMEGO_EINVAL, "host_chunk must be positive");
+        h->host_chunk = value;
         return MMEGO_OK;
     }
     if (!strcmp(key, "gcn_gemm")) {
@@ -899,9 +907,15 @@ int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_h
     if (!imu_host || !data_host || !initial_body_host) return fail(h, MMEGO_EINVAL, "infer_host: NULL argument");
     cudaSetDevice(h->device);
     if (!h->own_stream) CUDA_TRY(h, cudaStreamCreate(&h->own_stream));
+    if (!h->h2d_stream) CUDA_TRY(h, cudaStreamCreate(&h->h2d_stream));
+    if (!h->d2h_stream) CUDA_TRY(h, cudaStreamCreate(&h->d2h_stream));
     cudaStream_t st = h->own_stream;
+    // The batch is cut into chunks of `host_chunk` snippets: chunk i+1 is copied to the device while chunk i computes
+    // and chunk i-1's predictions travel back (three streams, two events per chunk).
+    const int Bc = (int)std::min<long long>(B, h->host_chunk);
+    const int nchunks = (B + Bc - 1) / Bc;
     const size_t F = (size_t)B * L;
-    const size_t ws_bytes = mmego_workspace_bytes(h, MMEGO_STAGE_PIPELINE, B, L, N, n_imu);
+    const size_t ws_bytes = mmego_workspace_bytes(h, MMEGO_STAGE_PIPELINE, Bc, L, N, n_imu);
     Carver c(nullptr);
     // staging layout: imu, data, body, target, pred, sums(double), ws
     auto plan = [&](Carver& k, float*& imu, float*& data, float*& body, float*& tg, float*& pred, float*& sums, float*& ws) {
@@ -925,21 +939,43 @@ int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_h
     }
     Carver k(h->stage_dev);
     plan(k, imu, data, body, tg, pred, sums, ws);
-    CUDA_TRY(h, cudaMemcpyAsync(imu, imu_host, F * n_imu * kImuFeat * sizeof(float), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(h, cudaMemcpyAsync(data, data_host, F * N * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(h, cudaMemcpyAsync(body, initial_body_host, (size_t)B_global * 60 * sizeof(float), cudaMemcpyHostToDevice, st));
-    const bool metrics = target_host && sums_host;
-    if (metrics) {
-        CUDA_TRY(h, cudaMemcpyAsync(tg, target_host, F * 63 * sizeof(float), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(h, cudaMemsetAsync(sums, 0, MMEGO_SUMS_LEN * sizeof(double), st));
+    while ((int)h->host_events.size() < 2 * nchunks) {
+        cudaEvent_t e;
+        CUDA_TRY(h, cudaEventCreate(&e));
+        h->host_events.push_back(e);
     }
-    int rc = mmego_pipeline_forward(h, imu, data, body, metrics ? tg : nullptr, pred, metrics ? reinterpret_cast<double*>(sums) : nullptr,
-                                    nullptr, nullptr, nullptr, nullptr, B, L, N, n_imu, body_index_mode, b_offset, B_global,
-                                    ws, ws_bytes + 256, st);
-    if (rc) return rc;
-    if (pred_host) CUDA_TRY(h, cudaMemcpyAsync(pred_host, pred, F * 63 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    const bool metrics = target_host && sums_host;
+    CUDA_TRY(h, cudaMemcpyAsync(body, initial_body_host, (size_t)B_global * 60 * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
+    if (metrics) CUDA_TRY(h, cudaMemsetAsync(sums, 0, MMEGO_SUMS_LEN * sizeof(double), h->h2d_stream));
+    for (int i = 0; i < nchunks; ++i) {
+        const size_t b0 = (size_t)i * Bc, nb = std::min<size_t>(Bc, B - b0), f0 = b0 * L, nf = nb * L;
+        CUDA_TRY(h, cudaMemcpyAsync(imu + f0 * n_imu * kImuFeat, imu_host + f0 * n_imu * kImuFeat,
+                                    nf * n_imu * kImuFeat * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
+        CUDA_TRY(h, cudaMemcpyAsync(data + f0 * N * 6, data_host + f0 * N * 6, nf * N * 6 * sizeof(float),
+                                    cudaMemcpyHostToDevice, h->h2d_stream));
+        if (metrics)
+            CUDA_TRY(h, cudaMemcpyAsync(tg + f0 * 63, target_host + f0 * 63, nf * 63 * sizeof(float), cudaMemcpyHostToDevice,
+                                        h->h2d_stream));
+        CUDA_TRY(h, cudaEventRecord(h->host_events[2 * i], h->h2d_stream));
+    }
+    for (int i = 0; i < nchunks; ++i) {
+        const size_t b0 = (size_t)i * Bc, nb = std::min<size_t>(Bc, B - b0), f0 = b0 * L, nf = nb * L;
+        CUDA_TRY(h, cudaStreamWaitEvent(st, h->host_events[2 * i], 0));
+        int rc = mmego_pipeline_forward(h, imu + f0 * n_imu * kImuFeat, data + f0 * N * 6, body, metrics ? tg + f0 * 63 : nullptr,
+                                        pred + f0 * 63, metrics ? reinterpret_cast<double*>(sums) : nullptr, nullptr, nullptr,
+                                        nullptr, nullptr, (int)nb, L, N, n_imu, body_index_mode, b_offset + (int)b0, B_global,
+                                        ws, ws_bytes + 256, st);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaEventRecord(h->host_events[2 * i + 1], st));
+        if (pred_host) {
+            CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->host_events[2 * i + 1], 0));
+            CUDA_TRY(h, cudaMemcpyAsync(pred_host + f0 * 63, pred + f0 * 63, nf * 63 * sizeof(float), cudaMemcpyDeviceToHost,
+                                        h->d2h_stream));
+        }
+    }
     if (metrics) CUDA_TRY(h, cudaMemcpyAsync(sums_host, sums, MMEGO_SUMS_LEN * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
+    CUDA_TRY(h, cudaStreamSynchronize(h->d2h_stream));
     return MMEGO_OK;
 }
 

@@ -235,5 +235,7 @@ struct mmego_handle {
     // host-API staging
     void* stage_dev = nullptr;
     size_t stage_bytes = 0;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
+    std::vector<cudaEvent_t> host_events;
+    long long host_chunk = 1024;   // snippets per H2D/compute/D2H pipeline stage of mmego_infer_host
 };

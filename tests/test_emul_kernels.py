@@ -73,3 +73,19 @@ def test_sharded_body_index(handle):
         ll = handle.lower_forward(g["upper_l"][b:b + 1].contiguous(), g["x1"][b:b + 1].clone(), g["skl"],
                                   g["R"][b:b + 1].contiguous(), g["t"][b:b + 1].contiguous(), b_offset=b, B_global=3)[0]
         assert P.maxerr(ll, g["lower_l"][b:b + 1]) < P.POS_TOL
+
+
+def test_infer_host_chunk_pipeline_matches_device_path(handle):
+    """mmego_infer_host cuts the batch into host_chunk-sized stages (b_offset/B_global keep the reference's
+    initial_body[r % B] indexing of the whole batch); results equal the one-shot device call."""
+    from oracle import mmego_oracle as O
+    sb = O.synth_batch(3, L=4, N=70, n_imu=2, seed=9, distinct_skeletons=True)
+    pred_d = handle.pipeline_forward(sb["imu"], sb["data"].clone(), sb["skl"])
+    tg = (pred_d + 0.01).contiguous()
+    handle.set_option("host_chunk", 2)
+    try:
+        pred_h, sums = handle.infer_host(sb["imu"], sb["data"], sb["skl"], tg)
+    finally:
+        handle.set_option("host_chunk", 1024)
+    assert torch.equal(pred_h, pred_d)
+    assert sums[43].item() == 12
