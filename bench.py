@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-snippets", type=int, default=256, help="snippets per CPU-baseline pass (bounded sample)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (repeatable)")
     ap.add_argument("--no-half", action="store_true", help="skip the extra pass in single-pass fp16 mode")
     ap.add_argument("--imu-gemm", type=int, default=None, help="0 fp32 FFMA, 1 tcgen05 fp16x3, 2 tcgen05 fp16 (default: library default)")
     args = ap.parse_args()
@@ -182,6 +183,9 @@ def main():
     pipe = MMEgoPipeline(dev, imu_state=None)
     if args.imu_gemm is not None:
         pipe.handle.set_option("imu_gemm", args.imu_gemm)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        pipe.handle.set_option(k, int(v))
     # this rank's shard of the global synthetic batch (seed depends on the rank; same distribution)
     sb = synth.batch(B, L=L, N=N_PTS, n_imu=N_IMU, seed=1234 + rank)
     imu_h, data_h, skl_h = sb["imu"].pin_memory(), sb["data"].pin_memory(), sb["skl"].pin_memory()

@@ -62,7 +62,8 @@ const char* mmego_last_error(const mmego_handle* h);
  *                         0 = fp32 FFMA GEMM),
  *          "gcn_gemm"    (ST-GCN GEMMs: 1 = tcgen05 fp16x3, default; 0 = fp32 FFMA),
  *          "host_chunk"  (mmego_infer_host: snippets per stage of its H2D / compute / D2H pipeline, default 1024),
- *          "tc_kb_chunk" (imu_gemm=1: K blocks of 64 accumulated in TMEM before draining into fp32 registers, default 2). */
+ *          "tc_kb_chunk" (imu_gemm=1: K blocks of 64 accumulated in TMEM before draining into fp32 registers, default 6),
+ *          "tc_cta_pair" (H=512 LSTM kernel on CTA pairs, cta_group::2 M=256 tiles, default 1). */
 int mmego_set_option(mmego_handle* h, const char* key, long long value);
 
 /* Replaces IMUNet.load / UpperNet.load / LowerNet.load (Net/IMU_Net.py:106-114, Net/Upper_Net.py:400-404,
@@ -140,6 +141,8 @@ long long mmego_launch_count(const mmego_handle* h);
 int mmego_profile_begin(mmego_handle* h);
 int mmego_profile_read(mmego_handle* h, const char* name, double* total_ms, long long* launches, long long* spans);
 int mmego_profile_end(mmego_handle* h);
+/* Cycle counters of the tensor-core LSTM kernel's instrumentation (option "tc_dbg" bit 2; diagnostics only). */
+int mmego_debug_stats(mmego_handle* h, unsigned long long* out8, int reset);
 
 #ifdef __cplusplus
 }

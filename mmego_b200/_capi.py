@@ -45,6 +45,7 @@ SIGNATURES = {
     "mmego_profile_begin": (_i, [_vp]),
     "mmego_profile_read": (_i, [_vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(_ll), C.POINTER(_ll)]),
     "mmego_profile_end": (_i, [_vp]),
+    "mmego_debug_stats": (_i, [_vp, C.POINTER(C.c_ulonglong), _i]),
 }
 
 PROFILE_SPANS = ("imu.fc1", "imu.lstm_step", "imu.pool", "imu.decode", "upper.point", "small_lstm", "upper.head_decode",
@@ -182,6 +183,11 @@ class Handle:
             if k.value:
                 out[name] = dict(ms=ms.value, launches=int(n.value), spans=int(k.value))
         return out
+
+    def debug_stats(self, reset=True):
+        buf = (C.c_ulonglong * 8)()
+        self._ck(self.lib.dll.mmego_debug_stats(self._h, buf, 1 if reset else 0), "debug_stats")
+        return list(buf)
 
     def profile_end(self):
         self._ck(self.lib.dll.mmego_profile_end(self._h), "profile_end")

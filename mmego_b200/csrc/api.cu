@@ -516,6 +516,14 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
         h->imu_gemm = (int)value;
         return MMEGO_OK;
     }
+    if (!strcmp(key, "tc_dbg")) {
+        h->tc_dbg = (int)value;
+        return MMEGO_OK;
+    }
+    if (!strcmp(key, "tc_cta_pair")) {
+        h->tc_cta_pair = value != 0;
+        return MMEGO_OK;
+    }
     if (!strcmp(key, "host_chunk")) {
         if (value <= 0) return fail(h, MMEGO_EINVAL, "host_chunk must be positive");
         h->host_chunk = value;
@@ -1015,6 +1023,16 @@ int mmego_profile_read(mmego_handle* h, const char* name, double* total_ms, long
     if (total_ms) *total_ms = ms;
     if (launches) *launches = n;
     if (spans) *spans = k;
+    return MMEGO_OK;
+}
+
+int mmego_debug_stats(mmego_handle* h, unsigned long long* out8, int reset) {
+    if (!h || !out8) return MMEGO_EINVAL;
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    if (!h->tc_stats) return MMEGO_OK;
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    CUDA_TRY(h, cudaMemcpy(out8, h->tc_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) CUDA_TRY(h, cudaMemset(h->tc_stats, 0, 8 * sizeof(unsigned long long)));
     return MMEGO_OK;
 }
 

@@ -64,7 +64,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant_
                const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, const GemmTcParams p) {
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + C::STAGES;

@@ -123,6 +123,8 @@ struct PackedSmallLstmLayer {  // H=64
 struct TcLstmLayer {
     alignas(64) unsigned char map_hi[128];
     alignas(64) unsigned char map_lo[128];
+    alignas(64) unsigned char map_hi2[128];    // same tensors, box of 128 rows: one CTA's half of a CTA pair's tile
+    alignas(64) unsigned char map_lo2[128];
     void* whi = nullptr;
     void* wlo = nullptr;
     float* bias = nullptr;     // [2][2048] packed row order
@@ -225,8 +227,11 @@ struct mmego_handle {
     long long imu_chunk = 2048;
     int imu_gemm = -1;        // -1: pick at first use (1 when the tcgen05 path is available, else 0)
     int tc_precise_act = 0;
+    void* tc_stats = nullptr; // device counters of the dbg & 4 instrumentation
+    int tc_dbg = 0;           // experiment switches of lstm_tc.cu (never set in product use)
+    int tc_cta_pair = 1;      // H=512 LSTM kernel: 1 = CTA pairs (cta_group::2, M = 256)
     int gcn_gemm = 0;         // ST-GCN GEMMs: 0 = fp32 FFMA, 1 = tcgen05 fp16x3 (default when available)
-    int tc_kb_chunk = 2;      // fp16x3 mode: K blocks (of 64) per TMEM partial accumulation
+    int tc_kb_chunk = 6;      // fp16x3 mode: K blocks (of 64) per TMEM partial accumulation (see lstm_tc.cu)
     mmego::ImuWeights imu;
     mmego::UpperWeights upper;
     mmego::LowerWeights lower;

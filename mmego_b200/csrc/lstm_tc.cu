@@ -47,12 +47,17 @@ constexpr uint32_t kTmemCols = 512;
 // a typical h ~ 0.05 would be a denormal and lose most of its 11 bits.
 constexpr float kActScale = 256.0f, kActInv = 1.0f / 256.0f;
 
-template <int NPASS>
+// NCTA = 2: a CTA pair (cta_group::2) shares one 256 x 256 accumulator tile pair: each CTA stages its own 128 sequences
+// of A and HALF of the weight tile, so a stage is 64 KB instead of 96 KB (3-deep ring instead of 2) and the weight bytes
+// that cross L2 -> shared memory halve.
+template <int NPASS, int NCTA>
 struct Cfg {
     static constexpr int PLANES = NPASS == 3 ? 2 : 1;
-    static constexpr int STAGE_BYTES = PLANES * (A_TILE + W_TILE);          // 96 KB / 48 KB
-    static constexpr int STAGES = NPASS == 3 ? 2 : 4;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int W_TILE_CTA = W_TILE / NCTA;
+    static constexpr int STAGE_BYTES = PLANES * (A_TILE + W_TILE_CTA);      // per CTA: 96 / 48 KB (1 CTA), 64 / 32 KB (pair)
+    static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 6 ? 6 : (196 * 1024) / STAGE_BYTES;
+    static constexpr int BIAS_BYTES = 2 * 4 * kImuH * 4;                    // both directions' bias vectors, staged once
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BIAS_BYTES;
 };
 
 struct StepParams {
@@ -70,30 +75,58 @@ struct StepParams {
     __half* out_lo;      // may be null (NPASS == 1)
     float out_scale;     // 2^-e
     int kb_chunk;        // K blocks accumulated in TMEM before the partial sum is drained into registers
+    unsigned long long* stats;   // dbg & 4: [0] epilogue cell-phase cycles, [1] epilogue wait-for-MMA cycles, [2] drain cycles,
+                         // [3] tiles, [4] MMA-thread cycles waiting for the epilogue, [5] waiting for TMA, [6] MMA issue cycles
+    int dbg;             // experiment switches (results are wrong when set): 1 = skip the cell math and stores, 2 = skip the TMEM drains
 };
 
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+// Gate non-linearities straight on the SFU instructions (MUFU.EX2 / MUFU.RCP, one instruction each; the CUDA
+// intrinsics wrap them in range-fixing code that triples the epilogue's instruction count).  Saturation is exact:
+// ex2 -> +inf gives rcp -> 0.  Absolute error <= 2e-7 on sigmoid and tanh.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+    return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * x)), 1.0f);
+}
+__device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po, float cprev, float& cn, float& h) {
+    cn = fmaf(sigmoid_fast(pf), cprev, sigmoid_fast(pi) * tanh_fast(pg));
+    h = sigmoid_fast(po) * tanh_fast(cn);
+}
 
-template <int NPASS>
+template <int NPASS, int NCTA>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtensorMap mXlo,
                     const __grid_constant__ CUtensorMap mYhi, const __grid_constant__ CUtensorMap mYlo,
                     const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo,
                     const StepParams p) {
-    using C = Cfg<NPASS>;
+    using C = Cfg<NPASS, NCTA>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space known to the compiler)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + C::STAGES;
     uint64_t* tfull = bars + 2 * C::STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* sbias = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = p.m_tiles * 2 * kNTiles;
+    for (int i = threadIdx.x; i < 2 * 4 * kImuH; i += kThreads) sbias[i] = p.bias[i];
+    // work items: (sequence-tile group, direction, unit tile); a group is NCTA consecutive sequence tiles, one per CTA
+    const int total_tiles = ((p.m_tiles + NCTA - 1) / NCTA) * 2 * kNTiles;
     const int kb_total = p.kb_in + p.kb_rec;
+    const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0;
+    const int first_item = blockIdx.x / NCTA, item_stride = gridDim.x / NCTA;
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&mXhi);
@@ -110,16 +143,22 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], kEpiWarps);
+            mbar_init(&tempty[a], NCTA * kEpiWarps);      // the leader's MMA thread waits for both CTAs' epilogues
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_holder, kTmemCols);
-        tmem_relinquish();
+        if (NCTA == 2) {
+            tmem_alloc_pair(tmem_holder, kTmemCols);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_holder, kTmemCols);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (NCTA == 2) cluster_sync_all();      // the peer's barriers must be initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
@@ -132,29 +171,37 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % kNTiles, dir = (tile / kNTiles) & 1, m = tile / (2 * kNTiles);
-                const int wrow = dir * 4 * kImuH + nt * BN;
+            for (int tile = first_item; tile < total_tiles; tile += item_stride) {
+                const int nt = tile % kNTiles, dir = (tile / kNTiles) & 1, m = (tile / (2 * kNTiles)) * NCTA + (int)rank;
+                const int wrow = dir * 4 * kImuH + nt * BN + (int)rank * (BN / NCTA);
                 const int tt = dir ? p.tt1 : p.tt0, tp = dir ? p.tp1 : p.tp0;
                 for (int kb = 0; kb < kb_total; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
                     uint8_t* sw = sa + C::PLANES * A_TILE;
-                    int wcol;
+                    int wcol, acol, at;
+                    const CUtensorMap *ahi, *alo;
                     if (kb < p.kb_in) {
-                        tma_load_3d(sa, &mXhi, &full[stage], kb * BK, tt, m * BM);
-                        if (NPASS == 3) tma_load_3d(sa + A_TILE, &mXlo, &full[stage], kb * BK, tt, m * BM);
-                        wcol = kb * BK;
+                        ahi = &mXhi; alo = &mXlo; acol = kb * BK; at = tt; wcol = kb * BK;
                     } else {
                         const int kr = kb - p.kb_in;
-                        tma_load_3d(sa, &mYhi, &full[stage], dir * kImuH + kr * BK, tp, m * BM);
-                        if (NPASS == 3)
-                            tma_load_3d(sa + A_TILE, &mYlo, &full[stage], dir * kImuH + kr * BK, tp, m * BM);
-                        wcol = p.in_features + kr * BK;
+                        ahi = &mYhi; alo = &mYlo; acol = dir * kImuH + kr * BK; at = tp; wcol = p.in_features + kr * BK;
                     }
-                    tma_load_2d(sw, &mWhi, &full[stage], wcol, wrow);
-                    if (NPASS == 3) tma_load_2d(sw + W_TILE, &mWlo, &full[stage], wcol, wrow);
+                    if (NCTA == 2) {
+                        // both CTAs' bytes are counted on the LEADER's barrier; only the leader arms it
+                        const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
+                        if (rank == 0) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+                        tma_load_3d_pair(sa, ahi, bar, acol, at, m * BM);
+                        if (NPASS == 3) tma_load_3d_pair(sa + A_TILE, alo, bar, acol, at, m * BM);
+                        tma_load_2d_pair(sw, &mWhi, bar, wcol, wrow);
+                        if (NPASS == 3) tma_load_2d_pair(sw + C::W_TILE_CTA, &mWlo, bar, wcol, wrow);
+                    } else {
+                        mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                        tma_load_3d(sa, ahi, &full[stage], acol, at, m * BM);
+                        if (NPASS == 3) tma_load_3d(sa + A_TILE, alo, &full[stage], acol, at, m * BM);
+                        tma_load_2d(sw, &mWhi, &full[stage], wcol, wrow);
+                        if (NPASS == 3) tma_load_2d(sw + C::W_TILE_CTA, &mWlo, &full[stage], wcol, wrow);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -167,25 +214,36 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
         // therefore cut into chunks of p.kb_chunk K-blocks: each chunk accumulates into one of the two TMEM buffers
         // from zero, and the epilogue warps drain finished chunks into fp32 registers (round-to-nearest adds) while
         // the next chunk is being multiplied.
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0 /*fp16*/);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(BM * NCTA, BN, 0 /*fp16*/);
             int stage = 0;
             uint32_t phase = 0;
             uint32_t cc = 0;      // running chunk counter (same sequence in the epilogue warps)
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            long long ms_epi = 0, ms_tma = 0;
+            const long long ms_start = (p.dbg & 4) ? clock64() : 0;
+            for (int tile = first_item; tile < total_tiles; tile += item_stride) {
                 for (int c0 = 0; c0 < kb_total; c0 += p.kb_chunk, ++cc) {
                     const uint32_t buf = cc & 1, bph = (cc >> 1) & 1;
+                    long long tm0 = 0;
+                    if (p.dbg & 4) tm0 = clock64();
                     mbar_wait(&tempty[buf], bph ^ 1);
                     tc_fence_after();
+                    if (p.dbg & 4) ms_epi += clock64() - tm0;
                     const uint32_t d_tmem = tmem_base + buf * BN;
                     const int c1 = min(kb_total, c0 + p.kb_chunk);
                     for (int kb = c0; kb < c1; ++kb) {
+                        if (p.dbg & 4) tm0 = clock64();
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
+                        if (p.dbg & 4) ms_tma += clock64() - tm0;
                         const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
                         const uint32_t a_lo = a_hi + A_TILE;
                         const uint32_t w_hi = a_hi + C::PLANES * A_TILE;
-                        const uint32_t w_lo = w_hi + W_TILE;
+                        const uint32_t w_lo = w_hi + C::W_TILE_CTA;
+                        auto mma = [&](uint64_t da, uint64_t dw, uint32_t accumulate) {
+                            if (NCTA == 2) mma_f16_ss_pair(d_tmem, da, dw, idesc, accumulate);
+                            else mma_f16_ss(d_tmem, da, dw, idesc, accumulate);
+                        };
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint64_t da_hi = make_sw128_kmajor_desc(a_hi + k * 32);
@@ -194,18 +252,27 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
                                 // small correction terms first, the large term last
                                 const uint64_t da_lo = make_sw128_kmajor_desc(a_lo + k * 32);
                                 const uint64_t dw_lo = make_sw128_kmajor_desc(w_lo + k * 32);
-                                mma_f16_ss(d_tmem, da_hi, dw_lo, idesc, (kb > c0) || (k > 0));
-                                mma_f16_ss(d_tmem, da_lo, dw_hi, idesc, 1);
-                                mma_f16_ss(d_tmem, da_hi, dw_hi, idesc, 1);
+                                mma(da_hi, dw_lo, (kb > c0) || (k > 0));
+                                mma(da_lo, dw_hi, 1);
+                                mma(da_hi, dw_hi, 1);
                             } else {
-                                mma_f16_ss(d_tmem, da_hi, dw_hi, idesc, (kb > c0) || (k > 0));
+                                mma(da_hi, dw_hi, (kb > c0) || (k > 0));
                             }
                         }
-                        mma_commit(&empty[stage]);      // frees the smem slot when these MMAs have read it
+                        // frees the smem slot (in both CTAs of a pair) when these MMAs have read it
+                        if (NCTA == 2) mma_commit_pair(&empty[stage], 3);
+                        else mma_commit(&empty[stage]);
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
-                    mma_commit(&tfull[buf]);            // partial accumulator complete -> epilogue
+                    // partial accumulator complete -> epilogue warps (of both CTAs)
+                    if (NCTA == 2) mma_commit_pair(&tfull[buf], 3);
+                    else mma_commit(&tfull[buf]);
                 }
+            }
+            if (p.dbg & 4) {
+                atomicAdd(p.stats + 4, (unsigned long long)ms_epi);
+                atomicAdd(p.stats + 5, (unsigned long long)ms_tma);
+                atomicAdd(p.stats + 6, (unsigned long long)(clock64() - ms_start));
             }
         }
         __syncwarp();
@@ -217,69 +284,85 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
         const int part = (warp - 4) >> 2;       // which 16 of the tile's 64 hidden units
         const int u0 = part * kUnitsPerEpiWarp;
         uint32_t cc = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int nt = tile % kNTiles, dir = (tile / kNTiles) & 1, m = tile / (2 * kNTiles);
+        long long st_wait = 0, st_drain = 0, st_cell = 0, st_tiles = 0;
+        const uint32_t tempty_remote[2] = {NCTA == 2 ? mapa_u32(smem_u32(&tempty[0]), 0) : 0,
+                                           NCTA == 2 ? mapa_u32(smem_u32(&tempty[1]), 0) : 0};
+        for (int tile = first_item; tile < total_tiles; tile += item_stride) {
+            const int nt = tile % kNTiles, dir = (tile / kNTiles) & 1, m = (tile / (2 * kNTiles)) * NCTA + (int)rank;
             float acc[4][kUnitsPerEpiWarp];     // i, f, g, o pre-activations (scaled) of this thread's row
+            const long long row = (long long)m * BM + q * 32 + lane;
+            const bool ok = row < p.S;
+            const bool has_state = p.kb_rec > 0;
+            float* cbase = p.cstate + ((long long)(dir * kImuH + nt * kUnitsPerTile + u0)) * p.Spad + row;
             for (int c0 = 0; c0 < kb_total; c0 += p.kb_chunk, ++cc) {
                 const uint32_t buf = cc & 1, bph = (cc >> 1) & 1;
+                if (c0 + p.kb_chunk >= kb_total && has_state && ok) {
+                    // last chunk of the tile: pull the cell state towards L2 now (no registers held), it is read below
+#pragma unroll
+                    for (int j = 0; j < kUnitsPerEpiWarp; ++j)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(cbase + (long long)j * p.Spad));
+                }
+                long long tq0 = 0;
+                if (p.dbg & 4) tq0 = clock64();
                 mbar_wait(&tfull[buf], bph);
                 tc_fence_after();
+                if (p.dbg & 4) { const long long t1 = clock64(); st_wait += t1 - tq0; tq0 = t1; }
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + u0);
+                if (!(p.dbg & 2))
 #pragma unroll
-                for (int g2 = 0; g2 < 2; ++g2) {
-                    uint32_t r0[16], r1[16];
-                    tmem_ld_x16(taddr + (2 * g2) * kUnitsPerTile, r0);
-                    tmem_ld_x16(taddr + (2 * g2 + 1) * kUnitsPerTile, r1);
+                for (int g = 0; g < 4; ++g) {        // one gate (16 columns) at a time keeps the temporaries at 16 registers
+                    uint32_t r0[16];
+                    tmem_ld_x16(taddr + g * kUnitsPerTile, r0);
                     tmem_ld_wait();
                     if (c0 == 0) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            acc[2 * g2][j] = __uint_as_float(r0[j]);
-                            acc[2 * g2 + 1][j] = __uint_as_float(r1[j]);
-                        }
+                        for (int j = 0; j < 16; ++j) acc[g][j] = __uint_as_float(r0[j]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            acc[2 * g2][j] += __uint_as_float(r0[j]);
-                            acc[2 * g2 + 1][j] += __uint_as_float(r1[j]);
-                        }
+                        for (int j = 0; j < 16; ++j) acc[g][j] += __uint_as_float(r0[j]);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[buf]);
+                if (lane == 0) {
+                    if (NCTA == 2) mbar_arrive_cluster(buf ? tempty_remote[1] : tempty_remote[0]);
+                    else mbar_arrive(&tempty[buf]);
+                }
+                if (p.dbg & 4) st_drain += clock64() - tq0;
             }
-            // ---- LSTM cell on the register-resident pre-activations
-            const long long row = (long long)m * BM + q * 32 + lane;
-            const bool ok = row < p.S;
-            const float* bias = p.bias + dir * 4 * kImuH + nt * BN + u0;
-            const bool has_state = p.kb_rec > 0;
-            float hv[kUnitsPerEpiWarp];
-            float* cbase = p.cstate + ((long long)(dir * kImuH + nt * kUnitsPerTile + u0)) * p.Spad + row;
+            if (p.dbg & 1) continue;
+            long long tc0 = 0;
+            if (p.dbg & 4) tc0 = clock64();
+            // ---- LSTM cell on the register-resident pre-activations (bias from shared memory: warp-wide broadcast reads)
+            const float* bias = sbias + dir * 4 * kImuH + nt * BN + u0;
+            float cprev[kUnitsPerEpiWarp];
 #pragma unroll
-            for (int j = 0; j < kUnitsPerEpiWarp; ++j) {
-                if ((j & 3) == 0) asm volatile("" ::: "memory");   // keep the bias / cell-state loads from being hoisted en bloc
-                const float pi = fmaf(acc[0][j], p.out_scale, __ldg(bias + j));
-                const float pf = fmaf(acc[1][j], p.out_scale, __ldg(bias + kUnitsPerTile + j));
-                const float pg = fmaf(acc[2][j], p.out_scale, __ldg(bias + 2 * kUnitsPerTile + j));
-                const float po = fmaf(acc[3][j], p.out_scale, __ldg(bias + 3 * kUnitsPerTile + j));
-                const float cprev = (has_state && ok) ? cbase[(long long)j * p.Spad] : 0.f;
-                const float cn = sigmoid_fast(pf) * cprev + sigmoid_fast(pi) * tanh_fast(pg);
-                hv[j] = sigmoid_fast(po) * tanh_fast(cn);
-                if (ok) cbase[(long long)j * p.Spad] = cn;
+            for (int j = 0; j < kUnitsPerEpiWarp; ++j)      // 16 independent coalesced loads in flight
+                cprev[j] = (has_state && ok) ? __ldcs(cbase + (long long)j * p.Spad) : 0.f;
+            uint32_t ph[8], pl[8];
+#pragma unroll
+            for (int j2 = 0; j2 < kUnitsPerEpiWarp / 2; ++j2) {
+                float hv2[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 2 * j2 + e;
+                    const float pi = fmaf(acc[0][j], p.out_scale, bias[j]);
+                    const float pf = fmaf(acc[1][j], p.out_scale, bias[kUnitsPerTile + j]);
+                    const float pg = fmaf(acc[2][j], p.out_scale, bias[2 * kUnitsPerTile + j]);
+                    const float po = fmaf(acc[3][j], p.out_scale, bias[3 * kUnitsPerTile + j]);
+                    float cn, hh;
+                    lstm_cell(pi, pf, pg, po, cprev[j], cn, hh);
+                    hv2[e] = hh * kActScale;
+                    if (ok) __stcs(cbase + (long long)j * p.Spad, cn);
+                }
+                const __half2 hh2 = __floats2half2_rn(hv2[0], hv2[1]);           // one packed conversion
+                const float2 back = __half22float2(hh2);
+                const __half2 ll2 = __floats2half2_rn(hv2[0] - back.x, hv2[1] - back.y);
+                ph[j2] = *reinterpret_cast<const uint32_t*>(&hh2);
+                pl[j2] = *reinterpret_cast<const uint32_t*>(&ll2);
             }
             if (ok) {
                 const long long o = (row * p.T + (dir ? p.tt1 : p.tt0)) * (2 * kImuH) + dir * kImuH + nt * kUnitsPerTile + u0;
-                uint32_t ph[8], pl[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float v0 = hv[2 * j] * kActScale, v1 = hv[2 * j + 1] * kActScale;
-                    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-                    const __half l0 = __float2half_rn(v0 - __half2float(h0));
-                    const __half l1 = __float2half_rn(v1 - __half2float(h1));
-                    ph[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                    pl[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-                }
                 uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
                 dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                 dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
@@ -289,14 +372,23 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
                     dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
                 }
             }
+            if (p.dbg & 4) { st_cell += clock64() - tc0; ++st_tiles; }
+        }
+        if ((p.dbg & 4) && warp == 4 && lane == 0) {
+            atomicAdd(p.stats + 0, (unsigned long long)st_cell);
+            atomicAdd(p.stats + 1, (unsigned long long)st_wait);
+            atomicAdd(p.stats + 2, (unsigned long long)st_drain);
+            atomicAdd(p.stats + 3, (unsigned long long)st_tiles);
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (NCTA == 2) cluster_sync_all();      // neither CTA may exit (or free TMEM) while the other still signals it
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (NCTA == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -493,11 +585,11 @@ bool make_act_map(CUtensorMap* m, const void* base, long long S, int T, int C) {
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-// weights [rows][K] fp16; box = 64 x 256
-bool make_w_map(CUtensorMap* m, const void* base, int rows, int K) {
+// weights [rows][K] fp16; box = 64 x box_rows (256 for a single CTA, 128 = one CTA's half for a CTA pair)
+bool make_w_map(CUtensorMap* m, const void* base, int rows, int K, int box_rows) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {BK, BN};
+    cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
     return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -559,8 +651,32 @@ bool tc_pack_layer(mmego_handle* h, const StateDict& sd, const std::string& pref
     out.K = K;
     out.out_scale = kActInv / scale;
     static_assert(sizeof(CUtensorMap) == sizeof(out.map_hi), "tensor map storage size");
-    return make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_hi), dhi, rows, K) &&
-           make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_lo), dlo, rows, K);
+    return make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_hi), dhi, rows, K, BN) &&
+           make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_lo), dlo, rows, K, BN) &&
+           make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_hi2), dhi, rows, K, BN / 2) &&
+           make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_lo2), dlo, rows, K, BN / 2);
+}
+
+template <int NPASS, int NCTA>
+void launch_step(int grid, cudaStream_t st, const CUtensorMap& mXhi, const CUtensorMap& mXlo, const CUtensorMap& mYhi,
+                 const CUtensorMap& mYlo, const CUtensorMap& mWhi, const CUtensorMap& mWlo, const StepParams& p) {
+    static bool attr_set[64] = {false};
+    if (first_use_on_device(attr_set))
+        cudaFuncSetAttribute(lstm_tc_step_kernel<NPASS, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg<NPASS, NCTA>::SMEM_BYTES);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg<NPASS, NCTA>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, lstm_tc_step_kernel<NPASS, NCTA>, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
 }
 
 // One bidirectional layer: x planes [S][T][In] -> y planes [S][T][1024]; cstate [2][512][Spad] fp32 scratch.
@@ -575,13 +691,9 @@ int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const
         mXlo = mXhi;
         mYlo = mYhi;
     }
-    static bool attr_set[64] = {false};
-    if (first_use_on_device(attr_set)) {
-        cudaFuncSetAttribute(lstm_tc_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::SMEM_BYTES);
-        cudaFuncSetAttribute(lstm_tc_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES);
-    }
-    const CUtensorMap& mWhi = *reinterpret_cast<const CUtensorMap*>(&lw.map_hi);
-    const CUtensorMap& mWlo = *reinterpret_cast<const CUtensorMap*>(&lw.map_lo);
+    const bool pair = h->tc_cta_pair != 0;
+    const CUtensorMap& mWhi = *reinterpret_cast<const CUtensorMap*>(pair ? &lw.map_hi2 : &lw.map_hi);
+    const CUtensorMap& mWlo = *reinterpret_cast<const CUtensorMap*>(pair ? &lw.map_lo2 : &lw.map_lo);
     StepParams p{};
     p.S = (int)S;
     p.m_tiles = (int)((S + BM - 1) / BM);
@@ -595,8 +707,15 @@ int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const
     p.out_lo = npass == 3 ? static_cast<__half*>(ylo) : nullptr;
     p.out_scale = lw.out_scale;
     const int chunk_opt = h->tc_kb_chunk;
-    const int total = p.m_tiles * 2 * kNTiles;
-    const int grid = total < h->sm_count ? total : h->sm_count;
+    p.dbg = h->tc_dbg;
+    if ((p.dbg & 4) && !h->tc_stats) {
+        cudaMalloc(&h->tc_stats, 8 * sizeof(unsigned long long));
+        cudaMemset(h->tc_stats, 0, 8 * sizeof(unsigned long long));
+    }
+    p.stats = static_cast<unsigned long long*>(h->tc_stats);
+    const int ncta = pair ? 2 : 1;
+    const int total = ((p.m_tiles + ncta - 1) / ncta) * 2 * kNTiles;          // work items (one per CTA or CTA pair)
+    int grid = (total < h->sm_count / ncta ? total : h->sm_count / ncta) * ncta;
     for (int step = 0; step < T; ++step) {
         p.kb_rec = step > 0 ? kImuH / BK : 0;
         p.kb_chunk = (npass == 3 && chunk_opt > 0) ? chunk_opt : (p.kb_in + p.kb_rec);
@@ -605,10 +724,13 @@ int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const
         p.tp0 = step > 0 ? step - 1 : 0;
         p.tp1 = step > 0 ? p.tt1 + 1 : p.tt1;
         ++g_launches;
-        if (npass == 3)
-            lstm_tc_step_kernel<3><<<grid, kThreads, Cfg<3>::SMEM_BYTES, st>>>(mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
-        else
-            lstm_tc_step_kernel<1><<<grid, kThreads, Cfg<1>::SMEM_BYTES, st>>>(mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
+        if (npass == 3) {
+            if (pair) launch_step<3, 2>(grid, st, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
+            else launch_step<3, 1>(grid, st, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
+        } else {
+            if (pair) launch_step<1, 2>(grid, st, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
+            else launch_step<1, 1>(grid, st, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
+        }
     }
     return 0;
 }
