@@ -539,6 +539,11 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
         h->gcn_gemm = (int)value;
         return MMEGO_OK;
     }
+    if (!strcmp(key, "tc_kb_chunk0")) {
+        if (value < 0 || value > 64) return fail(h, MMEGO_EINVAL, "tc_kb_chunk0 must be in 0..64");
+        h->tc_kb_chunk0 = (int)value;
+        return MMEGO_OK;
+    }
     if (!strcmp(key, "tc_kb_chunk")) {
         if (value < 0 || value > 64) return fail(h, MMEGO_EINVAL, "tc_kb_chunk must be in 0..64");
         h->tc_kb_chunk = (int)value;

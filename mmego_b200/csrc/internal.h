@@ -231,7 +231,8 @@ struct mmego_handle {
     int tc_dbg = 0;           // experiment switches of lstm_tc.cu (never set in product use)
     int tc_cta_pair = 1;      // H=512 LSTM kernel: 1 = CTA pairs (cta_group::2, M = 256)
     int gcn_gemm = 0;         // ST-GCN GEMMs: 0 = fp32 FFMA, 1 = tcgen05 fp16x3 (default when available)
-    int tc_kb_chunk = 6;      // fp16x3 mode: K blocks (of 64) per TMEM partial accumulation (see lstm_tc.cu)
+    int tc_kb_chunk0 = 8;     // ... of the first two chunks of every tile
+    int tc_kb_chunk = 4;      // fp16x3 mode: K blocks (of 64) per TMEM partial accumulation (see lstm_tc.cu)
     mmego::ImuWeights imu;
     mmego::UpperWeights upper;
     mmego::LowerWeights lower;

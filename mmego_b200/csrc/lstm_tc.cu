@@ -75,6 +75,8 @@ struct StepParams {
     __half* out_lo;      // may be null (NPASS == 1)
     float out_scale;     // 2^-e
     int kb_chunk;        // K blocks accumulated in TMEM before the partial sum is drained into registers
+    int kb_chunk0;       // length of the FIRST TWO chunks of a tile: they run while the epilogue warps are still busy with
+                         // the previous tile's cell update, so they are longer to give the MMA thread work until then
     unsigned long long* stats;   // dbg & 4: [0] epilogue cell-phase cycles, [1] epilogue wait-for-MMA cycles, [2] drain cycles,
                          // [3] tiles, [4] MMA-thread cycles waiting for the epilogue, [5] waiting for TMA, [6] MMA issue cycles
     int dbg;             // experiment switches (results are wrong when set): 1 = skip the cell math and stores, 2 = skip the TMEM drains
@@ -94,8 +96,16 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+// tanh: 1 - 2/(1 + e^2x) cancels for small |x| (absolute error ~3e-7 near 0, which dominated the error of h once the
+// accumulation error was fixed), so |x| < 0.25 uses the odd Taylor polynomial up to x^9 (truncation < 2e-8 relative).
 __device__ __forceinline__ float tanh_fast(float x) {
-    return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * x)), 1.0f);
+    const float x2 = x * x;
+    float p = fmaf(x2, 0.021869488536155203f, -0.053968253968253968f);   // 62/2835, -17/315
+    p = fmaf(x2, p, 0.13333333333333333f);                                // 2/15
+    p = fmaf(x2, p, -0.33333333333333333f);                               // -1/3
+    p = fmaf(x2 * x, p, x);
+    const float big = fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * x)), 1.0f);
+    return fabsf(x) < 0.25f ? p : big;
 }
 __device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po, float cprev, float& cn, float& h) {
     cn = fmaf(sigmoid_fast(pf), cprev, sigmoid_fast(pi) * tanh_fast(pg));
@@ -222,7 +232,8 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
             long long ms_epi = 0, ms_tma = 0;
             const long long ms_start = (p.dbg & 4) ? clock64() : 0;
             for (int tile = first_item; tile < total_tiles; tile += item_stride) {
-                for (int c0 = 0; c0 < kb_total; c0 += p.kb_chunk, ++cc) {
+                for (int c0 = 0, ci = 0; c0 < kb_total; ++cc, ++ci) {
+                    const int clen = ci < 2 ? p.kb_chunk0 : p.kb_chunk;
                     const uint32_t buf = cc & 1, bph = (cc >> 1) & 1;
                     long long tm0 = 0;
                     if (p.dbg & 4) tm0 = clock64();
@@ -230,7 +241,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
                     tc_fence_after();
                     if (p.dbg & 4) ms_epi += clock64() - tm0;
                     const uint32_t d_tmem = tmem_base + buf * BN;
-                    const int c1 = min(kb_total, c0 + p.kb_chunk);
+                    const int c1 = min(kb_total, c0 + clen);
                     for (int kb = c0; kb < c1; ++kb) {
                         if (p.dbg & 4) tm0 = clock64();
                         mbar_wait(&full[stage], phase);
@@ -267,6 +278,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
                     // partial accumulator complete -> epilogue warps (of both CTAs)
                     if (NCTA == 2) mma_commit_pair(&tfull[buf], 3);
                     else mma_commit(&tfull[buf]);
+                    c0 = c1;
                 }
             }
             if (p.dbg & 4) {
@@ -294,9 +306,11 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
             const bool ok = row < p.S;
             const bool has_state = p.kb_rec > 0;
             float* cbase = p.cstate + ((long long)(dir * kImuH + nt * kUnitsPerTile + u0)) * p.Spad + row;
-            for (int c0 = 0; c0 < kb_total; c0 += p.kb_chunk, ++cc) {
+            for (int c0 = 0, ci = 0; c0 < kb_total; ++cc, ++ci) {
+                const int clen = ci < 2 ? p.kb_chunk0 : p.kb_chunk;
+                const bool first = c0 == 0;
                 const uint32_t buf = cc & 1, bph = (cc >> 1) & 1;
-                if (c0 + p.kb_chunk >= kb_total && has_state && ok) {
+                if (c0 + clen >= kb_total && has_state && ok) {
                     // last chunk of the tile: pull the cell state towards L2 now (no registers held), it is read below
 #pragma unroll
                     for (int j = 0; j < kUnitsPerEpiWarp; ++j)
@@ -314,7 +328,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
                     uint32_t r0[16];
                     tmem_ld_x16(taddr + g * kUnitsPerTile, r0);
                     tmem_ld_wait();
-                    if (c0 == 0) {
+                    if (first) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) acc[g][j] = __uint_as_float(r0[j]);
                     } else {
@@ -329,6 +343,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
                     else mbar_arrive(&tempty[buf]);
                 }
                 if (p.dbg & 4) st_drain += clock64() - tq0;
+                c0 += clen;
             }
             if (p.dbg & 1) continue;
             long long tc0 = 0;
@@ -719,6 +734,7 @@ int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const
     for (int step = 0; step < T; ++step) {
         p.kb_rec = step > 0 ? kImuH / BK : 0;
         p.kb_chunk = (npass == 3 && chunk_opt > 0) ? chunk_opt : (p.kb_in + p.kb_rec);
+        p.kb_chunk0 = (npass == 3 && chunk_opt > 0) ? std::max(chunk_opt, h->tc_kb_chunk0) : p.kb_chunk;
         p.tt0 = step;
         p.tt1 = T - 1 - step;
         p.tp0 = step > 0 ? step - 1 : 0;

@@ -5,10 +5,10 @@ import json,sys
 d=json.loads(sys.stdin.read()); print('value',round(d['value']),'ms',round(d['ms_per_step'],1),'lstm ms',d['stage_ms_per_step']['imu.lstm_step'],'issued TF',round(d['roofline']['tensor_pipe_tflops_issued']),'clk',d['clocks']['sm_mhz'])"; }
 {
 set -e
-for a in "1 2 20 20" "1 3 5 3" "1 40 20 20" "1 7 20 11"; do
-  echo "defaults $a"; timeout 40 python scripts/tc_check.py $a 2>&1 | tail -3
-done
-for opts in "--opt tc_kb_chunk=6" "--opt tc_kb_chunk=8" "--opt tc_kb_chunk=4" "--imu-gemm 2"; do
+for c0 in 6 8; do for a in "1 3 5 3" "1 200 20 20"; do
+  echo "chunk0=$c0 chunk=4 $a"; TC_CHUNK0=$c0 TC_CHUNK=4 timeout 60 python scripts/tc_check.py $a 2>&1 | tail -3
+done; done
+for opts in "--opt tc_kb_chunk0=6" "--opt tc_kb_chunk0=8" "--opt tc_kb_chunk0=4"; do
   echo "$opts"; run $opts
 done
-} 2>&1 | tee gpurun_out/exp4.log
+} 2>&1 | tee gpurun_out/exp6.log

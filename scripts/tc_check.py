@@ -15,7 +15,8 @@ sd = O.synth_imu_state_dict(0)
 h.set_weights(_capi.NET_IMU, sd)
 h.set_option("imu_gemm", mode)
 h.set_option("tc_precise_act", int(os.environ.get("TC_PRECISE", "0")))
-h.set_option("tc_kb_chunk", int(os.environ.get("TC_CHUNK", "6")))
+h.set_option("tc_kb_chunk", int(os.environ.get("TC_CHUNK", "4")))
+h.set_option("tc_kb_chunk0", int(os.environ.get("TC_CHUNK0", "8")))
 h.set_option("tc_cta_pair", int(os.environ.get("TC_PAIR", "1")))
 sb = O.synth_batch(B, L=L, n_imu=n, seed=5)
 imu = sb["imu"]

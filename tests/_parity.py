@@ -155,7 +155,7 @@ def check_metrics(h):
     assert np.allclose(sums.cpu().numpy(), 2 * got, rtol=1e-12)
 
 
-def check_pipeline_vs_oracle(h, B=2, L=20, N=128, n_imu=20, seed=11, distinct=True, imu_seed=0, mode=None):
+def check_pipeline_vs_oracle(h, B=2, L=20, N=128, n_imu=20, seed=11, distinct=True, imu_seed=0, mode=None, pos_tol=None):
     """Whole chain on synthetic snippets vs the oracle pipeline (IMU_Net with the seeded stand-in weights)."""
     sb = O.synth_batch(B, L=L, N=N, n_imu=n_imu, seed=seed, distinct_skeletons=distinct)
     up_sd, lo_sd = checkpoints()
@@ -166,6 +166,8 @@ def check_pipeline_vs_oracle(h, B=2, L=20, N=128, n_imu=20, seed=11, distinct=Tr
     tg = dev(h, ref["pred"] + 0.03)
     sums = torch.zeros(_capi.SUMS_LEN, dtype=torch.float64, device=h.device)
     rt, tt, pt = IMU_MODE_TOL[1 if mode is None else mode]
+    if pos_tol is not None:
+        pt = pos_tol
     if mode is not None:
         h.set_option("imu_gemm", mode)
     try:

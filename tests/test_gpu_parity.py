@@ -98,7 +98,12 @@ def test_pipeline_larger_batch_multi_tile(handle):
 
 @pytest.mark.parametrize("B,L,N,n", [(3, 5, 70, 3), (1, 1, 64, 1), (2, 40, 256, 20), (5, 20, 512, 7)])
 def test_pipeline_ragged_and_sweep_shapes(handle, B, L, N, n):
-    P.check_pipeline_vs_oracle(handle, B=B, L=L, N=N, n_imu=n, seed=100 + B)
+    """Shapes away from Config/config.py (ragged tiles; N, L up to 4x).  With few IMU samples per frame (n = 1..7) the
+    stand-in IMU_Net's 6D vectors shrink to norm ~0.02, so the Gram-Schmidt step amplifies fp32-level noise ~50x: the
+    fp32 FFMA path sits at 3e-6 m here and the fp32-grade tensor-core path (about 3x the noise of plain fp32) at
+    ~1e-5 m, hence 2e-3 cm for these shapes; rotation entries keep the 2e-5 bound."""
+    _, errs = P.check_pipeline_vs_oracle(handle, B=B, L=L, N=N, n_imu=n, seed=100 + B, pos_tol=2e-5)
+    print(errs)
 
 
 def test_errors(handle):
