@@ -1,14 +1,14 @@
 #!/bin/bash
-# ncu evidence: launch list of one small bench pass + one full capture of the top kernel (selected by $1 regex, $2 skip)
+# ncu evidence at the bench's own shapes: launch list of one bench step + one full capture of the top kernel
 mkdir -p gpurun_out
 KREGEX=${1:-lstm_tc_step}
 SKIP=${2:-100}
-TAG=${3:-r01tc}
-CMD="python bench.py --batch 512 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-half"
+TAG=${3:-r01final}
+CMD="python bench.py --batch 2048 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-half"
 timeout 200 $CMD > gpurun_out/ncu_plain_${TAG}.log 2>&1 || { echo "plain run failed"; tail gpurun_out/ncu_plain_${TAG}.log; exit 1; }
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 500 -c 200 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launches_${TAG}.log 2>&1
-tail -3 gpurun_out/ncu_launches_${TAG}.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 210 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launches_${TAG}.log 2>&1
+tail -2 gpurun_out/ncu_launches_${TAG}.log
 timeout 200 $CMD > gpurun_out/ncu_plain2_${TAG}.log 2>&1 || exit 1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s ${SKIP} -c 3 -f -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
-tail -3 gpurun_out/ncu_full_${TAG}.log
-ls -la gpurun_out | head -30
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s ${SKIP} -c 3 -f -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
+tail -2 gpurun_out/ncu_full_${TAG}.log
+ls -la gpurun_out | grep ${TAG}
