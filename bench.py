@@ -279,33 +279,36 @@ def main():
 
     if rank == 0:
         peaks = measured_peaks()
-        # dominant kernel: the H=512 LSTM timestep launch (recurrent GEMM + fused cell), 160 launches per chunk
-        steps_fast = 2 * N_IMU                      # per chunk: 2 layers x n_imu steps with M = chunk*L sequences
-        steps_slow = 2 * L                          # 2 layers x L steps with M = chunk sequences
-        chunk = min(B, 512)
+        # dominant kernel: the H=512 LSTM timestep launch of rnn_fast (2 layers x n_imu steps per IMU chunk, both
+        # directions per launch, M = chunk*L sequences); rnn_slow's launches (M = chunk) are timed separately
+        chunk = min(B, 2048)
         nchunks = (B + chunk - 1) // chunk
-        fl = 0.0
+        fl_fast = 0.0
         for c in range(nchunks):
             bc = min(chunk, B - c * chunk)
-            fl += N_IMU * (lstm_step_flops(bc * L, H) + lstm_step_flops(bc * L, 2 * H))
-            fl += L * 2 * lstm_step_flops(bc, 2 * H)
+            fl_fast += N_IMU * (lstm_step_flops(bc * L, H) + lstm_step_flops(bc * L, 2 * H))
         peak = peaks["bf16_sustained"]
+        # DRAM bytes of one rnn_fast layer-1 step launch at M = 40,960 from `ncu --set full` (profiles/r01final_ncu_summary.txt)
+        NCU_TRAFFIC = {1: 1.463e9, 2: None, 0: None}
 
         def lstm_roofline(prof_, ms_, steps_, mode_):
-            lst = prof_.get("imu.lstm_step", dict(ms=0.0, launches=0))
-            per_launch_flops = fl * steps_ / max(1, lst["launches"])
+            lst = prof_.get("imu.lstm_fast", dict(ms=0.0, launches=0))
+            per_launch_flops = fl_fast * steps_ / max(1, lst["launches"])
             per_launch_ms = lst["ms"] / max(1, lst["launches"])
             ach = per_launch_flops / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
             passes = 3 if mode_ == 1 else 1
-            return {"bound": "tensor", "kernel": "H=512 LSTM timestep launch: " + KERNEL_NAMES[mode_],
-                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            slow = prof_.get("imu.lstm_slow", dict(ms=0.0))
+            return {"bound": "tensor", "kernel": "H=512 LSTM timestep launch (rnn_fast): " + KERNEL_NAMES[mode_],
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": NCU_TRAFFIC.get(mode_) if B >= 2048 else None,
+                    "traffic_note": "ncu dram read+write of a layer-1 step launch (M=40,960); algorithmic bytes 1.03e9",
                     "peak_source": peaks["source"] + ", sustained dense bf16 (kernel timed inside a long step)",
                     "avg_launch_ms": per_launch_ms, "launches": lst["launches"], "flops_per_launch": per_launch_flops,
                     "mma_passes": passes, "tensor_pipe_tflops_issued": ach * passes,
                     "note": ("fp32-grade results need 3 fp16 tensor-core products per algorithmic multiply; "
                              "`achieved` counts algorithmic FLOPs once, `tensor_pipe_tflops_issued` is the MMA work done")
                             if passes == 3 else "single-pass fp16",
-                    "share_of_step": lst["ms"] / ms_ if ms_ > 0 else None}
+                    "share_of_step": (lst["ms"] + slow["ms"]) / ms_ if ms_ > 0 else None}
 
         roofline = lstm_roofline(prof, ms, args.steps, mode)
         stage_ms = {k: round(v["ms"] / args.steps, 3) for k, v in prof.items()}

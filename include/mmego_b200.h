@@ -137,7 +137,7 @@ long long mmego_launch_count(const mmego_handle* h);
 /* Measurement hooks (bench.py): between profile_begin and profile_end every named group of launches is bracketed by
  * CUDA events on the launching stream.  profile_read synchronises on the recorded events and returns the summed
  * duration, the number of kernel launches and the number of spans of `name`
- * ("imu.fc1", "imu.lstm_step", "imu.pool", "imu.decode", "upper.point", "small_lstm", "upper.head_decode",
+ * ("imu.fc1", "imu.lstm_fast", "imu.lstm_slow", "imu.pool", "imu.decode", "upper.point", "small_lstm", "upper.head_decode",
  *  "lower.gcn", "lower.frame", "lower.head_decode", "assemble_metrics"). */
 int mmego_profile_begin(mmego_handle* h);
 int mmego_profile_read(mmego_handle* h, const char* name, double* total_ms, long long* launches, long long* spans);

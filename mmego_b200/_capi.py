@@ -48,7 +48,7 @@ SIGNATURES = {
     "mmego_debug_stats": (_i, [_vp, C.POINTER(C.c_ulonglong), _i]),
 }
 
-PROFILE_SPANS = ("imu.fc1", "imu.lstm_step", "imu.pool", "imu.decode", "upper.point", "small_lstm", "upper.head_decode",
+PROFILE_SPANS = ("imu.fc1", "imu.lstm_fast", "imu.lstm_slow", "imu.pool", "imu.decode", "upper.point", "small_lstm", "upper.head_decode",
                  "lower.gcn", "lower.frame", "lower.head_decode", "assemble_metrics")
 
 

@@ -195,9 +195,9 @@ void plan_imu(Carver& c, long long Bc, int L, int n, ImuWs& w) {
 // Each timestep is ONE launch covering both directions (blockIdx.z) of an fp32 GEMM over K = [x_t | h_{t-1}] with the
 // LSTM cell fused into the epilogue (gemm_ffma.cu).
 void run_big_lstm_layer(mmego_handle* h, const PackedBigLstmLayer& lw, const float* x, int In, float* y, float* cst,
-                        long long S, int T, cudaStream_t st) {
+                        long long S, int T, cudaStream_t st, const char* span) {
     const int H = kImuH;
-    Prof prof(h, "imu.lstm_step", st);
+    Prof prof(h, span, st);
     for (int step = 0; step < T; ++step) {
         GemmBatch b{};
         for (int d = 0; d < 2; ++d) {
@@ -226,16 +226,16 @@ int imu_chunk_forward(mmego_handle* h, const float* imu, float* R, float* t, lon
         linear(h, W.fc1, imu, kImuFeat, w.u, kImuH, S * n, 1, st);                      // Net/IMU_Net.py:79
     }
     tap(h, "imu.u", w.u, (size_t)S * n * kImuH * 4, st);
-    run_big_lstm_layer(h, W.fast[0], w.u, kImuH, w.y0, w.cst, S, n, st);                 // :80
-    run_big_lstm_layer(h, W.fast[1], w.y0, 2 * kImuH, w.y1, w.cst, S, n, st);
+    run_big_lstm_layer(h, W.fast[0], w.u, kImuH, w.y0, w.cst, S, n, st, "imu.lstm_fast");                 // :80
+    run_big_lstm_layer(h, W.fast[1], w.y0, 2 * kImuH, w.y1, w.cst, S, n, st, "imu.lstm_fast");
     tap(h, "imu.f", w.y1, (size_t)S * n * 2 * kImuH * 4, st);
     {
         Prof p(h, "imu.pool", st);
         launch_imu_pool(w.y1, W.attn.p, w.s, S, n, st);                                  // :82-83
     }
     tap(h, "imu.s", w.s, (size_t)S * 2 * kImuH * 4, st);
-    run_big_lstm_layer(h, W.slow[0], w.s, 2 * kImuH, w.z0, w.cst, Bc, L, st);            // :85
-    run_big_lstm_layer(h, W.slow[1], w.z0, 2 * kImuH, w.z1, w.cst, Bc, L, st);
+    run_big_lstm_layer(h, W.slow[0], w.s, 2 * kImuH, w.z0, w.cst, Bc, L, st, "imu.lstm_slow");            // :85
+    run_big_lstm_layer(h, W.slow[1], w.z0, 2 * kImuH, w.z1, w.cst, Bc, L, st, "imu.lstm_slow");
     tap(h, "imu.g", w.z1, (size_t)S * 2 * kImuH * 4, st);
     {
         Prof p(h, "imu.decode", st);
@@ -288,7 +288,7 @@ int imu_chunk_forward_tc(mmego_handle* h, const float* imu, float* R, float* t, 
     tap_split("imu.u", w.u, S * n * kImuH);
     int rc = 0;
     {
-        Prof p(h, "imu.lstm_step", st);
+        Prof p(h, "imu.lstm_fast", st);
         rc |= tc_lstm_layer(h, W.tc_fast[0], w.u[0], lo(w.u), w.y0[0], lo(w.y0), w.cst, S, w.Spad, n, npass, st);   // :80
         tap_split("imu.y0", w.y0, S * n * 2 * kImuH);
         rc |= tc_lstm_layer(h, W.tc_fast[1], w.y0[0], lo(w.y0), w.y1[0], lo(w.y1), w.cst, S, w.Spad, n, npass, st);
@@ -300,7 +300,7 @@ int imu_chunk_forward_tc(mmego_handle* h, const float* imu, float* R, float* t, 
     }
     tap_split("imu.s", w.s, S * 2 * kImuH);
     {
-        Prof p(h, "imu.lstm_step", st);
+        Prof p(h, "imu.lstm_slow", st);
         rc |= tc_lstm_layer(h, W.tc_slow[0], w.s[0], lo(w.s), w.z0[0], lo(w.z0), w.cst, Bc, w.Spad, L, npass, st);  // :85
         rc |= tc_lstm_layer(h, W.tc_slow[1], w.z0[0], lo(w.z0), w.z1[0], lo(w.z1), w.cst, Bc, w.Spad, L, npass, st);
     }

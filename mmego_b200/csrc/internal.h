@@ -119,15 +119,19 @@ struct PackedSmallLstmLayer {  // H=64
     DevBuf whh;                // [2][256][64]  row = thread order
     int in = 0;
 };
-// H=512 layer packed for the tcgen05 path (lstm_tc.cu): fp16 hi/lo planes [2 dirs * 2048 rows][In + 512], scaled by 2^e
-struct TcLstmLayer {
+// H=512 layer packed for the tcgen05 path (lstm_tc.cu): fp16 hi/lo planes [2 dirs * 2048 rows][In + 512], scaled by 2^e,
+// rows gate-interleaved per 256-column tile (64 hidden units)
+struct TcLstmVariant {
     alignas(64) unsigned char map_hi[128];
     alignas(64) unsigned char map_lo[128];
-    alignas(64) unsigned char map_hi2[128];    // same tensors, box of 128 rows: one CTA's half of a CTA pair's tile
+    alignas(64) unsigned char map_hi2[128];    // same tensors, box of half the rows: one CTA's half of a CTA pair's tile
     alignas(64) unsigned char map_lo2[128];
     void* whi = nullptr;
     void* wlo = nullptr;
     float* bias = nullptr;     // [2][2048] packed row order
+};
+struct TcLstmLayer {
+    TcLstmVariant v[1];
     int in_features = 0, K = 0;
     float out_scale = 1.f;     // 2^-e
 };

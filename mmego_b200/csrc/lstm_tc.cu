@@ -33,14 +33,21 @@ namespace {
 
 using namespace tc;
 
-constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int kUnitsPerTile = BN / 4;            // 64
-constexpr int kNTiles = 4 * kImuH / BN;          // 8
+constexpr int BM = 128, BK = 64;
 constexpr int kEpiWarps = 16;
-constexpr int kUnitsPerEpiWarp = kUnitsPerTile / (kEpiWarps / 4);   // 16
+// Tile geometry as a function of the tile width BN (gate columns): BN = 256 -> 64 hidden units per tile, 2 TMEM buffers;
+// BN = 128 -> 32 units per tile and FOUR TMEM buffers, so the MMA thread can run three chunks ahead of the epilogue
+// warps, whose per-thread accumulator set halves (32 registers) -- no spills in the LSTM cell phase.
+template <int BN>
+struct Geo {
+    static constexpr int UT = BN / 4;                    // hidden units per tile
+    static constexpr int NT = 4 * kImuH / BN;            // unit tiles per direction
+    static constexpr int UW = UT / (kEpiWarps / 4);      // units per epilogue warp (16 or 8)
+    static constexpr int NBUF = 512 / BN;                // TMEM accumulator buffers
+    static constexpr int W_TILE = BN * BK * 2;
+};
 constexpr int kThreads = 128 + kEpiWarps * 32;   // 640: warpgroup 0 = {TMA, MMA, 2 idle warps}, warpgroups 1..4 = epilogue
 constexpr int A_TILE = BM * BK * 2;              // 16 KB
-constexpr int W_TILE = BN * BK * 2;              // 32 KB
 constexpr uint32_t kTmemCols = 512;
 // Activation planes hold 2^8 * value: with |h| <= 1 (and |u| up to ~250) the hi part stays far below the fp16 maximum,
 // while the lo part (residual, ~2^-12 of the value) stays a NORMAL fp16 for |value| >= 1e-3 -- unscaled, the residual of
@@ -50,10 +57,10 @@ constexpr float kActScale = 256.0f, kActInv = 1.0f / 256.0f;
 // NCTA = 2: a CTA pair (cta_group::2) shares one 256 x 256 accumulator tile pair: each CTA stages its own 128 sequences
 // of A and HALF of the weight tile, so a stage is 64 KB instead of 96 KB (3-deep ring instead of 2) and the weight bytes
 // that cross L2 -> shared memory halve.
-template <int NPASS, int NCTA>
+template <int NPASS, int NCTA, int BN>
 struct Cfg {
     static constexpr int PLANES = NPASS == 3 ? 2 : 1;
-    static constexpr int W_TILE_CTA = W_TILE / NCTA;
+    static constexpr int W_TILE_CTA = Geo<BN>::W_TILE / NCTA;
     static constexpr int STAGE_BYTES = PLANES * (A_TILE + W_TILE_CTA);      // per CTA: 96 / 48 KB (1 CTA), 64 / 32 KB (pair)
     static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 6 ? 6 : (196 * 1024) / STAGE_BYTES;
     static constexpr int BIAS_BYTES = 2 * 4 * kImuH * 4;                    // both directions' bias vectors, staged once
@@ -77,8 +84,8 @@ struct StepParams {
     int kb_chunk;        // K blocks accumulated in TMEM before the partial sum is drained into registers
     int kb_chunk0;       // length of the FIRST TWO chunks of a tile: they run while the epilogue warps are still busy with
                          // the previous tile's cell update, so they are longer to give the MMA thread work until then
-    unsigned long long* stats;   // dbg & 4: [0] epilogue cell-phase cycles, [1] epilogue wait-for-MMA cycles, [2] drain cycles,
-                         // [3] tiles, [4] MMA-thread cycles waiting for the epilogue, [5] waiting for TMA, [6] MMA issue cycles
+    unsigned long long* stats;   // dbg & 4, MMA thread: [3] work items, [4] cycles waiting for the epilogue, [5] waiting for TMA,
+                         // [6] total cycles
     int dbg;             // experiment switches (results are wrong when set): 1 = skip the cell math and stores, 2 = skip the TMEM drains
 };
 
@@ -112,13 +119,15 @@ __device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po
     h = sigmoid_fast(po) * tanh_fast(cn);
 }
 
-template <int NPASS, int NCTA>
+template <int NPASS, int NCTA, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtensorMap mXlo,
                     const __grid_constant__ CUtensorMap mYhi, const __grid_constant__ CUtensorMap mYlo,
                     const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo,
                     const StepParams p) {
-    using C = Cfg<NPASS, NCTA>;
+    using C = Cfg<NPASS, NCTA, BN>;
+    using G = Geo<BN>;
+    constexpr int kUnitsPerTile = G::UT, kNTiles = G::NT, kUnitsPerEpiWarp = G::UW, NBUF = G::NBUF;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space known to the compiler)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -126,8 +135,8 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
     uint64_t* full = bars;
     uint64_t* empty = bars + C::STAGES;
     uint64_t* tfull = bars + 2 * C::STAGES;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tempty = tfull + NBUF;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + NBUF);
     float* sbias = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,7 +160,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < NBUF; ++a) {
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], NCTA * kEpiWarps);      // the leader's MMA thread waits for both CTAs' epilogues
         }
@@ -229,12 +238,13 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             uint32_t cc = 0;      // running chunk counter (same sequence in the epilogue warps)
-            long long ms_epi = 0, ms_tma = 0;
+            long long ms_epi = 0, ms_tma = 0, ms_tiles = 0;
             const long long ms_start = (p.dbg & 4) ? clock64() : 0;
             for (int tile = first_item; tile < total_tiles; tile += item_stride) {
+                if (p.dbg & 4) ++ms_tiles;
                 for (int c0 = 0, ci = 0; c0 < kb_total; ++cc, ++ci) {
                     const int clen = ci < 2 ? p.kb_chunk0 : p.kb_chunk;
-                    const uint32_t buf = cc & 1, bph = (cc >> 1) & 1;
+                    const uint32_t buf = cc % NBUF, bph = (cc / NBUF) & 1;
                     long long tm0 = 0;
                     if (p.dbg & 4) tm0 = clock64();
                     mbar_wait(&tempty[buf], bph ^ 1);
@@ -285,6 +295,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
                 atomicAdd(p.stats + 4, (unsigned long long)ms_epi);
                 atomicAdd(p.stats + 5, (unsigned long long)ms_tma);
                 atomicAdd(p.stats + 6, (unsigned long long)(clock64() - ms_start));
+                atomicAdd(p.stats + 3, (unsigned long long)ms_tiles);
             }
         }
         __syncwarp();
@@ -296,9 +307,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
         const int part = (warp - 4) >> 2;       // which 16 of the tile's 64 hidden units
         const int u0 = part * kUnitsPerEpiWarp;
         uint32_t cc = 0;
-        long long st_wait = 0, st_drain = 0, st_cell = 0, st_tiles = 0;
-        const uint32_t tempty_remote[2] = {NCTA == 2 ? mapa_u32(smem_u32(&tempty[0]), 0) : 0,
-                                           NCTA == 2 ? mapa_u32(smem_u32(&tempty[1]), 0) : 0};
+        const uint32_t tempty_remote0 = NCTA == 2 ? mapa_u32(smem_u32(&tempty[0]), 0) : 0;   // + 8 bytes per buffer
         for (int tile = first_item; tile < total_tiles; tile += item_stride) {
             const int nt = tile % kNTiles, dir = (tile / kNTiles) & 1, m = (tile / (2 * kNTiles)) * NCTA + (int)rank;
             float acc[4][kUnitsPerEpiWarp];     // i, f, g, o pre-activations (scaled) of this thread's row
@@ -309,91 +318,80 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
             for (int c0 = 0, ci = 0; c0 < kb_total; ++cc, ++ci) {
                 const int clen = ci < 2 ? p.kb_chunk0 : p.kb_chunk;
                 const bool first = c0 == 0;
-                const uint32_t buf = cc & 1, bph = (cc >> 1) & 1;
+                const uint32_t buf = cc % NBUF, bph = (cc / NBUF) & 1;
                 if (c0 + clen >= kb_total && has_state && ok) {
                     // last chunk of the tile: pull the cell state towards L2 now (no registers held), it is read below
 #pragma unroll
                     for (int j = 0; j < kUnitsPerEpiWarp; ++j)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(cbase + (long long)j * p.Spad));
                 }
-                long long tq0 = 0;
-                if (p.dbg & 4) tq0 = clock64();
                 mbar_wait(&tfull[buf], bph);
                 tc_fence_after();
-                if (p.dbg & 4) { const long long t1 = clock64(); st_wait += t1 - tq0; tq0 = t1; }
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + u0);
                 if (!(p.dbg & 2))
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {        // one gate (16 columns) at a time keeps the temporaries at 16 registers
-                    uint32_t r0[16];
-                    tmem_ld_x16(taddr + g * kUnitsPerTile, r0);
+                for (int g = 0; g < 4; ++g) {        // one gate at a time keeps the temporaries small
+                    uint32_t r0[kUnitsPerEpiWarp];
+                    if (kUnitsPerEpiWarp == 16) tmem_ld_x16(taddr + g * kUnitsPerTile, r0);
+                    else tmem_ld_x8(taddr + g * kUnitsPerTile, r0);
                     tmem_ld_wait();
                     if (first) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[g][j] = __uint_as_float(r0[j]);
+                        for (int j = 0; j < kUnitsPerEpiWarp; ++j) acc[g][j] = __uint_as_float(r0[j]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[g][j] += __uint_as_float(r0[j]);
+                        for (int j = 0; j < kUnitsPerEpiWarp; ++j) acc[g][j] += __uint_as_float(r0[j]);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (NCTA == 2) mbar_arrive_cluster(buf ? tempty_remote[1] : tempty_remote[0]);
+                    if (NCTA == 2) mbar_arrive_cluster(tempty_remote0 + buf * 8);
                     else mbar_arrive(&tempty[buf]);
                 }
-                if (p.dbg & 4) st_drain += clock64() - tq0;
                 c0 += clen;
             }
             if (p.dbg & 1) continue;
-            long long tc0 = 0;
-            if (p.dbg & 4) tc0 = clock64();
             // ---- LSTM cell on the register-resident pre-activations (bias from shared memory: warp-wide broadcast reads)
+            // The epilogue warps run at 112 registers with 64 of them holding the accumulators, and shared memory leaves almost
+            // no L1, so a spilled register costs an L2 round trip: the 16 units are processed in two halves of 8 whose
+            // temporaries (cell state, packed outputs) are kept small, with a scheduling fence between the halves.
             const float* bias = sbias + dir * 4 * kImuH + nt * BN + u0;
-            float cprev[kUnitsPerEpiWarp];
+            const long long o = (row * p.T + (dir ? p.tt1 : p.tt0)) * (2 * kImuH) + dir * kImuH + nt * kUnitsPerTile + u0;
 #pragma unroll
-            for (int j = 0; j < kUnitsPerEpiWarp; ++j)      // 16 independent coalesced loads in flight
-                cprev[j] = (has_state && ok) ? __ldcs(cbase + (long long)j * p.Spad) : 0.f;
-            uint32_t ph[8], pl[8];
+            for (int half = 0; half < kUnitsPerEpiWarp / 8; ++half) {
+                float cprev[8];
 #pragma unroll
-            for (int j2 = 0; j2 < kUnitsPerEpiWarp / 2; ++j2) {
-                float hv2[2];
+                for (int j = 0; j < 8; ++j)      // 8 independent coalesced loads in flight
+                    cprev[j] = (has_state && ok) ? __ldcs(cbase + (long long)(half * 8 + j) * p.Spad) : 0.f;
+                uint32_t ph[4], pl[4];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int j = 2 * j2 + e;
-                    const float pi = fmaf(acc[0][j], p.out_scale, bias[j]);
-                    const float pf = fmaf(acc[1][j], p.out_scale, bias[kUnitsPerTile + j]);
-                    const float pg = fmaf(acc[2][j], p.out_scale, bias[2 * kUnitsPerTile + j]);
-                    const float po = fmaf(acc[3][j], p.out_scale, bias[3 * kUnitsPerTile + j]);
-                    float cn, hh;
-                    lstm_cell(pi, pf, pg, po, cprev[j], cn, hh);
-                    hv2[e] = hh * kActScale;
-                    if (ok) __stcs(cbase + (long long)j * p.Spad, cn);
+                for (int j2 = 0; j2 < 4; ++j2) {
+                    float hv2[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = half * 8 + 2 * j2 + e;
+                        const float pi = fmaf(acc[0][j], p.out_scale, bias[j]);
+                        const float pf = fmaf(acc[1][j], p.out_scale, bias[kUnitsPerTile + j]);
+                        const float pg = fmaf(acc[2][j], p.out_scale, bias[2 * kUnitsPerTile + j]);
+                        const float po = fmaf(acc[3][j], p.out_scale, bias[3 * kUnitsPerTile + j]);
+                        float cn, hh;
+                        lstm_cell(pi, pf, pg, po, cprev[2 * j2 + e], cn, hh);
+                        hv2[e] = hh * kActScale;
+                        if (ok) __stcs(cbase + (long long)j * p.Spad, cn);
+                    }
+                    const __half2 hh2 = __floats2half2_rn(hv2[0], hv2[1]);           // one packed conversion
+                    const float2 back = __half22float2(hh2);
+                    const __half2 ll2 = __floats2half2_rn(hv2[0] - back.x, hv2[1] - back.y);
+                    ph[j2] = *reinterpret_cast<const uint32_t*>(&hh2);
+                    pl[j2] = *reinterpret_cast<const uint32_t*>(&ll2);
                 }
-                const __half2 hh2 = __floats2half2_rn(hv2[0], hv2[1]);           // one packed conversion
-                const float2 back = __half22float2(hh2);
-                const __half2 ll2 = __floats2half2_rn(hv2[0] - back.x, hv2[1] - back.y);
-                ph[j2] = *reinterpret_cast<const uint32_t*>(&hh2);
-                pl[j2] = *reinterpret_cast<const uint32_t*>(&ll2);
-            }
-            if (ok) {
-                const long long o = (row * p.T + (dir ? p.tt1 : p.tt0)) * (2 * kImuH) + dir * kImuH + nt * kUnitsPerTile + u0;
-                uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
-                dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-                if (p.out_lo) {
-                    uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
-                    dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-                    dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+                if (ok) {
+                    *reinterpret_cast<uint4*>(p.out_hi + o + half * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                    if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + o + half * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                 }
+                asm volatile("" ::: "memory");
             }
-            if (p.dbg & 4) { st_cell += clock64() - tc0; ++st_tiles; }
-        }
-        if ((p.dbg & 4) && warp == 4 && lane == 0) {
-            atomicAdd(p.stats + 0, (unsigned long long)st_cell);
-            atomicAdd(p.stats + 1, (unsigned long long)st_wait);
-            atomicAdd(p.stats + 2, (unsigned long long)st_drain);
-            atomicAdd(p.stats + 3, (unsigned long long)st_tiles);
         }
     }
 
@@ -616,11 +614,13 @@ bool make_w_map(CUtensorMap* m, const void* base, int rows, int K, int box_rows)
 // ================================================================================================ host interface
 bool tc_supported() { return encode_fn() != nullptr; }
 
-// Packs one bidirectional H=512 layer: rows gate-interleaved per tile of 64 units
-//   packed row p = dir*2048 + tile*256 + gate*64 + e   <->   torch row gate*512 + tile*64 + e   (gates i,f,g,o)
+// Packs one bidirectional H=512 layer for a tile of UT hidden units (64 for BN = 256, 32 for BN = 128): rows are
+// gate-interleaved per tile,
+//   packed row p = dir*2048 + tile*4UT + gate*UT + e   <->   torch row gate*512 + tile*UT + e   (gates i,f,g,o),
 // columns [W_ih (In) | W_hh (512)], scaled by 2^e and split into fp16 hi/lo.
-bool tc_pack_layer(mmego_handle* h, const StateDict& sd, const std::string& prefix, int layer, int In, TcLstmLayer& out) {
-    const int H = kImuH, K = In + H, rows = 2 * 4 * H;
+static bool pack_variant(mmego_handle* h, const StateDict& sd, const std::string& prefix, int layer, int In, int UT,
+                         TcLstmVariant& out, float* out_scale) {
+    const int H = kImuH, K = In + H, rows = 2 * 4 * H, BNv = 4 * UT;
     std::vector<float> w((size_t)rows * K), bias(rows);
     const char* sfx[2] = {"", "_reverse"};
     float wmax = 0.f;
@@ -631,8 +631,8 @@ bool tc_pack_layer(mmego_handle* h, const StateDict& sd, const std::string& pref
         const float* bih = sd.get(prefix + "bias_ih_" + k, 4 * H);
         const float* bhh = sd.get(prefix + "bias_hh_" + k, 4 * H);
         for (int pr = 0; pr < 4 * H; ++pr) {
-            const int tile = pr / BN, gate = (pr % BN) / kUnitsPerTile, e = pr % kUnitsPerTile;
-            const int r = gate * H + tile * kUnitsPerTile + e;
+            const int tile = pr / BNv, gate = (pr % BNv) / UT, e = pr % UT;
+            const int r = gate * H + tile * UT + e;
             float* dst = &w[((size_t)d * 4 * H + pr) * K];
             std::memcpy(dst, wih + (size_t)r * In, sizeof(float) * In);
             std::memcpy(dst + In, whh + (size_t)r * H, sizeof(float) * H);
@@ -662,27 +662,34 @@ bool tc_pack_layer(mmego_handle* h, const StateDict& sd, const std::string& pref
     out.whi = dhi;
     out.wlo = dlo;
     out.bias = static_cast<float*>(db);
-    out.in_features = In;
-    out.K = K;
-    out.out_scale = kActInv / scale;
+    *out_scale = kActInv / scale;
     static_assert(sizeof(CUtensorMap) == sizeof(out.map_hi), "tensor map storage size");
-    return make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_hi), dhi, rows, K, BN) &&
-           make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_lo), dlo, rows, K, BN) &&
-           make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_hi2), dhi, rows, K, BN / 2) &&
-           make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_lo2), dlo, rows, K, BN / 2);
+    return make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_hi), dhi, rows, K, BNv) &&
+           make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_lo), dlo, rows, K, BNv) &&
+           make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_hi2), dhi, rows, K, BNv / 2) &&
+           make_w_map(reinterpret_cast<CUtensorMap*>(&out.map_lo2), dlo, rows, K, BNv / 2);
 }
 
-template <int NPASS, int NCTA>
+bool tc_pack_layer(mmego_handle* h, const StateDict& sd, const std::string& prefix, int layer, int In, TcLstmLayer& out) {
+    out.in_features = In;
+    out.K = In + kImuH;
+    // Only the 256-column layout is packed: the 128-column / four-TMEM-buffer variant of the kernel (Geo<128>) was
+    // measured at 99 ms against 72 ms for the rnn_fast launches of a B=4096 step -- every activation tile is then
+    // fetched by 16 CTAs instead of 8 and the operand traffic, not the epilogue, becomes the limit.
+    return pack_variant(h, sd, prefix, layer, In, 64, out.v[0], &out.out_scale);
+}
+
+template <int NPASS, int NCTA, int BN>
 void launch_step(int grid, cudaStream_t st, const CUtensorMap& mXhi, const CUtensorMap& mXlo, const CUtensorMap& mYhi,
                  const CUtensorMap& mYlo, const CUtensorMap& mWhi, const CUtensorMap& mWlo, const StepParams& p) {
     static bool attr_set[64] = {false};
     if (first_use_on_device(attr_set))
-        cudaFuncSetAttribute(lstm_tc_step_kernel<NPASS, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             Cfg<NPASS, NCTA>::SMEM_BYTES);
+        cudaFuncSetAttribute(lstm_tc_step_kernel<NPASS, NCTA, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg<NPASS, NCTA, BN>::SMEM_BYTES);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = Cfg<NPASS, NCTA>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = Cfg<NPASS, NCTA, BN>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -691,7 +698,7 @@ void launch_step(int grid, cudaStream_t st, const CUtensorMap& mXhi, const CUten
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, lstm_tc_step_kernel<NPASS, NCTA>, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
+    cudaLaunchKernelEx(&cfg, lstm_tc_step_kernel<NPASS, NCTA, BN>, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
 }
 
 // One bidirectional layer: x planes [S][T][In] -> y planes [S][T][1024]; cstate [2][512][Spad] fp32 scratch.
@@ -707,15 +714,17 @@ int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const
         mYlo = mYhi;
     }
     const bool pair = h->tc_cta_pair != 0;
-    const CUtensorMap& mWhi = *reinterpret_cast<const CUtensorMap*>(pair ? &lw.map_hi2 : &lw.map_hi);
-    const CUtensorMap& mWlo = *reinterpret_cast<const CUtensorMap*>(pair ? &lw.map_lo2 : &lw.map_lo);
+    const int bn = 256;
+    const TcLstmVariant& wv = lw.v[0];
+    const CUtensorMap& mWhi = *reinterpret_cast<const CUtensorMap*>(pair ? &wv.map_hi2 : &wv.map_hi);
+    const CUtensorMap& mWlo = *reinterpret_cast<const CUtensorMap*>(pair ? &wv.map_lo2 : &wv.map_lo);
     StepParams p{};
     p.S = (int)S;
     p.m_tiles = (int)((S + BM - 1) / BM);
     p.kb_in = In / BK;
     p.in_features = In;
     p.T = T;
-    p.bias = lw.bias;
+    p.bias = wv.bias;
     p.cstate = cstate;
     p.Spad = Spad;
     p.out_hi = static_cast<__half*>(yhi);
@@ -729,24 +738,22 @@ int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const
     }
     p.stats = static_cast<unsigned long long*>(h->tc_stats);
     const int ncta = pair ? 2 : 1;
-    const int total = ((p.m_tiles + ncta - 1) / ncta) * 2 * kNTiles;          // work items (one per CTA or CTA pair)
+    const int total = ((p.m_tiles + ncta - 1) / ncta) * 2 * (4 * kImuH / bn);  // work items (one per CTA or CTA pair)
     int grid = (total < h->sm_count / ncta ? total : h->sm_count / ncta) * ncta;
     for (int step = 0; step < T; ++step) {
         p.kb_rec = step > 0 ? kImuH / BK : 0;
         p.kb_chunk = (npass == 3 && chunk_opt > 0) ? chunk_opt : (p.kb_in + p.kb_rec);
-        p.kb_chunk0 = (npass == 3 && chunk_opt > 0) ? std::max(chunk_opt, h->tc_kb_chunk0) : p.kb_chunk;
+        // with four TMEM buffers (BN = 128) the MMA thread has enough run-ahead without longer first chunks
+        p.kb_chunk0 = (npass == 3 && chunk_opt > 0) ? (bn == 128 ? chunk_opt : std::max(chunk_opt, h->tc_kb_chunk0)) : p.kb_chunk;
         p.tt0 = step;
         p.tt1 = T - 1 - step;
         p.tp0 = step > 0 ? step - 1 : 0;
         p.tp1 = step > 0 ? p.tt1 + 1 : p.tt1;
         ++g_launches;
-        if (npass == 3) {
-            if (pair) launch_step<3, 2>(grid, st, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
-            else launch_step<3, 1>(grid, st, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
-        } else {
-            if (pair) launch_step<1, 2>(grid, st, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
-            else launch_step<1, 1>(grid, st, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
-        }
+#define MMEGO_STEP(NP, NC, BNV) launch_step<NP, NC, BNV>(grid, st, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p)
+        if (npass == 3) { if (pair) MMEGO_STEP(3, 2, 256); else MMEGO_STEP(3, 1, 256); }
+        else { if (pair) MMEGO_STEP(1, 2, 256); else MMEGO_STEP(1, 1, 256); }
+#undef MMEGO_STEP
     }
     return 0;
 }

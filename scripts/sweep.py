@@ -91,7 +91,7 @@ def main():
                                   "frac_hbm": F * (N * 40 + 304) / pt / 1e6 / PEAKS["hbm_gbs"]}
             fr = row["ms"]["lower.frame"]
             row["lower_frame"] = {"gbs": F * (N * 36 + 15 * 64 * 4 + 192 * 4 + 48) / fr / 1e6}
-            lst = row["ms"]["imu.lstm_step"]
+            lst = row["ms"]["imu.lstm_fast"] + row["ms"]["imu.lstm_slow"]
             fl = imu_flops(F, 20, L)
             row["imu_lstm"] = {"algorithmic_tflops": fl / lst / 1e9,
                                "frac_of_measured_bf16_sustained": fl / lst / 1e9 / PEAKS["bf16_tflops_sustained"]}

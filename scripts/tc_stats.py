@@ -5,7 +5,7 @@ from mmego_b200 import _capi, synth
 h = _capi.Handle(); h.set_weights(_capi.NET_IMU, synth.imu_state_dict(0))
 imu = synth.batch(2048, seed=3)["imu"].cuda()
 import itertools
-for pair, chunk, extra in [(1, 4, 0), (1, 4, 8), (1, 4, 16), (1, 4, 24), (1, 8, 0), (1, 8, 8), (1, 8, 16)]:
+for pair, chunk, extra in [(1, 4, 0), (1, 8, 0), (0, 4, 0)]:
     if True:
         h.set_option("tc_cta_pair", pair); h.set_option("tc_kb_chunk", chunk); h.set_option("tc_dbg", 0)
         h.imu_forward(imu); torch.cuda.synchronize()
@@ -14,5 +14,5 @@ for pair, chunk, extra in [(1, 4, 0), (1, 4, 8), (1, 4, 16), (1, 4, 24), (1, 8, 
         e0.record(); h.imu_forward(imu); e1.record(); torch.cuda.synchronize()
         s = h.debug_stats()
         tiles = max(1, s[3])
-        print(f"pair={pair} chunk={chunk} extra={extra}: {e0.elapsed_time(e1):.1f} ms | per tile (epilogue warp 4): cell {s[0]/tiles:.0f} clk, wait-for-MMA {s[1]/tiles:.0f}, drain {s[2]/tiles:.0f}"
-              f" | MMA thread: total {s[6]/tiles:.0f} clk/tile, waiting epilogue {s[4]/tiles:.0f}, waiting TMA {s[5]/tiles:.0f}   (tiles {tiles})")
+        print(f"pair={pair} chunk={chunk}: {e0.elapsed_time(e1):.1f} ms | MMA thread per work item: total {s[6]/tiles:.0f} clk, "
+              f"waiting epilogue {s[4]/tiles:.0f}, waiting TMA {s[5]/tiles:.0f}   (items {tiles})")
