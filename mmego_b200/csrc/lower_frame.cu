@@ -20,6 +20,10 @@ namespace {
 
 using LL = LowerFrameLayout;
 constexpr int NT = 128;
+// BasePointNet's folded weights (W1..B3, 2.8k floats) in constant memory: immediate FFMA operands, as in point_upper.cu.
+// The three 64x64 projections stay in shared memory (they are indexed per thread).
+constexpr int kMlpFloats = LL::WQ;
+__constant__ float c_mlp[kMlpFloats];
 constexpr int NMAX = 512;      // max points per frame supported by the rank select
 constexpr int LDP = 65;
 
@@ -30,13 +34,7 @@ __device__ __forceinline__ void dense(const float* __restrict__ W, const float* 
     for (int o = 0; o < COUT; ++o) {
         float a = b[o];
 #pragma unroll
-        for (int c = 0; c < CINP; c += 4) {
-            const float4 w = *reinterpret_cast<const float4*>(W + o * CINP + c);
-            a = fmaf(w.x, x[c], a);
-            a = fmaf(w.y, x[c + 1], a);
-            a = fmaf(w.z, x[c + 2], a);
-            a = fmaf(w.w, x[c + 3], a);
-        }
+        for (int c = 0; c < CINP; ++c) a = fmaf(W[o * CINP + c], x[c], a);
         y[o] = RELU ? fmaxf(a, 0.f) : a;
     }
 }
@@ -104,9 +102,9 @@ __global__ void __launch_bounds__(NT) lower_frame_kernel(float* __restrict__ x, 
             const float* pp = s.pts + s.sel[tid] * 6;
             float in[8] = {pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], 0.f, 0.f};
             float a1[16], a2[32], a3[64];
-            dense<8, 16, true>(s.w + LL::W1, s.w + LL::B1, in, a1);
-            dense<16, 32, true>(s.w + LL::W2, s.w + LL::B2, a1, a2);
-            dense<32, 64, true>(s.w + LL::W3, s.w + LL::B3, a2, a3);   // rows 61..63 are zero padding
+            dense<8, 16, true>(c_mlp + LL::W1, c_mlp + LL::B1, in, a1);
+            dense<16, 32, true>(c_mlp + LL::W2, c_mlp + LL::B2, a1, a2);
+            dense<32, 64, true>(c_mlp + LL::W3, c_mlp + LL::B3, a2, a3);   // rows 61..63 are zero padding
             float* pr = s.P + tid * LDP;
             pr[0] = in[0]; pr[1] = in[1]; pr[2] = in[2];
 #pragma unroll
@@ -222,6 +220,7 @@ void launch_lower_frame(float* x, const float* R, const float* t, const float* k
     if (first_use_on_device(attr_set)) {
         cudaFuncSetAttribute(lower_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     }
+    cudaMemcpyToSymbolAsync(c_mlp, wblob, sizeof(float) * kMlpFloats, 0, cudaMemcpyDeviceToDevice, st);
     long long grid = F < (long long)sm_count * 2 ? F : (long long)sm_count * 2;
     MMEGO_LAUNCH(lower_frame_kernel, dim3((unsigned)grid), dim3(NT), sizeof(Smem), st, x, R, t, kfeat, wblob, ak, F, N);
 }

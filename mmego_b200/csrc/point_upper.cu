@@ -16,6 +16,12 @@ namespace {
 
 using UL = UpperPointLayout;
 constexpr int PT = 128;          // threads per CTA = points per chunk
+
+// The folded MLP weights live in constant memory: every thread of a warp needs the same weight at the same time and the
+// layer loops are fully unrolled, so each weight becomes an immediate constant-bank operand of its FFMA -- no load
+// instruction at all.  (Reading them from shared memory instead costs one broadcast LDS per four FFMAs and capped the
+// kernel at ~22 TFLOP/s.)  Refreshed from the handle's packed blob, stream-ordered, before every launch.
+__constant__ float c_w[UL::TOTAL];
 constexpr int RED_LD = PT + 1;   // padded row of the transposed reduction tile
 
 template <int CINP, int COUT, bool RELU>
@@ -25,13 +31,7 @@ __device__ __forceinline__ void dense(const float* __restrict__ W, const float* 
     for (int o = 0; o < COUT; ++o) {
         float a = b[o];
 #pragma unroll
-        for (int c = 0; c < CINP; c += 4) {
-            const float4 w = *reinterpret_cast<const float4*>(W + o * CINP + c);
-            a = fmaf(w.x, x[c], a);
-            a = fmaf(w.y, x[c + 1], a);
-            a = fmaf(w.z, x[c + 2], a);
-            a = fmaf(w.w, x[c + 3], a);
-        }
+        for (int c = 0; c < CINP; ++c) a = fmaf(W[o * CINP + c], x[c], a);
         y[o] = RELU ? fmaxf(a, 0.f) : a;
     }
 }
@@ -64,16 +64,13 @@ __global__ void __launch_bounds__(PT) upper_point_kernel(float* __restrict__ x, 
                                                          const float* __restrict__ wblob, float* __restrict__ gout,
                                                          float* __restrict__ gw, long long F, int N) {
     MMEGO_DYN_SMEM(float, smem);
-    float* sw = smem;                          // UL::TOTAL
-    float* red = sw + UL::TOTAL;               // [64][RED_LD]
+    const float* sw = c_w;                     // constant bank
+    float* red = smem;                         // [64][RED_LD]
     float* part = red + 64 * RED_LD;           // [2][64]
     float* scratch = part + 128;               // [8]
     float* srt = scratch + 8;                  // [12] R,t of the frame
     const int tid = threadIdx.x;
-
-    for (int i = tid * 4; i < UL::TOTAL; i += PT * 4)
-        *reinterpret_cast<float4*>(sw + i) = *reinterpret_cast<const float4*>(wblob + i);
-    __syncthreads();
+    (void)wblob;
 
     for (long long f = blockIdx.x; f < F; f += gridDim.x) {
         if (tid < 9) srt[tid] = R[f * 9 + tid];
@@ -144,7 +141,7 @@ __global__ void __launch_bounds__(PT) upper_point_kernel(float* __restrict__ x, 
 
 }  // namespace
 
-size_t upper_point_smem_bytes() { return (size_t)(UL::TOTAL + 64 * RED_LD + 128 + 8 + 12 + 4) * sizeof(float); }
+size_t upper_point_smem_bytes() { return (size_t)(64 * RED_LD + 128 + 8 + 12 + 4) * sizeof(float); }
 
 void launch_upper_point(float* x, const float* R, const float* t, const float* wblob, float* g, float* gw,
                         long long F, int N, int sm_count, cudaStream_t st) {
@@ -154,7 +151,8 @@ void launch_upper_point(float* x, const float* R, const float* t, const float* w
         cudaFuncSetAttribute(upper_point_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)upper_point_smem_bytes());
     }
-    long long grid = F < (long long)sm_count * 3 ? F : (long long)sm_count * 3;
+    cudaMemcpyToSymbolAsync(c_w, wblob, sizeof(float) * UL::TOTAL, 0, cudaMemcpyDeviceToDevice, st);
+    long long grid = F < (long long)sm_count * 4 ? F : (long long)sm_count * 4;
     MMEGO_LAUNCH(upper_point_kernel, dim3((unsigned)grid), dim3(PT), upper_point_smem_bytes(), st, x, R, t, wblob, g,
                  gw, F, N);
 }
