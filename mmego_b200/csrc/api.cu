@@ -539,6 +539,11 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
         h->gcn_gemm = (int)value;
         return MMEGO_OK;
     }
+    if (!strcmp(key, "point_gemm")) {
+        if (value < 0 || value > 1) return fail(h, MMEGO_EINVAL, "point_gemm must be 0 (fp32 FFMA) or 1 (mma.sync fp16x3)");
+        h->point_gemm = (int)value;
+        return MMEGO_OK;
+    }
     if (!strcmp(key, "tc_kb_chunk0")) {
         if (value < 0 || value > 64) return fail(h, MMEGO_EINVAL, "tc_kb_chunk0 must be in 0..64");
         h->tc_kb_chunk0 = (int)value;
@@ -604,7 +609,10 @@ int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const 
         } else if (net == MMEGO_NET_UPPER) {
             UpperWeights& W = h->upper;
             W.ready = false;
-            ok &= upload(h, pack_upper_point(sd), W.point);
+            {
+                const std::vector<float> folded = pack_upper_point(sd);
+                ok &= upload(h, folded, W.point) && upload(h, pack_upper_point_mma(folded), W.point_mma);
+            }
             for (int l = 0; l < 3; ++l) {
                 HostSmallLstm s = pack_small_lstm(sd, "module1.grnn.", l, l == 0 ? 64 : 128);
                 ok &= upload(h, s.ih, W.lstm[l].ih) && upload(h, s.whh, W.lstm[l].whh);
@@ -619,7 +627,10 @@ int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const 
             W.tc_ready = false;
             bool tc_ok = true;
             (void)tc_ok;
-            ok &= upload(h, pack_lower_frame(sd), W.frame);
+            {
+                const std::vector<float> folded = pack_lower_frame(sd);
+                ok &= upload(h, folded, W.frame) && upload(h, pack_lower_frame_mma(folded), W.frame_mma);
+            }
             const std::string gp = "keyEncoder.gcn.";
             ok &= upload(h, pack_data_bn(sd, gp), W.data_bn);
             const int ch[4] = {3, 32, 64, 128};
@@ -748,7 +759,10 @@ int mmego_upper_forward(mmego_handle* h, float* x, const float* h0, const float*
     const UpperWeights& W = h->upper;
     {
         Prof p(h, "upper.point", st);
-        launch_upper_point(x, R, t, W.point.p, w.g, global_w, F, N, h->sm_count, st);   // Upper_Net.py:379-381 (+gpointnet)
+        if (h->point_gemm)                                                               // Upper_Net.py:379-381 (+gpointnet)
+            launch_upper_point_mma(x, R, t, W.point_mma.p, w.g, global_w, F, N, h->sm_count, st);
+        else
+            launch_upper_point(x, R, t, W.point.p, w.g, global_w, F, N, h->sm_count, st);
     }
     tap(h, "upper.g", w.g, (size_t)F * 64 * 4, st);
     const float* hs = run_small_lstm(h, W.lstm, w.g, 64, h0, c0, hn, cn, B, L, w.lstm, st);   // :339
@@ -800,7 +814,10 @@ int mmego_lower_forward(mmego_handle* h, const float* upper_l, float* x, const f
     tap(h, "lower.K", w.kf, (size_t)F * kGcnV * 64 * 4, st);
     {
         Prof p(h, "lower.frame", st);
-        launch_lower_frame(x, R, t, w.kf, W.frame.p, w.ak, F, N, h->sm_count, st);       // :191-192, 216-227, 231, 104-116
+        if (h->point_gemm)                                                                // :191-192, 216-227, 231, 104-116
+            launch_lower_frame_mma(x, R, t, w.kf, W.frame_mma.p, w.ak, F, N, h->sm_count, st);
+        else
+            launch_lower_frame(x, R, t, w.kf, W.frame.p, w.ak, F, N, h->sm_count, st);
     }
     tap(h, "lower.ak", w.ak, (size_t)F * 192 * 4, st);
     const float* hs = run_small_lstm(h, W.lstm, w.ak, 192, nullptr, nullptr, nullptr, nullptr, B, L, w.lstm, st);   // :117

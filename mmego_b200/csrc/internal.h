@@ -77,10 +77,14 @@ void launch_upper_point(float* x, const float* R, const float* t, const float* w
                         int N, int sm_count, cudaStream_t st);
 void launch_lstm_small(const float* gx, const float* whh, const float* h0, const float* c0, float* y, float* hn,
                        float* cn, int S, int T, cudaStream_t st);
+void launch_upper_point_mma(float* x, const float* R, const float* t, const float* wblob, float* g, float* gw,
+                            long long F, int N, int sm_count, cudaStream_t st);
 size_t lower_frame_smem_bytes();
 int lower_frame_max_points();
 void launch_lower_frame(float* x, const float* R, const float* t, const float* kfeat, const float* wblob, float* ak,
                         long long F, int N, int sm_count, cudaStream_t st);
+void launch_lower_frame_mma(float* x, const float* R, const float* t, const float* kfeat, const float* wblob,
+                            float* ak, long long F, int N, int sm_count, cudaStream_t st);
 void launch_gcn_prep(const float* upper, const float* R, const float* t, const float* bn, float* uh, float* y0,
                      long long F, cudaStream_t st);
 void launch_gcn_prep_raw(const float* x, const float* bn, float* y0, int B, int T, cudaStream_t st);
@@ -159,6 +163,7 @@ struct ImuWeights {
 struct UpperWeights {
     bool ready = false;
     DevBuf point;      // folded per-point MLP blob (point_layout.h)
+    DevBuf point_mma;  // the same network as mma.sync fragments (UpperMmaLayout)
     PackedSmallLstmLayer lstm[3];
     PackedGemm fc1, fc2;
 };
@@ -173,6 +178,7 @@ struct LowerWeights {
     bool tc_ready = false;
     TcGemmW tc_gconv[3], tc_tconv[3], tc_fcn;
     DevBuf frame;      // folded per-point MLP + to_q/to_k/to_v blob (point_layout.h)
+    DevBuf frame_mma;  // the same as mma.sync fragments (LowerMmaLayout)
     DevBuf data_bn;    // [45] scale, [45] offset
     GcnLayerWeights gcn[3];
     PackedGemm fcn;
@@ -235,6 +241,7 @@ struct mmego_handle {
     int tc_dbg = 0;           // experiment switches of lstm_tc.cu (never set in product use)
     int tc_cta_pair = 1;      // H=512 LSTM kernel: 1 = CTA pairs (cta_group::2, M = 256)
     int gcn_gemm = 0;         // ST-GCN GEMMs: 0 = fp32 FFMA, 1 = tcgen05 fp16x3 (default when available)
+    int point_gemm = 1;       // point encoders + cross attention: 0 = fp32 FFMA, 1 = mma.sync fp16x3 (default)
     int tc_kb_chunk0 = 8;     // ... of the first two chunks of every tile
     int tc_kb_chunk = 4;      // fp16x3 mode: K blocks (of 64) per TMEM partial accumulation (see lstm_tc.cu)
     mmego::ImuWeights imu;

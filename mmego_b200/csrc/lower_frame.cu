@@ -13,6 +13,7 @@
 // sum_s (alpha[s,:] @ v) is evaluated as (sum_s alpha[s,:]) @ v, so attn @ v is never materialised.
 #include "internal.h"
 #include "point_layout.h"
+#include "mma_frag.cuh"
 
 namespace mmego {
 
@@ -208,6 +209,251 @@ __global__ void __launch_bounds__(NT) lower_frame_kernel(float* __restrict__ x, 
     }
 }
 
+
+// ================================================================================================================
+// Tensor-core version (default): the same per-frame work on mma.sync m16n8k16 fragments (mma_frag.cuh), fp16 hi/lo
+// split products with fp32 accumulation.  128 threads = 4 warps per frame:
+//   A  all threads: stage the frame's joint features, second in-place Transform2H, keys
+//   B  all threads: rank select of the top 64;  then warps 0,1: to_k, warps 2,3: to_v of the 15 (16) joints
+//   C  warp w: selected points 16w..16w+15 through BasePointNet -> P' = [feat61 | xyz] -> to_q -> q k^T -> softmax;
+//      column sums of P and of alpha leave through quad shuffles
+//   D  merge the four warps: a = sum P, a_T = (sum alpha) @ v, kbar
+// Per frame: 4 x 186 + 192 = 936 MMAs instead of 0.61 M FFMAs.
+// ================================================================================================================
+using LM = LowerMmaLayout;
+constexpr int KF_LD = 72;               // joint-feature row stride (floats): conflict-free float2 fragment reads
+constexpr int KP_LD = 36;               // to_k(K) row stride in half2 words (32 + 4 pad): conflict-free B fragments
+constexpr int kSmemWeightWords = LM::FK;   // layers 1-3 + to_q live in shared memory; to_k / to_v are read through L1
+
+struct MmaCarve {
+    uint32_t* w;
+    float *pts, *key, *Kf, *vp, *psum, *asum;
+    int* sel;
+    uint32_t *kph, *kpl;
+    size_t bytes;
+};
+__host__ __device__ inline MmaCarve lower_mma_carve(unsigned char* base, int N) {
+    MmaCarve c;
+    size_t off = 0;
+    auto take = [&](size_t n) { unsigned char* p = base + off; off += (n + 15) & ~size_t(15); return p; };
+    c.w = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * kSmemWeightWords));
+    c.Kf = reinterpret_cast<float*>(take(sizeof(float) * 16 * KF_LD));
+    c.vp = reinterpret_cast<float*>(take(sizeof(float) * 16 * 64));
+    c.kph = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * 16 * KP_LD));
+    c.kpl = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * 16 * KP_LD));
+    c.psum = reinterpret_cast<float*>(take(sizeof(float) * 4 * 64));
+    c.asum = reinterpret_cast<float*>(take(sizeof(float) * 4 * 16));
+    c.sel = reinterpret_cast<int*>(take(sizeof(int) * kLowerPts));
+    c.key = reinterpret_cast<float*>(take(sizeof(float) * N));
+    c.pts = reinterpret_cast<float*>(take(sizeof(float) * N * 6));
+    c.bytes = off;
+    return c;
+}
+
+__global__ void __launch_bounds__(NT, 4) lower_frame_mma_kernel(float* __restrict__ x, const float* __restrict__ R,
+                                                                const float* __restrict__ t,
+                                                                const float* __restrict__ kfeat,
+                                                                const float* __restrict__ wblob,
+                                                                float* __restrict__ ak, long long F, int N) {
+    MMEGO_DYN_SMEM(unsigned char, raw);
+    const MmaCarve s = lower_mma_carve(raw, N);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+    for (int i = tid * 4; i < kSmemWeightWords; i += NT * 4)
+        *reinterpret_cast<uint4*>(s.w + i) = *reinterpret_cast<const uint4*>(wblob + i);
+    for (int i = tid; i < KF_LD; i += NT) s.Kf[15 * KF_LD + i] = 0.f;     // joint 15 is padding
+    const uint4* wf = reinterpret_cast<const uint4*>(s.w);
+    const float* wfl = reinterpret_cast<const float*>(s.w);
+    const uint4* wg = reinterpret_cast<const uint4*>(wblob);              // to_k / to_v fragments (global, L1-resident)
+    const float os1 = wblob[LM::OS + 0], os2 = wblob[LM::OS + 1], os3 = wblob[LM::OS + 2], osq = wblob[LM::OS + 3];
+    const float oskv = wblob[LM::OS + (warp < 2 ? 4 : 5)];
+
+    for (long long f = blockIdx.x; f < F; f += gridDim.x) {
+        __syncthreads();   // previous frame fully consumed (and weights staged on the first pass)
+        // ---- A: joint features, second transform (in place), keys ------------------------------------------------
+        for (int i = tid; i < kGcnV * 64; i += NT) s.Kf[(i >> 6) * KF_LD + (i & 63)] = kfeat[f * (kGcnV * 64) + i];
+        {
+            const float* Rf = R + f * 9;
+            const float* tf = t + f * 3;
+            const float r0 = __ldg(Rf), r1 = __ldg(Rf + 1), r2 = __ldg(Rf + 2), r3 = __ldg(Rf + 3), r4 = __ldg(Rf + 4),
+                        r5 = __ldg(Rf + 5), r6 = __ldg(Rf + 6), r7 = __ldg(Rf + 7), r8 = __ldg(Rf + 8);
+            const float t0 = __ldg(tf), t1 = __ldg(tf + 1), t2 = __ldg(tf + 2);
+            float* xf = x + f * (long long)N * 6;
+            for (int p = tid; p < N; p += NT) {
+                const float2 v0 = *reinterpret_cast<const float2*>(xf + p * 6);
+                const float2 v1 = *reinterpret_cast<const float2*>(xf + p * 6 + 2);
+                const float2 v2 = *reinterpret_cast<const float2*>(xf + p * 6 + 4);
+                const float dx = v0.x - t0, dy = v0.y - t1, dz = v1.x - t2;
+                const float nx = r0 * dx + r1 * dy + r2 * dz;
+                const float ny = r3 * dx + r4 * dy + r5 * dz;
+                const float nz = r6 * dx + r7 * dy + r8 * dz;
+                *reinterpret_cast<float2*>(xf + p * 6) = make_float2(nx, ny);
+                xf[p * 6 + 2] = nz;
+                float* pp = s.pts + p * 6;
+                *reinterpret_cast<float2*>(pp) = make_float2(nx, ny);
+                *reinterpret_cast<float2*>(pp + 2) = make_float2(nz, v1.y);
+                *reinterpret_cast<float2*>(pp + 4) = v2;
+                s.key[p] = nx;
+            }
+        }
+        __syncthreads();
+        // ---- B1: rank select (equal keys: the lower slot wins) ---------------------------------------------------
+        for (int p = tid; p < N; p += NT) {
+            const float kx = s.key[p];
+            int rank = 0;
+            for (int q = 0; q < N; ++q) {
+                const float kq = s.key[q];
+                rank += (kq > kx || (kq == kx && q < p)) ? 1 : 0;
+            }
+            if (rank < kLowerPts) s.sel[rank] = p;
+        }
+        // ---- B2: to_k (warps 0,1) / to_v (warps 2,3) of the joint features: 4 n-tiles each ----------------------
+        {
+            uint32_t kh[LM::KSP][4], kl[LM::KSP][4];
+#pragma unroll
+            for (int ks = 0; ks < LM::KSP; ++ks) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const float2 r0 = *reinterpret_cast<const float2*>(s.Kf + g * KF_LD + 16 * ks + 8 * hh + 2 * tq);
+                    const float2 r1 = *reinterpret_cast<const float2*>(s.Kf + (g + 8) * KF_LD + 16 * ks + 8 * hh + 2 * tq);
+                    frag::split2(r0.x, r0.y, kh[ks][2 * hh], kl[ks][2 * hh]);
+                    frag::split2(r1.x, r1.y, kh[ks][2 * hh + 1], kl[ks][2 * hh + 1]);
+                }
+            }
+            const bool isv = warp >= 2;
+            const int j0 = (warp & 1) * 4;
+            float o[4][4];
+            frag::dense_tile<LM::KSP, 4, false, LM::NTP>(wg + (isv ? LM::FV : LM::FK) / 4, wblob + (isv ? LM::BV : LM::BK),
+                                                         oskv, kh, kl, o, lane, j0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = 8 * (j0 + j) + 2 * tq;
+                if (isv) {
+                    *reinterpret_cast<float2*>(s.vp + g * 64 + col) = make_float2(o[j][0], o[j][1]);
+                    *reinterpret_cast<float2*>(s.vp + (g + 8) * 64 + col) = make_float2(o[j][2], o[j][3]);
+                } else {
+                    uint32_t hi, lo;
+                    frag::split2(o[j][0], o[j][1], hi, lo);
+                    s.kph[g * KP_LD + (col >> 1)] = hi;
+                    s.kpl[g * KP_LD + (col >> 1)] = lo;
+                    frag::split2(o[j][2], o[j][3], hi, lo);
+                    s.kph[(g + 8) * KP_LD + (col >> 1)] = hi;
+                    s.kpl[(g + 8) * KP_LD + (col >> 1)] = lo;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- C: this warp's 16 selected points ---------------------------------------------------------------------
+        {
+            const float* pr0 = s.pts + s.sel[warp * 16 + g] * 6;
+            const float* pr1 = s.pts + s.sel[warp * 16 + g + 8] * 6;
+            uint32_t a1h[1][4], a1l[1][4];
+            {
+                float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+                if (tq < 3) {
+                    v0 = *reinterpret_cast<const float2*>(pr0 + 2 * tq);
+                    v1 = *reinterpret_cast<const float2*>(pr1 + 2 * tq);
+                }
+                frag::split2(v0.x, v0.y, a1h[0][0], a1l[0][0]);
+                frag::split2(v1.x, v1.y, a1h[0][1], a1l[0][1]);
+                a1h[0][2] = a1h[0][3] = a1l[0][2] = a1l[0][3] = 0u;
+            }
+            float P[LM::NT3][4];
+            {
+                float c1[LM::NT1][4];
+                frag::dense_tile<LM::KS1, LM::NT1, true>(wf + LM::F1 / 4, wfl + LM::BI1, os1, a1h, a1l, c1, lane);
+                uint32_t a2h[LM::KS2][4], a2l[LM::KS2][4];
+                frag::to_afrag<LM::NT1, LM::KS2>(c1, a2h, a2l);
+                float c2[LM::NT2][4];
+                frag::dense_tile<LM::KS2, LM::NT2, true>(wf + LM::F2 / 4, wfl + LM::BI2, os2, a2h, a2l, c2, lane);
+                uint32_t a3h[LM::KS3][4], a3l[LM::KS3][4];
+                frag::to_afrag<LM::NT2, LM::KS3>(c2, a3h, a3l);
+                frag::dense_tile<LM::KS3, LM::NT3, true>(wf + LM::F3 / 4, wfl + LM::BI3, os3, a3h, a3l, P, lane);
+            }
+            // P' columns 61..63 (zero so far: padded rows of layer 3) take x, y, z
+            if (tq == 2) { P[7][1] = pr0[0]; P[7][3] = pr1[0]; }
+            if (tq == 3) { P[7][0] = pr0[1]; P[7][1] = pr0[2]; P[7][2] = pr1[1]; P[7][3] = pr1[2]; }
+            // column sums of P over the tile's 16 points -> psum[warp][channel in the reference's order xyz | feat]
+#pragma unroll
+            for (int j = 0; j < LM::NT3; ++j) {
+                float v0 = P[j][0] + P[j][2], v1 = P[j][1] + P[j][3];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                    v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                }
+                if (g == 0) {
+                    const int c0 = 8 * j + 2 * tq, c1 = c0 + 1;
+                    s.psum[warp * 64 + (c0 < 61 ? c0 + 3 : c0 - 61)] = v0;
+                    s.psum[warp * 64 + (c1 < 61 ? c1 + 3 : c1 - 61)] = v1;
+                }
+            }
+            // to_q, then scores against to_k(K)
+            uint32_t qh[LM::KSP][4], ql[LM::KSP][4];
+            {
+                uint32_t ph[LM::KSP][4], pl[LM::KSP][4];
+                frag::to_afrag<LM::NT3, LM::KSP>(P, ph, pl);
+                float q[LM::NTP][4];
+                frag::dense_tile<LM::KSP, LM::NTP, false>(wf + LM::FQ / 4, wfl + LM::BQ, osq, ph, pl, q, lane);
+                frag::to_afrag<LM::NTP, LM::KSP>(q, qh, ql);
+            }
+            float sc[2][4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float big[4] = {0.f, 0.f, 0.f, 0.f}, small[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < LM::KSP; ++ks) {
+                    const int wi = (8 * j + g) * KP_LD + 8 * ks + tq;
+                    const uint4 b = make_uint4(s.kph[wi], s.kph[wi + 4], s.kpl[wi], s.kpl[wi + 4]);
+                    frag::mma3(big, small, qh[ks], ql[ks], b);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sc[j][i] = (big[i] + small[i]) * 0.125f;      // dim_head^-0.5, Lower_Net.py:106
+            }
+            if (tq == 3) { sc[1][1] = -INFINITY; sc[1][3] = -INFINITY; }                   // joint 15 does not exist
+            float al[2][2];                                                                // alpha summed over rows g, g+8
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                float m = fmaxf(fmaxf(sc[0][2 * r], sc[0][2 * r + 1]), fmaxf(sc[1][2 * r], sc[1][2 * r + 1]));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                float e[4] = {expf(sc[0][2 * r] - m), expf(sc[0][2 * r + 1] - m), expf(sc[1][2 * r] - m),
+                              expf(sc[1][2 * r + 1] - m)};
+                float sum = (e[0] + e[1]) + (e[2] + e[3]);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                const float inv = 1.0f / sum;
+                if (r == 0) { al[0][0] = e[0] * inv; al[0][1] = e[1] * inv; al[1][0] = e[2] * inv; al[1][1] = e[3] * inv; }
+                else { al[0][0] += e[0] * inv; al[0][1] += e[1] * inv; al[1][0] += e[2] * inv; al[1][1] += e[3] * inv; }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float v = al[j][e];
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (g == 0) s.asum[warp * 16 + 8 * j + 2 * tq + e] = v;
+                }
+        }
+        __syncthreads();
+        // ---- D: merge ---------------------------------------------------------------------------------------------------
+        if (tid < 64) {
+            ak[f * 192 + tid] = (s.psum[tid] + s.psum[64 + tid]) + (s.psum[128 + tid] + s.psum[192 + tid]);
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < kGcnV; ++j)
+                a = fmaf((s.asum[j] + s.asum[16 + j]) + (s.asum[32 + j] + s.asum[48 + j]), s.vp[j * 64 + tid], a);
+            ak[f * 192 + 64 + tid] = a;
+        } else {
+            const int c = tid - 64;
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < kGcnV; ++j) a += s.Kf[j * KF_LD + c];
+            ak[f * 192 + 128 + c] = a * (1.0f / 15.0f);
+        }
+    }
+}
+
 }  // namespace
 
 size_t lower_frame_smem_bytes() { return sizeof(Smem); }
@@ -223,6 +469,22 @@ void launch_lower_frame(float* x, const float* R, const float* t, const float* k
     cudaMemcpyToSymbolAsync(c_mlp, wblob, sizeof(float) * kMlpFloats, 0, cudaMemcpyDeviceToDevice, st);
     long long grid = F < (long long)sm_count * 2 ? F : (long long)sm_count * 2;
     MMEGO_LAUNCH(lower_frame_kernel, dim3((unsigned)grid), dim3(NT), sizeof(Smem), st, x, R, t, kfeat, wblob, ak, F, N);
+}
+
+// wblob: LowerMmaLayout (pack_lower_frame_mma)
+void launch_lower_frame_mma(float* x, const float* R, const float* t, const float* kfeat, const float* wblob, float* ak,
+                            long long F, int N, int sm_count, cudaStream_t st) {
+    if (F <= 0) return;
+    const size_t smem = lower_mma_carve(nullptr, N).bytes;
+    static int attr_bytes[64] = {0};
+    int d = 0;
+    cudaGetDevice(&d);
+    if (attr_bytes[d & 63] < (int)smem) {
+        cudaFuncSetAttribute(lower_frame_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_bytes[d & 63] = (int)smem;
+    }
+    long long grid = F < (long long)sm_count * 4 ? F : (long long)sm_count * 4;
+    MMEGO_LAUNCH(lower_frame_mma_kernel, dim3((unsigned)grid), dim3(NT), smem, st, x, R, t, kfeat, wblob, ak, F, N);
 }
 
 }  // namespace mmego

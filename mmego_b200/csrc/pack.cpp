@@ -166,6 +166,158 @@ std::vector<float> pack_lower_frame(const StateDict& sd) {
     return v;
 }
 
+// ------------------------------------------------------------------------------------------------ mma.sync packing
+namespace {
+// IEEE binary16 <-> binary32 on the host (round to nearest even, saturating to +-65504), bit-exact with the device's
+// cvt.rn.satfinite.f16.f32
+uint16_t f32_to_f16_bits(float x) {
+    if (!(x == x)) return 0x7e00;
+    if (x > 65504.f) x = 65504.f;
+    if (x < -65504.f) x = -65504.f;
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    const uint32_t sign = (u >> 16) & 0x8000u;
+    u &= 0x7fffffffu;
+    if (u >= 0x38800000u) {                       // normal half: rebias the exponent, round 13 dropped bits
+        uint32_t r = u - 0x38000000u;
+        const uint32_t rem = r & 0x1fffu;
+        r >>= 13;
+        if (rem > 0x1000u || (rem == 0x1000u && (r & 1u))) ++r;
+        return (uint16_t)(sign | r);
+    }
+    if (u < 0x33000000u) return (uint16_t)sign;   // < 2^-25: rounds to zero
+    const int e = (int)(u >> 23);                 // subnormal half
+    const uint32_t m = (u & 0x7fffffu) | 0x800000u;
+    const int shift = 126 - e;                    // 14..24
+    uint32_t r = m >> shift;
+    const uint32_t rem = m & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (r & 1u))) ++r;
+    return (uint16_t)(sign | r);
+}
+float f16_bits_to_f32(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    const uint32_t e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+    float f;
+    if (e == 0) {
+        f = std::ldexp((float)m, -24);
+    } else if (e == 31) {
+        f = m ? NAN : INFINITY;
+    } else {
+        f = std::ldexp((float)(m | 0x400u), (int)e - 25);
+    }
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    u |= sign;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+float word_as_float(uint32_t w) {
+    float f;
+    std::memcpy(&f, &w, 4);
+    return f;
+}
+}  // namespace
+
+// B operand of  out[n] = sum_k in[k] * W[nmap[n]][kmap[k]]  (entries mapped to -1 are zero), see point_layout.h
+float pack_mma_weight(const float* W, int ldw, const std::vector<int>& kmap, const std::vector<int>& nmap, float* out) {
+    const int KS = (int)kmap.size() / 16, NT = (int)nmap.size() / 8;
+    auto V = [&](int k, int n) { return (kmap[k] >= 0 && nmap[n] >= 0) ? W[(size_t)nmap[n] * ldw + kmap[k]] : 0.f; };
+    float mx = 0.f;
+    for (int k = 0; k < KS * 16; ++k)
+        for (int n = 0; n < NT * 8; ++n) mx = std::max(mx, std::fabs(V(k, n)));
+    int e = 0;
+    if (mx > 0.f) {
+        int ex;
+        std::frexp(mx, &ex);            // mx = f * 2^ex, f in [0.5, 1)
+        e = 14 - ex;                    // scaled max in [2^13, 2^14)
+        e = std::max(-24, std::min(e, 40));
+    }
+    for (int s = 0; s < KS; ++s)
+        for (int j = 0; j < NT; ++j)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, t = lane & 3, n = 8 * j + g;
+                uint32_t w[4];
+                for (int r = 0; r < 2; ++r) {
+                    uint16_t hi[2], lo[2];
+                    for (int i = 0; i < 2; ++i) {
+                        const float v = std::ldexp(V(16 * s + 2 * t + 8 * r + i, n), e);
+                        hi[i] = f32_to_f16_bits(v);
+                        lo[i] = f32_to_f16_bits(v - f16_bits_to_f32(hi[i]));
+                    }
+                    w[r] = (uint32_t)hi[0] | ((uint32_t)hi[1] << 16);
+                    w[2 + r] = (uint32_t)lo[0] | ((uint32_t)lo[1] << 16);
+                }
+                float* dst = out + ((size_t)(s * NT + j) * 32 + lane) * 4;
+                for (int i = 0; i < 4; ++i) dst[i] = word_as_float(w[i]);
+            }
+    return std::ldexp(1.0f, -e);
+}
+
+namespace {
+std::vector<int> iota_map(int n, int pad_to, int first = 0) {
+    std::vector<int> m(pad_to, -1);
+    for (int i = 0; i < n; ++i) m[i] = first + i;
+    return m;
+}
+}  // namespace
+
+std::vector<float> pack_upper_point_mma(const std::vector<float>& f) {
+    using UL = UpperPointLayout;
+    using UM = UpperMmaLayout;
+    std::vector<float> v(UM::TOTAL, 0.f);
+    struct Lyr { int W, B, cin_pad, cout, F, BI, KS, NT; std::vector<int> kmap; };
+    std::vector<int> k4(32, -1);                 // layer 4 input order: feat 0..23 | x[0:4] | 4 pad  (source order: x[0:4] | feat)
+    for (int i = 0; i < 24; ++i) k4[i] = 4 + i;
+    for (int i = 0; i < 4; ++i) k4[24 + i] = i;
+    const Lyr L[6] = {
+        {UL::W1, UL::B1, pad4(UL::C0), UL::C1, UM::F1, UM::BI1, UM::KS1, UM::NT1, iota_map(UL::C0, 16)},
+        {UL::W2, UL::B2, pad4(UL::C1), UL::C2, UM::F2, UM::BI2, UM::KS2, UM::NT2, iota_map(UL::C1, 16)},
+        {UL::W3, UL::B3, pad4(UL::C2), UL::C3, UM::F3, UM::BI3, UM::KS3, UM::NT3, iota_map(UL::C2, 16)},
+        {UL::W4, UL::B4, pad4(UL::C3C), UL::C4, UM::F4, UM::BI4, UM::KS4, UM::NT4, k4},
+        {UL::W5, UL::B5, pad4(UL::C4), UL::C5, UM::F5, UM::BI5, UM::KS5, UM::NT5, iota_map(UL::C4, 32)},
+        {UL::W6, UL::B6, pad4(UL::C5), UL::C6, UM::F6, UM::BI6, UM::KS6, UM::NT6, iota_map(UL::C5, 48)},
+    };
+    for (int l = 0; l < 6; ++l) {
+        v[UM::OS + l] = pack_mma_weight(&f[L[l].W], L[l].cin_pad, L[l].kmap, iota_map(L[l].cout, L[l].NT * 8), &v[L[l].F]);
+        for (int o = 0; o < L[l].cout; ++o) v[L[l].BI + o] = f[L[l].B + o];
+    }
+    for (int c = 0; c < 64; ++c) v[UM::WA + c] = f[UL::WA + c];
+    v[UM::BA] = f[UL::BA];
+    return v;
+}
+
+std::vector<float> pack_lower_frame_mma(const std::vector<float>& f) {
+    using LL = LowerFrameLayout;
+    using LM = LowerMmaLayout;
+    std::vector<float> v(LM::TOTAL, 0.f);
+    v[LM::OS + 0] = pack_mma_weight(&f[LL::W1], pad4(LL::C0), iota_map(LL::C0, 16), iota_map(LL::C1, 16), &v[LM::F1]);
+    v[LM::OS + 1] = pack_mma_weight(&f[LL::W2], pad4(LL::C1), iota_map(LL::C1, 16), iota_map(LL::C2, 32), &v[LM::F2]);
+    v[LM::OS + 2] = pack_mma_weight(&f[LL::W3], pad4(LL::C2), iota_map(LL::C2, 32), iota_map(LL::C3, 64), &v[LM::F3]);
+    for (int o = 0; o < LL::C1; ++o) v[LM::BI1 + o] = f[LL::B1 + o];
+    for (int o = 0; o < LL::C2; ++o) v[LM::BI2 + o] = f[LL::B2 + o];
+    for (int o = 0; o < LL::C3; ++o) v[LM::BI3 + o] = f[LL::B3 + o];
+    // to_q reads P' = [feat 0..60 | x y z]; the reference's P is [x y z | feat] (Net/Lower_Net.py:70-71)
+    std::vector<int> kq(64);
+    for (int i = 0; i < 61; ++i) kq[i] = 3 + i;
+    for (int i = 0; i < 3; ++i) kq[61 + i] = i;
+    v[LM::OS + 3] = pack_mma_weight(&f[LL::WQ], 64, kq, iota_map(64, 64), &v[LM::FQ]);
+    // the fp32 blob stores to_k / to_v transposed ([c][o]); undo that here
+    std::vector<float> wk(64 * 64), wv(64 * 64);
+    for (int o = 0; o < 64; ++o)
+        for (int c = 0; c < 64; ++c) {
+            wk[o * 64 + c] = f[LL::WK + c * 64 + o];
+            wv[o * 64 + c] = f[LL::WV + c * 64 + o];
+        }
+    v[LM::OS + 4] = pack_mma_weight(wk.data(), 64, iota_map(64, 64), iota_map(64, 64), &v[LM::FK]);
+    v[LM::OS + 5] = pack_mma_weight(wv.data(), 64, iota_map(64, 64), iota_map(64, 64), &v[LM::FV]);
+    for (int o = 0; o < 64; ++o) {
+        v[LM::BQ + o] = f[LL::BQ + o];
+        v[LM::BK + o] = f[LL::BK + o];
+        v[LM::BV + o] = f[LL::BV + o];
+    }
+    return v;
+}
+
 std::vector<float> pack_data_bn(const StateDict& sd, const std::string& gp) {
     BnAffine a = bn_affine(sd, gp + "data_bn", 45);
     std::vector<float> v(90);

@@ -43,6 +43,10 @@ HostSmallLstm pack_small_lstm(const StateDict& sd, const std::string& prefix, in
 
 std::vector<float> pack_upper_point(const StateDict& sd);
 std::vector<float> pack_lower_frame(const StateDict& sd);
+// mma.sync (fp16 hi/lo fragment) packing of the folded blobs above (point_layout.h: UpperMmaLayout / LowerMmaLayout)
+float pack_mma_weight(const float* W, int ldw, const std::vector<int>& kmap, const std::vector<int>& nmap, float* out);
+std::vector<float> pack_upper_point_mma(const std::vector<float>& folded);
+std::vector<float> pack_lower_frame_mma(const std::vector<float>& folded);
 
 struct HostGcnLayer {
     std::vector<float> ahat;

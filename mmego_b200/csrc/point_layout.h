@@ -47,4 +47,52 @@ struct LowerFrameLayout {
     static constexpr int TOTAL = BV + D;
 };
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core (mma.sync m16n8k16, fp16 hi/lo split) packing of the same networks: offsets in 32-bit WORDS.
+// A layer with KS k-steps and NT n-tiles is stored as KS*NT*32 uint4 {hi.b0, hi.b1, lo.b0, lo.b1} in fragment order
+// (index (s*NT + j)*32 + lane, see mma_frag.cuh), scaled by a power of two 2^e (undone by OS[layer] = 2^-e), followed
+// by its fp32 bias padded to NT*8.
+constexpr int mma_frag_words(int ks, int nt) { return ks * nt * 32 * 4; }
+
+struct UpperMmaLayout {
+    // layer:            L1      L2      L3      L4 (in: feat24|x0..3|pad)  L5      L6
+    static constexpr int KS1 = 1, NT1 = 1, KS2 = 1, NT2 = 2, KS3 = 1, NT3 = 3, KS4 = 2, NT4 = 4, KS5 = 2, NT5 = 6,
+                         KS6 = 3, NT6 = 8;
+    static constexpr int F1 = 0;
+    static constexpr int BI1 = F1 + mma_frag_words(KS1, NT1);
+    static constexpr int F2 = BI1 + NT1 * 8;
+    static constexpr int BI2 = F2 + mma_frag_words(KS2, NT2);
+    static constexpr int F3 = BI2 + NT2 * 8;
+    static constexpr int BI3 = F3 + mma_frag_words(KS3, NT3);
+    static constexpr int F4 = BI3 + NT3 * 8;
+    static constexpr int BI4 = F4 + mma_frag_words(KS4, NT4);
+    static constexpr int F5 = BI4 + NT4 * 8;
+    static constexpr int BI5 = F5 + mma_frag_words(KS5, NT5);
+    static constexpr int F6 = BI5 + NT5 * 8;
+    static constexpr int BI6 = F6 + mma_frag_words(KS6, NT6);
+    static constexpr int WA = BI6 + NT6 * 8;    // attn weight [64] fp32
+    static constexpr int BA = WA + 64;          // attn bias
+    static constexpr int OS = BA + 1;           // out scales [6]
+    static constexpr int TOTAL = (OS + 6 + 3) / 4 * 4;
+};
+
+struct LowerMmaLayout {
+    // BasePointNet 6->16->32->61(64), then to_q on P' = [feat61 | x y z], to_k / to_v on the 15(16) joint features
+    static constexpr int KS1 = 1, NT1 = 2, KS2 = 1, NT2 = 4, KS3 = 2, NT3 = 8, KSP = 4, NTP = 8;
+    static constexpr int F1 = 0;
+    static constexpr int BI1 = F1 + mma_frag_words(KS1, NT1);
+    static constexpr int F2 = BI1 + NT1 * 8;
+    static constexpr int BI2 = F2 + mma_frag_words(KS2, NT2);
+    static constexpr int F3 = BI2 + NT2 * 8;
+    static constexpr int BI3 = F3 + mma_frag_words(KS3, NT3);
+    static constexpr int FQ = BI3 + NT3 * 8;
+    static constexpr int BQ = FQ + mma_frag_words(KSP, NTP);
+    static constexpr int FK = BQ + 64;
+    static constexpr int BK = FK + mma_frag_words(KSP, NTP);
+    static constexpr int FV = BK + 64;
+    static constexpr int BV = FV + mma_frag_words(KSP, NTP);
+    static constexpr int OS = BV + 64;          // out scales [6]: L1, L2, L3, q, k, v
+    static constexpr int TOTAL = (OS + 6 + 3) / 4 * 4;
+};
+
 }  // namespace mmego

@@ -157,4 +157,12 @@ void warp_exchange(const void* in, void* out, size_t bytes, int src_lane) {
     warp_barrier();
 }
 
+void warp_allgather(const void* in, void* out_all, size_t bytes) {
+    Warp& w = my_warp();
+    std::memcpy(w.buf[lane_id()], in, bytes);
+    warp_barrier();
+    for (int l = 0; l < 32; ++l) std::memcpy(static_cast<unsigned char*>(out_all) + l * bytes, w.buf[l], bytes);
+    warp_barrier();
+}
+
 }  // namespace emul

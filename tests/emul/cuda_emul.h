@@ -36,6 +36,7 @@ struct uint2 { unsigned x, y; };
 static inline float2 make_float2(float x, float y) { return {x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
 static inline int4 make_int4(int x, int y, int z, int w) { return {x, y, z, w}; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return {x, y, z, w}; }
 
 namespace emul {
 struct Ctx {
@@ -47,6 +48,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 void syncthreads();
 void warp_exchange(const void* in, void* out, size_t bytes, int src_lane);
 void warp_barrier();
+void warp_allgather(const void* in, void* out_all, size_t bytes);   // out_all: [32][bytes], bytes <= 32
 int lane_id();
 }  // namespace emul
 
