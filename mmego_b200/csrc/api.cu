@@ -166,6 +166,19 @@ const float* run_small_lstm(mmego_handle* h, const PackedSmallLstmLayer* layers,
     long long ld = in_ld;
     Prof prof(h, "small_lstm", st);
     for (int l = 0; l < 3; ++l) {
+        if (h->small_lstm_gemm) {
+            const size_t so = (size_t)l * 2 * S * kSmallH;
+            launch_lstm_small_mma(cur, ld, layers[l].in, layers[l].mma.p, w.gx, h0 ? h0 + so : nullptr,
+                                  c0 ? c0 + so : nullptr, w.y[l & 1], hn ? hn + so : nullptr, cn ? cn + so : nullptr,
+                                  (int)S, T, h->sm_count, st);
+            cur = w.y[l & 1];
+            ld = 128;
+            const char* gxn[3] = {"small_lstm.gx0", "small_lstm.gx1", "small_lstm.gx2"};
+            const char* yn[3] = {"small_lstm.y0", "small_lstm.y1", "small_lstm.y2"};
+            tap(h, gxn[l], w.gx, (size_t)S * T * 512 * 4, st);
+            tap(h, yn[l], cur, (size_t)S * T * 128 * 4, st);
+            continue;
+        }
         linear(h, layers[l].ih, cur, ld, w.gx, 512, S * T, 0, st);
         const size_t so = (size_t)l * 2 * S * kSmallH;
         launch_lstm_small(w.gx, layers[l].whh.p, h0 ? h0 + so : nullptr, c0 ? c0 + so : nullptr, w.y[l & 1],
@@ -544,6 +557,11 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
         h->point_gemm = (int)value;
         return MMEGO_OK;
     }
+    if (!strcmp(key, "small_lstm_gemm")) {
+        if (value < 0 || value > 1) return fail(h, MMEGO_EINVAL, "small_lstm_gemm must be 0 (fp32 FFMA) or 1 (mma.sync fp16x3)");
+        h->small_lstm_gemm = (int)value;
+        return MMEGO_OK;
+    }
     if (!strcmp(key, "tc_kb_chunk0")) {
         if (value < 0 || value > 64) return fail(h, MMEGO_EINVAL, "tc_kb_chunk0 must be in 0..64");
         h->tc_kb_chunk0 = (int)value;
@@ -616,6 +634,7 @@ int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const 
             for (int l = 0; l < 3; ++l) {
                 HostSmallLstm s = pack_small_lstm(sd, "module1.grnn.", l, l == 0 ? 64 : 128);
                 ok &= upload(h, s.ih, W.lstm[l].ih) && upload(h, s.whh, W.lstm[l].whh);
+                ok &= upload(h, pack_small_lstm_mma(sd, "module1.grnn.", l, l == 0 ? 64 : 128), W.lstm[l].mma);
                 W.lstm[l].in = s.in;
             }
             ok &= upload(h, pack_linear(sd.get("mlpHead.fc1.weight", 128 * 128), sd.get("mlpHead.fc1.bias", 128), 128, {128}), W.fc1);
@@ -652,6 +671,7 @@ int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const 
             for (int l = 0; l < 3; ++l) {
                 HostSmallLstm s = pack_small_lstm(sd, "fusion.rnn_pk.", l, l == 0 ? 192 : 128);
                 ok &= upload(h, s.ih, W.lstm[l].ih) && upload(h, s.whh, W.lstm[l].whh);
+                ok &= upload(h, pack_small_lstm_mma(sd, "fusion.rnn_pk.", l, l == 0 ? 192 : 128), W.lstm[l].mma);
                 W.lstm[l].in = s.in;
             }
             ok &= upload(h, pack_linear(sd.get("fusion.fc0.weight", 128 * 173), sd.get("fusion.fc0.bias", 128), 128, {128, 45}), W.fc0);

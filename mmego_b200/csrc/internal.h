@@ -79,6 +79,9 @@ void launch_lstm_small(const float* gx, const float* whh, const float* h0, const
                        float* cn, int S, int T, cudaStream_t st);
 void launch_upper_point_mma(float* x, const float* R, const float* t, const float* wblob, float* g, float* gw,
                             long long F, int N, int sm_count, cudaStream_t st);
+void launch_lstm_small_mma(const float* x, long long ldx, int In, const float* blob, float* gx, const float* h0,
+                           const float* c0, float* y, float* hn, float* cn, int S, int T, int sm_count,
+                           cudaStream_t st);
 size_t lower_frame_smem_bytes();
 int lower_frame_max_points();
 void launch_lower_frame(float* x, const float* R, const float* t, const float* kfeat, const float* wblob, float* ak,
@@ -121,6 +124,7 @@ struct PackedBigLstmLayer {   // one layer, both directions, H=512, gate-interle
 struct PackedSmallLstmLayer {  // H=64
     PackedGemm ih;             // [512][In] both dirs, column order = recurrent-kernel thread order; bias = b_ih+b_hh
     DevBuf whh;                // [2][256][64]  row = thread order
+    DevBuf mma;                // both GEMMs as mma.sync fragments (pack_small_lstm_mma)
     int in = 0;
 };
 // H=512 layer packed for the tcgen05 path (lstm_tc.cu): fp16 hi/lo planes [2 dirs * 2048 rows][In + 512], scaled by 2^e,
@@ -242,6 +246,7 @@ struct mmego_handle {
     int tc_cta_pair = 1;      // H=512 LSTM kernel: 1 = CTA pairs (cta_group::2, M = 256)
     int gcn_gemm = 0;         // ST-GCN GEMMs: 0 = fp32 FFMA, 1 = tcgen05 fp16x3 (default when available)
     int point_gemm = 1;       // point encoders + cross attention: 0 = fp32 FFMA, 1 = mma.sync fp16x3 (default)
+    int small_lstm_gemm = 1;  // H=64 LSTMs: 0 = fp32 FFMA, 1 = mma.sync fp16x3 (default)
     int tc_kb_chunk0 = 8;     // ... of the first two chunks of every tile
     int tc_kb_chunk = 4;      // fp16x3 mode: K blocks (of 64) per TMEM partial accumulation (see lstm_tc.cu)
     mmego::ImuWeights imu;

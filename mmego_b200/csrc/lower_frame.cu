@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(NT, 4) lower_frame_mma_kernel(float* __restric
                 float sum = (e[0] + e[1]) + (e[2] + e[3]);
                 sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                 sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                const float inv = 1.0f / sum;
+                const float inv = __fdividef(1.0f, sum);     // branch-free (no IEEE slow path between warp-wide MMAs)
                 if (r == 0) { al[0][0] = e[0] * inv; al[0][1] = e[1] * inv; al[1][0] = e[2] * inv; al[1][1] = e[3] * inv; }
                 else { al[0][0] += e[0] * inv; al[0][1] += e[1] * inv; al[1][0] += e[2] * inv; al[1][1] += e[3] * inv; }
             }

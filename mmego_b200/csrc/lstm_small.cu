@@ -11,6 +11,8 @@
 //   * c stays in the registers of lanes 0..7 of each warp.
 // One __syncthreads per timestep.
 #include "internal.h"
+#include "mma_frag.cuh"
+#include "point_layout.h"
 
 namespace mmego {
 
@@ -21,6 +23,11 @@ constexpr int NTH = 256;       // 4 gates x 64 units
 constexpr int SEQ = 8;         // sequences per CTA
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Branch-free variant for the mma.sync kernel.  The IEEE division above carries a slow path (a CALL taken per lane when
+// the denominator leaves [2^-126, 2^126], i.e. for pre-activations beyond +-87, which rnn_pk's first layer reaches);
+// taken divergently right before the next warp-wide mma.sync it left the warp unconverged on the B200 and every later
+// result of that warp was garbage.  __fdividef is MUFU.RCP + FMUL, 2 ulp, and returns 0 for denominators >= 2^126.
+__device__ __forceinline__ float sigmoid_nb(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
 
 // gx   [S][T][2][256]   input projection incl. biases, column = thread order (w*32 + gate*8 + e)
 // whh  [2][256][64]     recurrent weights, row = thread order
@@ -111,6 +118,177 @@ __global__ void __launch_bounds__(NTH) lstm_small_kernel(const float* __restrict
     }
 }
 
+
+// ================================================================================================================
+// Tensor-core version (default): both GEMMs of the layer on mma.sync m16n8k16 fragments (mma_frag.cuh, fp16 hi/lo
+// split products, fp32 accumulation).  Gate columns are interleaved per 8 units (n-tile 4u + gate), see
+// pack_small_lstm_mma.
+//   lstm_proj_mma_kernel<KS>: gx[M, 512] = x[M, In] W_ih^T + b for all timesteps and both directions.  A CTA owns a
+//     slab of 128 gate columns (its fragments staged once in shared memory) and walks over 64-row tiles; a warp holds
+//     the A fragments of its 16 rows in registers for the whole slab.
+//   lstm_rec_mma_kernel: the recurrence.  A warp owns 16 sequences of one direction for all T steps: h_{t-1} lives in
+//     registers AS the A fragments of the next step (the C fragment of unit group u is half of k-step u/2), c in
+//     registers, W_hh fragments in shared memory (64 KB).  No block-level synchronisation inside the time loop.
+// ================================================================================================================
+constexpr int PROJ_NT = 128;
+template <int KS>
+__global__ void __launch_bounds__(PROJ_NT) lstm_proj_mma_kernel(const float* __restrict__ x, long long ldx,
+                                                                const float* __restrict__ blob,
+                                                                float* __restrict__ gx, long long M) {
+    MMEGO_DYN_SMEM(uint4, wf);                       // [KS][16 n-tiles][32 lanes]
+    __shared__ float sbias[128];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+    const int slab = blockIdx.y, dir = slab >> 1, jbase = (slab & 1) * 16;
+    const size_t ihw = (size_t)mma_frag_words(KS, 32), hhw = (size_t)mma_frag_words(4, 32);
+    const uint4* src = reinterpret_cast<const uint4*>(blob + dir * ihw);
+    for (int i = tid; i < KS * 16 * 32; i += PROJ_NT) {
+        const int s = i / 512, r = i % 512;
+        wf[i] = src[(s * 32 + jbase) * 32 + r];
+    }
+    sbias[tid] = blob[2 * ihw + dir * 256 + jbase * 8 + tid];
+    const float os = blob[2 * ihw + 512 + 2 * hhw + dir];
+    __syncthreads();
+    for (long long r0 = ((long long)blockIdx.x * 4 + warp) * 16; r0 < M; r0 += (long long)gridDim.x * 64) {
+        uint32_t ah[KS][4], al[KS][4];
+        const bool live0 = r0 + g < M, live1 = r0 + g + 8 < M;
+        const float* x0 = x + (r0 + g) * ldx;
+        const float* x1 = x + (r0 + g + 8) * ldx;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int col = 16 * s + 8 * hh + 2 * tq;
+                const float2 v0 = live0 ? *reinterpret_cast<const float2*>(x0 + col) : make_float2(0.f, 0.f);
+                const float2 v1 = live1 ? *reinterpret_cast<const float2*>(x1 + col) : make_float2(0.f, 0.f);
+                frag::split2(v0.x, v0.y, ah[s][2 * hh], al[s][2 * hh]);
+                frag::split2(v1.x, v1.y, ah[s][2 * hh + 1], al[s][2 * hh + 1]);
+            }
+        }
+        float* o0 = gx + (r0 + g) * 512 + slab * 128 + 2 * tq;
+        float* o1 = gx + (r0 + g + 8) * 512 + slab * 128 + 2 * tq;
+#pragma unroll 1
+        for (int jg = 0; jg < 4; ++jg) {
+            float out[4][4];
+            frag::dense_tile<KS, 4, false, 16>(wf, sbias, os, ah, al, out, lane, 4 * jg);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (live0) *reinterpret_cast<float2*>(o0 + 8 * (4 * jg + j)) = make_float2(out[j][0], out[j][1]);
+                if (live1) *reinterpret_cast<float2*>(o1 + 8 * (4 * jg + j)) = make_float2(out[j][2], out[j][3]);
+            }
+        }
+    }
+}
+
+constexpr int REC_NT = 128;
+__device__ __forceinline__ float2 ld2_or_zero(const float* p, bool live) {
+    return live ? *reinterpret_cast<const float2*>(p) : make_float2(0.f, 0.f);
+}
+
+// gx [S][T][2][256] (mma column order), blob as packed by pack_small_lstm_mma (KS = In/16), h0/c0/hn/cn [2][S][64]
+__global__ void __launch_bounds__(REC_NT) lstm_rec_mma_kernel(const float* __restrict__ gx,
+                                                              const float* __restrict__ blob, int KS,
+                                                              const float* __restrict__ h0,
+                                                              const float* __restrict__ c0, float* __restrict__ y,
+                                                              float* __restrict__ hn, float* __restrict__ cn, int S,
+                                                              int T) {
+    MMEGO_DYN_SMEM(uint4, wf);                       // [4][32 n-tiles][32 lanes]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+    const int dir = blockIdx.y;
+    const size_t ihw = (size_t)mma_frag_words(KS, 32), hhw = (size_t)mma_frag_words(4, 32);
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(blob + 2 * ihw + 512 + dir * hhw);
+        for (int i = tid; i < 4 * 32 * 32; i += REC_NT) wf[i] = src[i];
+    }
+    const float os = blob[2 * ihw + 512 + 2 * hhw + 2 + dir];
+    __syncthreads();
+    const long long q0 = (long long)blockIdx.x * 64 + warp * 16 + g, q1 = q0 + 8;   // this lane's two sequences
+    const bool live0 = q0 < S, live1 = q1 < S;
+    float c[8][4];
+    uint32_t ah[4][4], al[4][4];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int col = 8 * u + 2 * tq;
+        const float2 ca = ld2_or_zero(c0 ? c0 + ((long long)dir * S + q0) * H + col : nullptr, live0 && c0);
+        const float2 cb = ld2_or_zero(c0 ? c0 + ((long long)dir * S + q1) * H + col : nullptr, live1 && c0);
+        c[u][0] = ca.x; c[u][1] = ca.y; c[u][2] = cb.x; c[u][3] = cb.y;
+        const float2 ha = ld2_or_zero(h0 ? h0 + ((long long)dir * S + q0) * H + col : nullptr, live0 && h0);
+        const float2 hb = ld2_or_zero(h0 ? h0 + ((long long)dir * S + q1) * H + col : nullptr, live1 && h0);
+        frag::split2(ha.x, ha.y, ah[u >> 1][2 * (u & 1)], al[u >> 1][2 * (u & 1)]);
+        frag::split2(hb.x, hb.y, ah[u >> 1][2 * (u & 1) + 1], al[u >> 1][2 * (u & 1) + 1]);
+    }
+    float hl[8][4];                                   // last h (for hn)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) hl[u][0] = hl[u][1] = hl[u][2] = hl[u][3] = 0.f;
+
+    for (int step = 0; step < T; ++step) {
+        const int tt = dir ? (T - 1 - step) : step;
+        const float* g0 = gx + ((q0 * T + tt) * 2 + dir) * 256 + 2 * tq;
+        const float* g1 = gx + ((q1 * T + tt) * 2 + dir) * 256 + 2 * tq;
+        float* y0 = y + (q0 * T + tt) * (2 * H) + dir * H + 2 * tq;
+        float* y1 = y + (q1 * T + tt) * (2 * H) + dir * H + 2 * tq;
+        uint32_t nh[4][4], nl[4][4];
+        float2 pa[4], pb[4];                          // gx of the unit group in flight (rows g / g+8, 4 gates)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { pa[k] = ld2_or_zero(g0 + 8 * k, live0); pb[k] = ld2_or_zero(g1 + 8 * k, live1); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float2 na[4], nb[4];
+            if (u < 7) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    na[k] = ld2_or_zero(g0 + 8 * (4 * (u + 1) + k), live0);
+                    nb[k] = ld2_or_zero(g1 + 8 * (4 * (u + 1) + k), live1);
+                }
+            }
+            float pre[4][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float big[4] = {0.f, 0.f, 0.f, 0.f}, small[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int s = 0; s < 4; ++s) frag::mma3(big, small, ah[s], al[s], wf[(s * 32 + 4 * u + k) * 32 + lane]);
+                pre[k][0] = fmaf(big[0] + small[0], os, pa[k].x);
+                pre[k][1] = fmaf(big[1] + small[1], os, pa[k].y);
+                pre[k][2] = fmaf(big[2] + small[2], os, pb[k].x);
+                pre[k][3] = fmaf(big[3] + small[3], os, pb[k].y);
+            }
+            float hv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float ig = sigmoid_nb(pre[0][i]), fg = sigmoid_nb(pre[1][i]), gg = tanhf(pre[2][i]),
+                            og = sigmoid_nb(pre[3][i]);
+                const float cnew = fg * c[u][i] + ig * gg;
+                c[u][i] = cnew;
+                hv[i] = og * tanhf(cnew);
+                hl[u][i] = hv[i];
+            }
+            if (live0) *reinterpret_cast<float2*>(y0 + 8 * u) = make_float2(hv[0], hv[1]);
+            if (live1) *reinterpret_cast<float2*>(y1 + 8 * u) = make_float2(hv[2], hv[3]);
+            frag::split2(hv[0], hv[1], nh[u >> 1][2 * (u & 1)], nl[u >> 1][2 * (u & 1)]);
+            frag::split2(hv[2], hv[3], nh[u >> 1][2 * (u & 1) + 1], nl[u >> 1][2 * (u & 1) + 1]);
+            if (u < 7) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { pa[k] = na[k]; pb[k] = nb[k]; }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ah[s][i] = nh[s][i]; al[s][i] = nl[s][i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int col = 8 * u + 2 * tq;
+        if (hn && T > 0) {
+            if (live0) *reinterpret_cast<float2*>(hn + ((long long)dir * S + q0) * H + col) = make_float2(hl[u][0], hl[u][1]);
+            if (live1) *reinterpret_cast<float2*>(hn + ((long long)dir * S + q1) * H + col) = make_float2(hl[u][2], hl[u][3]);
+        }
+        if (cn) {
+            if (live0) *reinterpret_cast<float2*>(cn + ((long long)dir * S + q0) * H + col) = make_float2(c[u][0], c[u][1]);
+            if (live1) *reinterpret_cast<float2*>(cn + ((long long)dir * S + q1) * H + col) = make_float2(c[u][2], c[u][3]);
+        }
+    }
+}
+
 }  // namespace
 
 void launch_lstm_small(const float* gx, const float* whh, const float* h0, const float* c0, float* y, float* hn,
@@ -118,6 +296,35 @@ void launch_lstm_small(const float* gx, const float* whh, const float* h0, const
     if (S <= 0 || T <= 0) return;
     dim3 grid((S + SEQ - 1) / SEQ, 2);
     MMEGO_LAUNCH(lstm_small_kernel, grid, dim3(NTH), 0, st, gx, whh, h0, c0, y, hn, cn, S, T);
+}
+
+// One H=64 bidirectional layer on mma.sync: x [S*T, In] (row stride ldx) -> gx (workspace [S*T, 512]) -> y [S, T, 128]
+void launch_lstm_small_mma(const float* x, long long ldx, int In, const float* blob, float* gx, const float* h0,
+                           const float* c0, float* y, float* hn, float* cn, int S, int T, int sm_count,
+                           cudaStream_t st) {
+    if (S <= 0 || T <= 0) return;
+    const int KS = In / 16;
+    const long long M = (long long)S * T;
+    const size_t psmem = (size_t)KS * 16 * 32 * sizeof(uint4), rsmem = (size_t)4 * 32 * 32 * sizeof(uint4);
+    static bool attr_set[64] = {false};
+    if (first_use_on_device(attr_set)) {
+        cudaFuncSetAttribute(lstm_proj_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16 * 32 * 16);
+        cudaFuncSetAttribute(lstm_proj_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 16 * 32 * 16);
+        cudaFuncSetAttribute(lstm_proj_mma_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 16 * 32 * 16);
+        cudaFuncSetAttribute(lstm_rec_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+    }
+    const long long tiles = (M + 63) / 64;
+    const long long per_slab = (long long)sm_count * 2 / 4 > 0 ? (long long)sm_count * 2 / 4 : 1;
+    dim3 pgrid((unsigned)(tiles < per_slab ? tiles : per_slab), 4);
+    if (KS == 4) {
+        MMEGO_LAUNCH(lstm_proj_mma_kernel<4>, pgrid, dim3(PROJ_NT), psmem, st, x, ldx, blob, gx, M);
+    } else if (KS == 8) {
+        MMEGO_LAUNCH(lstm_proj_mma_kernel<8>, pgrid, dim3(PROJ_NT), psmem, st, x, ldx, blob, gx, M);
+    } else {
+        MMEGO_LAUNCH(lstm_proj_mma_kernel<12>, pgrid, dim3(PROJ_NT), psmem, st, x, ldx, blob, gx, M);
+    }
+    dim3 rgrid((unsigned)((S + 63) / 64), 2);
+    MMEGO_LAUNCH(lstm_rec_mma_kernel, rgrid, dim3(REC_NT), rsmem, st, gx, blob, KS, h0, c0, y, hn, cn, S, T);
 }
 
 }  // namespace mmego

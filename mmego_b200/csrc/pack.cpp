@@ -318,6 +318,33 @@ std::vector<float> pack_lower_frame_mma(const std::vector<float>& f) {
     return v;
 }
 
+// H=64 bi-LSTM layer for lstm_small.cu's mma.sync kernels.  Gate column order (both GEMMs): n-tile j = 4u + gate holds
+// units 8u..8u+7 of gate (i, f, g, o), so the four gates of a cell sit in the same lane of four neighbouring n-tiles.
+//   blob = ih frags [2 dirs][KS=In/16][32 n-tiles][32 lanes] uint4 | bias [2][256] (b_ih + b_hh) | hh frags [2][4][32][32]
+//          uint4 | out scales {ih d0, ih d1, hh d0, hh d1}
+std::vector<float> pack_small_lstm_mma(const StateDict& sd, const std::string& prefix, int layer, int In) {
+    const int H = kSmallH, KS = In / 16;
+    if (In % 16) throw std::runtime_error("pack_small_lstm_mma: In must be a multiple of 16");
+    const size_t ihw = (size_t)mma_frag_words(KS, 32), hhw = (size_t)mma_frag_words(4, 32);
+    std::vector<float> v(2 * ihw + 512 + 2 * hhw + 4, 0.f);
+    std::vector<int> nmap(256);
+    for (int j = 0; j < 32; ++j)
+        for (int n = 0; n < 8; ++n) nmap[8 * j + n] = (j & 3) * H + 8 * (j >> 2) + n;
+    const char* sfx[2] = {"", "_reverse"};
+    for (int d = 0; d < 2; ++d) {
+        const std::string k = "l" + std::to_string(layer) + sfx[d];
+        const float* wih = sd.get(prefix + "weight_ih_" + k, (long long)4 * H * In);
+        const float* whh = sd.get(prefix + "weight_hh_" + k, (long long)4 * H * H);
+        const float* bih = sd.get(prefix + "bias_ih_" + k, 4 * H);
+        const float* bhh = sd.get(prefix + "bias_hh_" + k, 4 * H);
+        float* tail = &v[2 * ihw + 512 + 2 * hhw];
+        tail[d] = pack_mma_weight(wih, In, iota_map(In, In), nmap, &v[d * ihw]);
+        tail[2 + d] = pack_mma_weight(whh, H, iota_map(H, H), nmap, &v[2 * ihw + 512 + d * hhw]);
+        for (int c = 0; c < 256; ++c) v[2 * ihw + d * 256 + c] = bih[nmap[c]] + bhh[nmap[c]];
+    }
+    return v;
+}
+
 std::vector<float> pack_data_bn(const StateDict& sd, const std::string& gp) {
     BnAffine a = bn_affine(sd, gp + "data_bn", 45);
     std::vector<float> v(90);
