@@ -289,7 +289,7 @@ int imu_chunk_forward_tc(mmego_handle* h, const float* imu, float* R, float* t, 
     auto lo = [&](void* const* planes) { return npass == 3 ? planes[1] : nolo; };
     {
         Prof p(h, "imu.fc1", st);
-        tc_imu_fc1(imu, W.fc1, w.u[0], lo(w.u), S * n, st);                               // Net/IMU_Net.py:79
+        tc_imu_fc1(imu, W.fc1_mma.p, w.u[0], lo(w.u), S * n, h->sm_count, st);                               // Net/IMU_Net.py:79
     }
     auto tap_split = [&](const char* name, void* const* planes, long long elems) {
         auto it = h->taps.find(name);
@@ -594,7 +594,10 @@ int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const 
             ImuWeights& W = h->imu;
             W.ready = false;
             const int H = kImuH;
-            ok &= upload(h, pack_linear(sd.get("fc1.weight", H * kImuFeat), sd.get("fc1.bias", H), H, {kImuFeat}), W.fc1);
+            {
+                const HostPackedGemm fc1 = pack_linear(sd.get("fc1.weight", H * kImuFeat), sd.get("fc1.bias", H), H, {kImuFeat});
+                ok &= upload(h, fc1, W.fc1) && upload(h, pack_imu_fc1_mma(fc1), W.fc1_mma);
+            }
             for (int l = 0; l < 2; ++l) {
                 HostBigLstm f = pack_big_lstm(sd, "rnn_fast.", l, l == 0 ? H : 2 * H, H);
                 HostBigLstm s = pack_big_lstm(sd, "rnn_slow.", l, 2 * H, H);

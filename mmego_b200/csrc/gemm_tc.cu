@@ -335,6 +335,84 @@ __global__ void gcn_agg_split_kernel(const __half* __restrict__ yhi, const __hal
     }
 }
 
+// The same aggregation for C % 8 == 0 (layers 1 and 2), written for HBM: the kernel above issues 30 two-byte loads
+// per output pair.  Here a CTA stages the 15 x C inputs of a few frames in shared memory (16-byte plane loads, hi + lo
+// summed once), then thread (w, 8-channel chunk) runs the dense 15-term contraction for both partitions from shared
+// memory and writes its results with four 16-byte stores.  Double-buffered: one barrier per group of frames.
+template <int C>
+__global__ void __launch_bounds__(256) gcn_agg8_split_kernel(const __half* __restrict__ yhi, const __half* __restrict__ ylo,
+                                                             const float* __restrict__ ahat, __half* __restrict__ ohi,
+                                                             __half* __restrict__ olo, long long F) {
+    constexpr int NCH = C / 8;                  // 8-channel chunks per row
+    constexpr int ITEMS = kGcnV * NCH;          // (joint, chunk) pairs per frame
+    constexpr int FPB = 256 / ITEMS;            // frames per CTA iteration
+    __shared__ float sa[2 * kGcnV * kGcnV];
+    __shared__ __align__(16) float ys[2][2][FPB][kGcnV][NCH][4];   // [buffer][first/second half of a chunk]
+    for (int i = threadIdx.x; i < 2 * kGcnV * kGcnV; i += 256) sa[i] = ahat[i];
+    const int tid = threadIdx.x;
+    const bool active = tid < FPB * ITEMS;
+    const int fl = tid / ITEMS, it = tid % ITEMS, w = it / NCH, ch = it % NCH;
+    const long long ngroups = (F + FPB - 1) / FPB;
+    auto stage = [&](long long grp, int buf) {
+        const long long f = grp * FPB + fl;
+        if (!active) return;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (f < F) {
+            const long long o = (f * kGcnV + w) * C + ch * 8;
+            const uint4 a = *reinterpret_cast<const uint4*>(yhi + o);
+            const uint4 b = *reinterpret_cast<const uint4*>(ylo + o);
+            const __half2* ah = reinterpret_cast<const __half2*>(&a);
+            const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 x = __half22float2(ah[k]), y = __half22float2(bh[k]);
+                v[2 * k] = x.x + y.x;
+                v[2 * k + 1] = x.y + y.y;
+            }
+        }
+        *reinterpret_cast<float4*>(ys[buf][0][fl][w][ch]) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(ys[buf][1][fl][w][ch]) = make_float4(v[4], v[5], v[6], v[7]);
+    };
+    int buf = 0;
+    if (blockIdx.x < ngroups) stage(blockIdx.x, 0);
+    __syncthreads();
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x, buf ^= 1) {
+        if (grp + gridDim.x < ngroups) stage(grp + gridDim.x, buf ^ 1);
+        const long long f = grp * FPB + fl;
+        if (active && f < F) {
+            float a0[8], a1[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a0[k] = a1[k] = 0.f;
+#pragma unroll
+            for (int v = 0; v < kGcnV; ++v) {
+                const float c0 = sa[v * kGcnV + w], c1 = sa[kGcnV * kGcnV + v * kGcnV + w];
+                const float4 p = *reinterpret_cast<const float4*>(ys[buf][0][fl][v][ch]);
+                const float4 q = *reinterpret_cast<const float4*>(ys[buf][1][fl][v][ch]);
+                const float x[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    a0[k] = fmaf(x[k], c0, a0[k]);
+                    a1[k] = fmaf(x[k], c1, a1[k]);
+                }
+            }
+            __align__(16) __half h0[8], l0[8], h1[8], l1[8];     // values already carry the 2^4 scale
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                h0[k] = __float2half_rn(a0[k]);
+                l0[k] = __float2half_rn(a0[k] - __half2float(h0[k]));
+                h1[k] = __float2half_rn(a1[k]);
+                l1[k] = __float2half_rn(a1[k] - __half2float(h1[k]));
+            }
+            const long long o = (f * kGcnV + w) * (2 * C) + ch * 8;
+            *reinterpret_cast<uint4*>(ohi + o) = *reinterpret_cast<const uint4*>(h0);
+            *reinterpret_cast<uint4*>(olo + o) = *reinterpret_cast<const uint4*>(l0);
+            *reinterpret_cast<uint4*>(ohi + o + C) = *reinterpret_cast<const uint4*>(h1);
+            *reinterpret_cast<uint4*>(olo + o + C) = *reinterpret_cast<const uint4*>(l1);
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -490,13 +568,24 @@ void tc_gcn_agg(const void* yhi, const void* ylo, const float* ahat, void* ohi, 
                 int OS, int sm_count, cudaStream_t st) {
     const long long total = F * kGcnV * C;
     if (total <= 0) return;
+    const __half* ih = static_cast<const __half*>(yhi);
+    const __half* il = static_cast<const __half*>(ylo);
+    __half* oh = static_cast<__half*>(ohi);
+    __half* ol = static_cast<__half*>(olo);
+    ++g_launches;
+    if ((C == 32 || C == 64) && CS == C && OS == 2 * C) {
+        const int fpb = 256 / (kGcnV * (C / 8));
+        long long blocks = (F + fpb - 1) / fpb;
+        const long long cap = (long long)sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        if (C == 32) gcn_agg8_split_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(ih, il, ahat, oh, ol, F);
+        else gcn_agg8_split_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(ih, il, ahat, oh, ol, F);
+        return;
+    }
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)sm_count * 16;
     if (blocks > cap) blocks = cap;
-    ++g_launches;
-    gcn_agg_split_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __half*>(yhi), static_cast<const __half*>(ylo),
-                                                           ahat, static_cast<__half*>(ohi), static_cast<__half*>(olo), F,
-                                                           C, CS, OS);
+    gcn_agg_split_kernel<<<(unsigned)blocks, 256, 0, st>>>(ih, il, ahat, oh, ol, F, C, CS, OS);
 }
 
 }  // namespace mmego

@@ -160,6 +160,7 @@ struct ImuWeights {
     bool tc_ready = false;
     TcLstmLayer tc_fast[2], tc_slow[2];
     PackedGemm fc1;
+    DevBuf fc1_mma;    // fc1 as mma.sync fragments (pack_imu_fc1_mma)
     PackedBigLstmLayer fast[2], slow[2];
     DevBuf attn;       // [1024] + [1] bias at the end
     DevBuf fc2;        // [9][1024] + [9]
@@ -206,7 +207,8 @@ bool tc_supported();
 bool tc_pack_layer(mmego_handle* h, const StateDict& sd, const std::string& prefix, int layer, int In, TcLstmLayer& out);
 int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const void* xlo, void* yhi, void* ylo,
                   float* cstate, long long S, long long Spad, int T, int npass, cudaStream_t st);
-void tc_imu_fc1(const float* imu, const PackedGemm& fc1, void* uhi, void* ulo, long long rows, cudaStream_t st);
+void tc_imu_fc1(const float* imu, const float* fc1_mma, void* uhi, void* ulo, long long rows, int sm_count,
+                cudaStream_t st);
 void tc_imu_pool(const void* yhi, const void* ylo, const float* attn, void* shi, void* slo, long long F, int n,
                  cudaStream_t st);
 void tc_imu_decode(const void* ghi, const void* glo, const float* fc2, float* R, float* t, long long F, cudaStream_t st);

@@ -26,6 +26,8 @@
 #include "internal.h"
 #include "pack.h"
 #include "tc_common.cuh"
+#include "mma_frag.cuh"
+#include "point_layout.h"
 
 namespace mmego {
 
@@ -413,45 +415,59 @@ __device__ __forceinline__ void store_split(__half* hi, __half* lo, long long i,
     if (lo) lo[i] = __float2half_rn(v - __half2float(h));
 }
 
-// fc1 + ReLU (Net/IMU_Net.py:79): imu [rows,15] -> u [rows,512] as fp16 hi/lo planes.  HBM-bound (writes 2 KB per row).
-constexpr int FC1_ROWS = 128;
-__global__ void __launch_bounds__(256) imu_fc1_split_kernel(const float* __restrict__ imu, const float* __restrict__ w,
-                                                            const float* __restrict__ b, int ldw,
-                                                            __half* __restrict__ uhi, __half* __restrict__ ulo,
-                                                            long long rows) {
-    __shared__ float xs[FC1_ROWS][16];
-    const int tid = threadIdx.x;
-    const long long r0 = (long long)blockIdx.x * FC1_ROWS;
-    for (int i = tid; i < FC1_ROWS * 16; i += 256) {
-        const int r = i / 16, c = i % 16;
-        xs[r][c] = (c < kImuFeat && (r0 + r) < rows) ? imu[(r0 + r) * kImuFeat + c] : 0.f;
-    }
-    // thread owns output channels 2*tid, 2*tid+1 of every row of the tile; its 30 weights stay in registers
-    float w0[kImuFeat], w1[kImuFeat];
-#pragma unroll
-    for (int k = 0; k < kImuFeat; ++k) {
-        w0[k] = w[(2 * tid) * ldw + k];
-        w1[k] = w[(2 * tid + 1) * ldw + k];
-    }
-    const float b0 = b[2 * tid], b1 = b[2 * tid + 1];
+// fc1 + ReLU (Net/IMU_Net.py:79): imu [rows,15] -> u [rows,512] as fp16 hi/lo planes.  HBM-bound (writes 2 KB per
+// row against 7.7 KFLOP), so the 15 -> 512 projection runs on mma.sync (mma_frag.cuh, fp16x3) to keep the issue slots
+// for the split/pack/store epilogue: a warp owns 16 rows, one k-step, 64 n-tiles; the column permutation of
+// pack_imu_fc1_mma gives every lane 8 consecutive channels per row = one 16-byte store per plane.
+constexpr int FC1_WORDS = mma_frag_words(1, 64);
+__global__ void __launch_bounds__(256) imu_fc1_mma_kernel(const float* __restrict__ imu, const float* __restrict__ blob,
+                                                          __half* __restrict__ uhi, __half* __restrict__ ulo,
+                                                          long long rows) {
+    extern __shared__ __align__(16) uint32_t fsm[];    // frags [64][32] uint4 | bias [512]
+    for (int i = threadIdx.x * 4; i < FC1_WORDS + kImuH; i += 256 * 4)
+        *reinterpret_cast<uint4*>(fsm + i) = *reinterpret_cast<const uint4*>(blob + i);
+    const float os = blob[FC1_WORDS + kImuH];
     __syncthreads();
-    const int nr = (int)((rows - r0) < FC1_ROWS ? (rows - r0) : FC1_ROWS);
-#pragma unroll 4
-    for (int r = 0; r < nr; ++r) {
-        float a0 = b0, a1 = b1;
-#pragma unroll
-        for (int k = 0; k < kImuFeat; ++k) {
-            a0 = fmaf(w0[k], xs[r][k], a0);
-            a1 = fmaf(w1[k], xs[r][k], a1);
+    const uint4* wf = reinterpret_cast<const uint4*>(fsm);
+    const float* bias = reinterpret_cast<const float*>(fsm + FC1_WORDS);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tq = lane & 3;
+    for (long long r0 = ((long long)blockIdx.x * 8 + warp) * 16; r0 < rows; r0 += (long long)gridDim.x * 128) {
+        const long long ra = r0 + g, rb = r0 + g + 8;
+        const bool la = ra < rows, lb = rb < rows;
+        const float* pa = imu + ra * kImuFeat;
+        const float* pb = imu + rb * kImuFeat;
+        uint32_t ah[1][4], al[1][4];
+        {
+            const int c = 2 * tq;
+            const float a0 = la ? pa[c] : 0.f, a1 = la ? pa[c + 1] : 0.f;
+            const float b0 = lb ? pb[c] : 0.f, b1 = lb ? pb[c + 1] : 0.f;
+            const float a2 = la ? pa[c + 8] : 0.f, a3 = (la && c + 9 < kImuFeat) ? pa[c + 9] : 0.f;
+            const float b2 = lb ? pb[c + 8] : 0.f, b3 = (lb && c + 9 < kImuFeat) ? pb[c + 9] : 0.f;
+            frag::split2(a0, a1, ah[0][0], al[0][0]);
+            frag::split2(b0, b1, ah[0][1], al[0][1]);
+            frag::split2(a2, a3, ah[0][2], al[0][2]);
+            frag::split2(b2, b3, ah[0][3], al[0][3]);
         }
-        a0 = fminf(fmaxf(a0, 0.f) * kActScale, 65000.f);
-        a1 = fminf(fmaxf(a1, 0.f) * kActScale, 65000.f);
-        const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
-        const long long o = (r0 + r) * kImuH + 2 * tid;
-        *reinterpret_cast<__half2*>(uhi + o) = __halves2half2(h0, h1);
-        if (ulo)
-            *reinterpret_cast<__half2*>(ulo + o) =
-                __halves2half2(__float2half_rn(a0 - __half2float(h0)), __float2half_rn(a1 - __half2float(h1)));
+#pragma unroll 2
+        for (int q = 0; q < 16; ++q) {
+            float out[4][4];
+            frag::dense_tile<1, 4, true, 64>(wf, bias, os, ah, al, out, lane, 4 * q);
+            uint32_t h0[4], l0[4], h1[4], l1[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                frag::split2(fminf(out[j][0] * kActScale, 65000.f), fminf(out[j][1] * kActScale, 65000.f), h0[j], l0[j]);
+                frag::split2(fminf(out[j][2] * kActScale, 65000.f), fminf(out[j][3] * kActScale, 65000.f), h1[j], l1[j]);
+            }
+            const long long ca = ra * kImuH + 32 * q + 8 * tq, cb = rb * kImuH + 32 * q + 8 * tq;
+            if (la) {
+                *reinterpret_cast<uint4*>(uhi + ca) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+                if (ulo) *reinterpret_cast<uint4*>(ulo + ca) = make_uint4(l0[0], l0[1], l0[2], l0[3]);
+            }
+            if (lb) {
+                *reinterpret_cast<uint4*>(uhi + cb) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+                if (ulo) *reinterpret_cast<uint4*>(ulo + cb) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+            }
+        }
     }
 }
 
@@ -478,47 +494,95 @@ __device__ __forceinline__ void load8(const __half* hi, const __half* lo, long l
     for (int k = 0; k < 8; ++k) v[k] *= kActInv;
 }
 
-// attention pooling over the n samples of a frame (Net/IMU_Net.py:82-83) on split planes: y [F,n,1024] -> s [F,1024]
-__global__ void __launch_bounds__(128) imu_pool_split_kernel(const __half* __restrict__ yhi, const __half* __restrict__ ylo,
-                                                             const float* __restrict__ attn, __half* __restrict__ shi,
-                                                             __half* __restrict__ slo, long long F, int n) {
-    __shared__ float sc[64];
-    __shared__ float part[4][64];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const long long f = blockIdx.x;
-    const long long base = f * (long long)n * 1024;
-    float aw[8];
+// attention pooling over the n samples of a frame (Net/IMU_Net.py:82-83) on split planes: y [F,n,1024] -> s [F,1024].
+// HBM-bound: 4 KB (8 KB with the lo plane) in per sample, read ONCE.  One warp owns a frame: lane l holds channels
+// i*256 + 8l .. +7 (i = 0..3) of every sample, the score is a warp reduction, and the softmax is folded in online
+// (running max / sum / weighted channel sums), so there is no second pass over y, no shared memory and no block barrier.
+// The next sample's 8 x 16 B loads are issued before the current one is consumed.
+struct PoolRow {
+    uint4 h[4], l[4];
+};
+__device__ __forceinline__ void pool_load(const __half* yhi, const __half* ylo, long long off, int lane, PoolRow& r) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) aw[k] = attn[tid * 8 + k];
-    // thread owns channels [8 tid, 8 tid + 8) of every sample; scores need a block reduction per sample
+    for (int i = 0; i < 4; ++i) {
+        r.h[i] = *reinterpret_cast<const uint4*>(yhi + off + i * 256 + lane * 8);
+        if (ylo) r.l[i] = *reinterpret_cast<const uint4*>(ylo + off + i * 256 + lane * 8);
+    }
+}
+__device__ __forceinline__ void pool_unpack(const PoolRow& r, bool has_lo, float* v) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2* ah = reinterpret_cast<const __half2*>(&r.h[i]);
+        const __half2* bh = reinterpret_cast<const __half2*>(&r.l[i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float2 f = __half22float2(ah[k]);
+            if (has_lo) {
+                const float2 g = __half22float2(bh[k]);
+                f.x += g.x;
+                f.y += g.y;
+            }
+            v[i * 8 + 2 * k] = f.x * kActInv;
+            v[i * 8 + 2 * k + 1] = f.y * kActInv;
+        }
+    }
+}
+constexpr int POOL_WARPS = 4;
+__global__ void __launch_bounds__(POOL_WARPS * 32) imu_pool_split_kernel(const __half* __restrict__ yhi,
+                                                                        const __half* __restrict__ ylo,
+                                                                        const float* __restrict__ attn,
+                                                                        __half* __restrict__ shi, __half* __restrict__ slo,
+                                                                        long long F, int n) {
+    const int lane = threadIdx.x & 31;
+    const long long f = (long long)blockIdx.x * POOL_WARPS + (threadIdx.x >> 5);
+    if (f >= F) return;
+    float aw[32];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) aw[i * 8 + k] = attn[i * 256 + lane * 8 + k];
+    const float ab = attn[1024];
+    const bool has_lo = ylo != nullptr;
+    const long long base = f * (long long)n * 1024;
+    float m = -INFINITY, sum = 0.f, acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+    PoolRow cur, nxt;
+    pool_load(yhi, ylo, base, lane, cur);
     for (int s0 = 0; s0 < n; ++s0) {
-        float v[8];
-        load8(yhi, ylo, base + (long long)s0 * 1024 + tid * 8, v);
+        if (s0 + 1 < n) pool_load(yhi, ylo, base + (long long)(s0 + 1) * 1024, lane, nxt);
+        float v[32];
+        pool_unpack(cur, has_lo, v);
         float a = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) a = fmaf(v[k], aw[k], a);
+        for (int k = 0; k < 32; ++k) a = fmaf(v[k], aw[k], a);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) part[w][s0] = a;
+        a += ab;
+        const float nm = fmaxf(m, a);
+        const float r = expf(m - nm);          // first sample: exp(-inf) = 0
+        const float w = expf(a - nm);
+        sum = fmaf(sum, r, w);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc[k] = fmaf(acc[k], r, w * v[k]);
+        m = nm;
+        cur = nxt;
     }
-    __syncthreads();
-    if (tid < n) sc[tid] = part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid] + attn[1024];
-    __syncthreads();
-    float m = -INFINITY;
-    for (int i = 0; i < n; ++i) m = fmaxf(m, sc[i]);
-    float sum = 0.f;
-    for (int i = 0; i < n; ++i) sum += expf(sc[i] - m);
     const float inv = 1.0f / sum;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int i = 0; i < n; ++i) {
-        const float wgt = expf(sc[i] - m) * inv;
-        float v[8];
-        load8(yhi, ylo, base + (long long)i * 1024 + tid * 8, v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+    for (int i = 0; i < 4; ++i) {
+        __align__(16) __half hi[8];
+        __align__(16) __half lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float val = fminf(fmaxf(acc[i * 8 + k] * inv * kActScale, -65000.f), 65000.f);
+            hi[k] = __float2half_rn(val);
+            lo[k] = __float2half_rn(val - __half2float(hi[k]));
+        }
+        const long long o = f * 1024 + i * 256 + lane * 8;
+        *reinterpret_cast<uint4*>(shi + o) = *reinterpret_cast<const uint4*>(hi);
+        if (slo) *reinterpret_cast<uint4*>(slo + o) = *reinterpret_cast<const uint4*>(lo);
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) store_split(shi, slo, f * 1024 + tid * 8 + k, acc[k]);
 }
 
 __device__ __forceinline__ void ortho6d_cols(const float* a6, float eps, float* m) {
@@ -535,34 +599,57 @@ __device__ __forceinline__ void ortho6d_cols(const float* a6, float eps, float* 
     m[6] = az; m[7] = yz; m[8] = zz;
 }
 
-// fc2 + ortho6d (Net/IMU_Net.py:87-93) on split planes; one warp per frame
+// fc2 + ortho6d (Net/IMU_Net.py:87-93) on split planes; one warp per frame, persistent CTAs with fc2 (36 KB) staged
+// once in shared memory (reading it through L1/L2 for every frame made this kernel L2-bound at 9x its HBM bytes).
+// Lane l holds channels i*128 + 4l .. +3 (i = 0..7): 8-byte plane loads, conflict-free 16-byte weight reads.
 __global__ void __launch_bounds__(256) imu_decode_split_kernel(const __half* __restrict__ ghi, const __half* __restrict__ glo,
                                                                const float* __restrict__ fc2, float* __restrict__ R,
                                                                float* __restrict__ t, long long F) {
+    extern __shared__ __align__(16) float sw[];        // [9][1024] + [9]
+    for (int i = threadIdx.x * 4; i < 9 * 1024; i += 256 * 4)
+        *reinterpret_cast<float4*>(sw + i) = *reinterpret_cast<const float4*>(fc2 + i);
+    if (threadIdx.x < 9) sw[9 * 1024 + threadIdx.x] = fc2[9 * 1024 + threadIdx.x];
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    const long long f = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (f >= F) return;
-    float x[32];
+    for (long long f = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); f < F; f += (long long)gridDim.x * 8) {
+        float x[32];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) load8(ghi, glo, f * 1024 + i * 256 + lane * 8, x + i * 8);
-    float T9[9];
+        for (int i = 0; i < 8; ++i) {
+            const uint2 a = *reinterpret_cast<const uint2*>(ghi + f * 1024 + i * 128 + lane * 4);
+            float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
+            float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+            if (glo) {
+                const uint2 b = *reinterpret_cast<const uint2*>(glo + f * 1024 + i * 128 + lane * 4);
+                const float2 q0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x));
+                const float2 q1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
+                p0.x += q0.x; p0.y += q0.y; p1.x += q1.x; p1.y += q1.y;
+            }
+            x[i * 4] = p0.x * kActInv; x[i * 4 + 1] = p0.y * kActInv;
+            x[i * 4 + 2] = p1.x * kActInv; x[i * 4 + 3] = p1.y * kActInv;
+        }
+        float T9[9];
 #pragma unroll
-    for (int o = 0; o < 9; ++o) {
-        float a = 0.f;
+        for (int o = 0; o < 9; ++o) {
+            float a = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i) {
+                const float4 wv = *reinterpret_cast<const float4*>(sw + o * 1024 + i * 128 + lane * 4);
+                a = fmaf(wv.x, x[i * 4], a);
+                a = fmaf(wv.y, x[i * 4 + 1], a);
+                a = fmaf(wv.z, x[i * 4 + 2], a);
+                a = fmaf(wv.w, x[i * 4 + 3], a);
+            }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) a = fmaf(fc2[o * 1024 + i * 256 + lane * 8 + k], x[i * 8 + k], a);
+            for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+            T9[o] = a + sw[9 * 1024 + o];
+        }
+        if (lane == 0) {
+            float mm[9];
+            ortho6d_cols(T9, 1e-8f, mm);
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-        T9[o] = a + fc2[9 * 1024 + o];
-    }
-    if (lane == 0) {
-        float m[9];
-        ortho6d_cols(T9, 1e-8f, m);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) R[f * 9 + k] = m[k];
-        t[f * 3] = T9[6]; t[f * 3 + 1] = T9[7]; t[f * 3 + 2] = T9[8];
+            for (int k = 0; k < 9; ++k) R[f * 9 + k] = mm[k];
+            t[f * 3] = T9[6]; t[f * 3 + 1] = T9[7]; t[f * 3 + 2] = T9[8];
+        }
     }
 }
 
@@ -758,24 +845,41 @@ int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const
     return 0;
 }
 
-void tc_imu_fc1(const float* imu, const PackedGemm& fc1, void* uhi, void* ulo, long long rows, cudaStream_t st) {
+void tc_imu_fc1(const float* imu, const float* fc1_mma, void* uhi, void* ulo, long long rows, int sm_count,
+                cudaStream_t st) {
     if (rows <= 0) return;
+    const int smem = (FC1_WORDS + kImuH) * 4;
+    static bool attr_set[64] = {false};
+    if (first_use_on_device(attr_set))
+        cudaFuncSetAttribute(imu_fc1_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    long long blocks = (rows + 127) / 128;
+    if (blocks > 4LL * sm_count) blocks = 4LL * sm_count;
     ++g_launches;
-    imu_fc1_split_kernel<<<(unsigned)((rows + FC1_ROWS - 1) / FC1_ROWS), 256, 0, st>>>(
-        imu, fc1.w.p, fc1.bias.p, fc1.ldw, static_cast<__half*>(uhi), static_cast<__half*>(ulo), rows);
+    imu_fc1_mma_kernel<<<(unsigned)blocks, 256, smem, st>>>(imu, fc1_mma, static_cast<__half*>(uhi),
+                                                            static_cast<__half*>(ulo), rows);
 }
 void tc_imu_pool(const void* yhi, const void* ylo, const float* attn, void* shi, void* slo, long long F, int n,
                  cudaStream_t st) {
     if (F <= 0) return;
     ++g_launches;
-    imu_pool_split_kernel<<<(unsigned)F, 128, 0, st>>>(static_cast<const __half*>(yhi), static_cast<const __half*>(ylo),
-                                                       attn, static_cast<__half*>(shi), static_cast<__half*>(slo), F, n);
+    imu_pool_split_kernel<<<(unsigned)((F + POOL_WARPS - 1) / POOL_WARPS), POOL_WARPS * 32, 0, st>>>(
+        static_cast<const __half*>(yhi), static_cast<const __half*>(ylo), attn, static_cast<__half*>(shi),
+        static_cast<__half*>(slo), F, n);
 }
 void tc_imu_decode(const void* ghi, const void* glo, const float* fc2, float* R, float* t, long long F, cudaStream_t st) {
     if (F <= 0) return;
+    const int smem = (9 * 1024 + 16) * (int)sizeof(float);
+    static bool attr_set[64] = {false};
+    if (first_use_on_device(attr_set))
+        cudaFuncSetAttribute(imu_decode_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (F + 7) / 8;
+    if (blocks > 2LL * sms) blocks = 2LL * sms;
     ++g_launches;
-    imu_decode_split_kernel<<<(unsigned)((F + 7) / 8), 256, 0, st>>>(static_cast<const __half*>(ghi),
-                                                                     static_cast<const __half*>(glo), fc2, R, t, F);
+    imu_decode_split_kernel<<<(unsigned)blocks, 256, smem, st>>>(static_cast<const __half*>(ghi),
+                                                                 static_cast<const __half*>(glo), fc2, R, t, F);
 }
 void tc_unsplit(const void* hi, const void* lo, float* out, long long n, cudaStream_t st) {
     if (n <= 0) return;

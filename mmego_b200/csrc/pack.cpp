@@ -345,6 +345,21 @@ std::vector<float> pack_small_lstm_mma(const StateDict& sd, const std::string& p
     return v;
 }
 
+// IMU_Net fc1 (15 -> 512) for imu_fc1_mma_kernel: one k-step, 64 n-tiles.  Output channels are permuted inside every
+// group of four n-tiles so that a lane's eight accumulators of a row are eight CONSECUTIVE channels (one 16-byte store):
+//   column n of n-tile j  <->  channel 32 (j/4) + 8 (n/2) + 2 (j%4) + n%2
+//   blob = frags [64][32] uint4 | bias [512] in column order | out scale
+std::vector<float> pack_imu_fc1_mma(const HostPackedGemm& g) {
+    const int H = kImuH;
+    std::vector<float> v((size_t)mma_frag_words(1, 64) + H + 4, 0.f);
+    std::vector<int> nmap(H);
+    for (int j = 0; j < 64; ++j)
+        for (int n = 0; n < 8; ++n) nmap[8 * j + n] = 32 * (j >> 2) + 8 * (n >> 1) + 2 * (j & 3) + (n & 1);
+    v[mma_frag_words(1, 64) + H] = pack_mma_weight(g.w.data(), g.ldw, iota_map(kImuFeat, 16), nmap, v.data());
+    for (int c = 0; c < H; ++c) v[mma_frag_words(1, 64) + c] = g.bias[nmap[c]];
+    return v;
+}
+
 std::vector<float> pack_data_bn(const StateDict& sd, const std::string& gp) {
     BnAffine a = bn_affine(sd, gp + "data_bn", 45);
     std::vector<float> v(90);
