@@ -179,112 +179,132 @@ __global__ void __launch_bounds__(PROJ_NT) lstm_proj_mma_kernel(const float* __r
     }
 }
 
-constexpr int REC_NT = 128;
 __device__ __forceinline__ float2 ld2_or_zero(const float* p, bool live) {
     return live ? *reinterpret_cast<const float2*>(p) : make_float2(0.f, 0.f);
 }
 
-// gx [S][T][2][256] (mma column order), blob as packed by pack_small_lstm_mma (KS = In/16), h0/c0/hn/cn [2][S][64]
-__global__ void __launch_bounds__(REC_NT) lstm_rec_mma_kernel(const float* __restrict__ gx,
-                                                              const float* __restrict__ blob, int KS,
-                                                              const float* __restrict__ h0,
-                                                              const float* __restrict__ c0, float* __restrict__ y,
-                                                              float* __restrict__ hn, float* __restrict__ cn, int S,
-                                                              int T) {
-    MMEGO_DYN_SMEM(uint4, wf);                       // [4][32 n-tiles][32 lanes]
+// gx [S][T][2][256] (mma column order), blob as packed by pack_small_lstm_mma (KS = In/16), h0/c0/hn/cn [2][S][64].
+// TPC tiles of 16 sequences per CTA; four warps per tile, warp qw owning unit groups 2qw, 2qw+1 (16 hidden units = one
+// k-step of the next step's A operand).  h_t travels between the four warps of a tile as ready-made A-fragment words
+// through a double-buffered 4 KB shared-memory slot: one __syncthreads per timestep.
+template <int TPC>
+__global__ void __launch_bounds__(TPC * 128) lstm_rec_mma_kernel(const float* __restrict__ gx,
+                                                                 const float* __restrict__ blob, int KS,
+                                                                 const float* __restrict__ h0,
+                                                                 const float* __restrict__ c0, float* __restrict__ y,
+                                                                 float* __restrict__ hn, float* __restrict__ cn, int S,
+                                                                 int T) {
+    MMEGO_DYN_SMEM(uint4, wf);                       // [4][32 n-tiles][32 lanes] | hx [2][TPC][4 k-steps][hi, lo][32 lanes]
+    uint4* hx = wf + 4 * 32 * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+    const int tile = warp >> 2, qw = warp & 3;
     const int dir = blockIdx.y;
     const size_t ihw = (size_t)mma_frag_words(KS, 32), hhw = (size_t)mma_frag_words(4, 32);
     {
         const uint4* src = reinterpret_cast<const uint4*>(blob + 2 * ihw + 512 + dir * hhw);
-        for (int i = tid; i < 4 * 32 * 32; i += REC_NT) wf[i] = src[i];
+        for (int i = tid; i < 4 * 32 * 32; i += TPC * 128) wf[i] = src[i];
     }
     const float os = blob[2 * ihw + 512 + 2 * hhw + 2 + dir];
-    __syncthreads();
-    const long long q0 = (long long)blockIdx.x * 64 + warp * 16 + g, q1 = q0 + 8;   // this lane's two sequences
+    auto slot = [&](int buf, int s, int plane) { return hx + (((buf * TPC + tile) * 4 + s) * 2 + plane) * 32 + lane; };
+    const long long q0 = ((long long)blockIdx.x * TPC + tile) * 16 + g, q1 = q0 + 8;   // this lane's two sequences
     const bool live0 = q0 < S, live1 = q1 < S;
-    float c[8][4];
-    uint32_t ah[4][4], al[4][4];
+    float c[2][4], hl[2][4];
+    {
+        uint32_t nh[4], nl[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int col = 8 * u + 2 * tq;
-        const float2 ca = ld2_or_zero(c0 ? c0 + ((long long)dir * S + q0) * H + col : nullptr, live0 && c0);
-        const float2 cb = ld2_or_zero(c0 ? c0 + ((long long)dir * S + q1) * H + col : nullptr, live1 && c0);
-        c[u][0] = ca.x; c[u][1] = ca.y; c[u][2] = cb.x; c[u][3] = cb.y;
-        const float2 ha = ld2_or_zero(h0 ? h0 + ((long long)dir * S + q0) * H + col : nullptr, live0 && h0);
-        const float2 hb = ld2_or_zero(h0 ? h0 + ((long long)dir * S + q1) * H + col : nullptr, live1 && h0);
-        frag::split2(ha.x, ha.y, ah[u >> 1][2 * (u & 1)], al[u >> 1][2 * (u & 1)]);
-        frag::split2(hb.x, hb.y, ah[u >> 1][2 * (u & 1) + 1], al[u >> 1][2 * (u & 1) + 1]);
+        for (int uu = 0; uu < 2; ++uu) {
+            const int col = 8 * (2 * qw + uu) + 2 * tq;
+            const float2 ca = ld2_or_zero(c0 ? c0 + ((long long)dir * S + q0) * H + col : nullptr, live0 && c0);
+            const float2 cb = ld2_or_zero(c0 ? c0 + ((long long)dir * S + q1) * H + col : nullptr, live1 && c0);
+            c[uu][0] = ca.x; c[uu][1] = ca.y; c[uu][2] = cb.x; c[uu][3] = cb.y;
+            const float2 ha = ld2_or_zero(h0 ? h0 + ((long long)dir * S + q0) * H + col : nullptr, live0 && h0);
+            const float2 hb = ld2_or_zero(h0 ? h0 + ((long long)dir * S + q1) * H + col : nullptr, live1 && h0);
+            hl[uu][0] = ha.x; hl[uu][1] = ha.y; hl[uu][2] = hb.x; hl[uu][3] = hb.y;
+            frag::split2(ha.x, ha.y, nh[2 * uu], nl[2 * uu]);
+            frag::split2(hb.x, hb.y, nh[2 * uu + 1], nl[2 * uu + 1]);
+        }
+        *slot(0, qw, 0) = make_uint4(nh[0], nh[1], nh[2], nh[3]);
+        *slot(0, qw, 1) = make_uint4(nl[0], nl[1], nl[2], nl[3]);
     }
-    float hl[8][4];                                   // last h (for hn)
-#pragma unroll
-    for (int u = 0; u < 8; ++u) hl[u][0] = hl[u][1] = hl[u][2] = hl[u][3] = 0.f;
-
-    for (int step = 0; step < T; ++step) {
+    // gx of the first step (rows g / g+8; [unit group][gate])
+    float2 pa[2][4], pb[2][4];
+    auto load_gx = [&](int step, float2 (&a)[2][4], float2 (&b)[2][4]) {
         const int tt = dir ? (T - 1 - step) : step;
         const float* g0 = gx + ((q0 * T + tt) * 2 + dir) * 256 + 2 * tq;
         const float* g1 = gx + ((q1 * T + tt) * 2 + dir) * 256 + 2 * tq;
-        float* y0 = y + (q0 * T + tt) * (2 * H) + dir * H + 2 * tq;
-        float* y1 = y + (q1 * T + tt) * (2 * H) + dir * H + 2 * tq;
-        uint32_t nh[4][4], nl[4][4];
-        float2 pa[4], pb[4];                          // gx of the unit group in flight (rows g / g+8, 4 gates)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { pa[k] = ld2_or_zero(g0 + 8 * k, live0); pb[k] = ld2_or_zero(g1 + 8 * k, live1); }
+        for (int uu = 0; uu < 2; ++uu)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            float2 na[4], nb[4];
-            if (u < 7) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    na[k] = ld2_or_zero(g0 + 8 * (4 * (u + 1) + k), live0);
-                    nb[k] = ld2_or_zero(g1 + 8 * (4 * (u + 1) + k), live1);
-                }
+            for (int k = 0; k < 4; ++k) {
+                a[uu][k] = ld2_or_zero(g0 + 8 * (4 * (2 * qw + uu) + k), live0);
+                b[uu][k] = ld2_or_zero(g1 + 8 * (4 * (2 * qw + uu) + k), live1);
             }
+    };
+    if (T > 0) load_gx(0, pa, pb);
+    __syncthreads();
+
+    for (int step = 0; step < T; ++step) {
+        const int buf = step & 1;
+        const int tt = dir ? (T - 1 - step) : step;
+        float2 na[2][4], nb[2][4];
+        if (step + 1 < T) load_gx(step + 1, na, nb);
+        uint32_t ah[4][4], al[4][4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const uint4 vh = *slot(buf, s, 0), vl = *slot(buf, s, 1);
+            ah[s][0] = vh.x; ah[s][1] = vh.y; ah[s][2] = vh.z; ah[s][3] = vh.w;
+            al[s][0] = vl.x; al[s][1] = vl.y; al[s][2] = vl.z; al[s][3] = vl.w;
+        }
+        uint32_t nh[4], nl[4];
+#pragma unroll
+        for (int uu = 0; uu < 2; ++uu) {
+            const int u = 2 * qw + uu;
             float pre[4][4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float big[4] = {0.f, 0.f, 0.f, 0.f}, small[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int s = 0; s < 4; ++s) frag::mma3(big, small, ah[s], al[s], wf[(s * 32 + 4 * u + k) * 32 + lane]);
-                pre[k][0] = fmaf(big[0] + small[0], os, pa[k].x);
-                pre[k][1] = fmaf(big[1] + small[1], os, pa[k].y);
-                pre[k][2] = fmaf(big[2] + small[2], os, pb[k].x);
-                pre[k][3] = fmaf(big[3] + small[3], os, pb[k].y);
+                pre[k][0] = fmaf(big[0] + small[0], os, pa[uu][k].x);
+                pre[k][1] = fmaf(big[1] + small[1], os, pa[uu][k].y);
+                pre[k][2] = fmaf(big[2] + small[2], os, pb[uu][k].x);
+                pre[k][3] = fmaf(big[3] + small[3], os, pb[uu][k].y);
             }
             float hv[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float ig = sigmoid_nb(pre[0][i]), fg = sigmoid_nb(pre[1][i]), gg = tanhf(pre[2][i]),
                             og = sigmoid_nb(pre[3][i]);
-                const float cnew = fg * c[u][i] + ig * gg;
-                c[u][i] = cnew;
+                const float cnew = fg * c[uu][i] + ig * gg;
+                c[uu][i] = cnew;
                 hv[i] = og * tanhf(cnew);
-                hl[u][i] = hv[i];
+                hl[uu][i] = hv[i];
             }
-            if (live0) *reinterpret_cast<float2*>(y0 + 8 * u) = make_float2(hv[0], hv[1]);
-            if (live1) *reinterpret_cast<float2*>(y1 + 8 * u) = make_float2(hv[2], hv[3]);
-            frag::split2(hv[0], hv[1], nh[u >> 1][2 * (u & 1)], nl[u >> 1][2 * (u & 1)]);
-            frag::split2(hv[2], hv[3], nh[u >> 1][2 * (u & 1) + 1], nl[u >> 1][2 * (u & 1) + 1]);
-            if (u < 7) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { pa[k] = na[k]; pb[k] = nb[k]; }
-            }
+            float* y0 = y + (q0 * T + tt) * (2 * H) + dir * H + 8 * u + 2 * tq;
+            float* y1 = y + (q1 * T + tt) * (2 * H) + dir * H + 8 * u + 2 * tq;
+            if (live0) *reinterpret_cast<float2*>(y0) = make_float2(hv[0], hv[1]);
+            if (live1) *reinterpret_cast<float2*>(y1) = make_float2(hv[2], hv[3]);
+            frag::split2(hv[0], hv[1], nh[2 * uu], nl[2 * uu]);
+            frag::split2(hv[2], hv[3], nh[2 * uu + 1], nl[2 * uu + 1]);
         }
+        *slot(buf ^ 1, qw, 0) = make_uint4(nh[0], nh[1], nh[2], nh[3]);
+        *slot(buf ^ 1, qw, 1) = make_uint4(nl[0], nl[1], nl[2], nl[3]);
 #pragma unroll
-        for (int s = 0; s < 4; ++s)
+        for (int uu = 0; uu < 2; ++uu)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { ah[s][i] = nh[s][i]; al[s][i] = nl[s][i]; }
+            for (int k = 0; k < 4; ++k) { pa[uu][k] = na[uu][k]; pb[uu][k] = nb[uu][k]; }
+        __syncthreads();
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int col = 8 * u + 2 * tq;
-        if (hn && T > 0) {
-            if (live0) *reinterpret_cast<float2*>(hn + ((long long)dir * S + q0) * H + col) = make_float2(hl[u][0], hl[u][1]);
-            if (live1) *reinterpret_cast<float2*>(hn + ((long long)dir * S + q1) * H + col) = make_float2(hl[u][2], hl[u][3]);
+    for (int uu = 0; uu < 2; ++uu) {
+        const int col = 8 * (2 * qw + uu) + 2 * tq;
+        if (hn) {
+            if (live0) *reinterpret_cast<float2*>(hn + ((long long)dir * S + q0) * H + col) = make_float2(hl[uu][0], hl[uu][1]);
+            if (live1) *reinterpret_cast<float2*>(hn + ((long long)dir * S + q1) * H + col) = make_float2(hl[uu][2], hl[uu][3]);
         }
         if (cn) {
-            if (live0) *reinterpret_cast<float2*>(cn + ((long long)dir * S + q0) * H + col) = make_float2(c[u][0], c[u][1]);
-            if (live1) *reinterpret_cast<float2*>(cn + ((long long)dir * S + q1) * H + col) = make_float2(c[u][2], c[u][3]);
+            if (live0) *reinterpret_cast<float2*>(cn + ((long long)dir * S + q0) * H + col) = make_float2(c[uu][0], c[uu][1]);
+            if (live1) *reinterpret_cast<float2*>(cn + ((long long)dir * S + q1) * H + col) = make_float2(c[uu][2], c[uu][3]);
         }
     }
 }
@@ -311,7 +331,9 @@ void launch_lstm_small_mma(const float* x, long long ldx, int In, const float* b
         cudaFuncSetAttribute(lstm_proj_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16 * 32 * 16);
         cudaFuncSetAttribute(lstm_proj_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 16 * 32 * 16);
         cudaFuncSetAttribute(lstm_proj_mma_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 16 * 32 * 16);
-        cudaFuncSetAttribute(lstm_rec_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+        cudaFuncSetAttribute(lstm_rec_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem + 2 * 1 * 8192);
+        cudaFuncSetAttribute(lstm_rec_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem + 2 * 2 * 8192);
+        cudaFuncSetAttribute(lstm_rec_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem + 2 * 4 * 8192);
     }
     const long long tiles = (M + 63) / 64;
     const long long per_slab = (long long)sm_count * 2 / 4 > 0 ? (long long)sm_count * 2 / 4 : 1;
@@ -323,8 +345,18 @@ void launch_lstm_small_mma(const float* x, long long ldx, int In, const float* b
     } else {
         MMEGO_LAUNCH(lstm_proj_mma_kernel<12>, pgrid, dim3(PROJ_NT), psmem, st, x, ldx, blob, gx, M);
     }
-    dim3 rgrid((unsigned)((S + 63) / 64), 2);
-    MMEGO_LAUNCH(lstm_rec_mma_kernel, rgrid, dim3(REC_NT), rsmem, st, gx, blob, KS, h0, c0, y, hn, cn, S, T);
+    // tiles (16 sequences) per CTA: as many as still leave about one CTA per SM
+    const long long tiles16 = ((long long)S + 15) / 16;
+    const int tpc = tiles16 * 2 >= 4LL * sm_count ? 4 : (tiles16 * 2 >= 2LL * sm_count ? 2 : 1);
+    const size_t rsm = rsmem + (size_t)2 * tpc * 4 * 2 * 32 * sizeof(uint4);
+    dim3 rgrid((unsigned)((tiles16 + tpc - 1) / tpc), 2);
+    if (tpc == 4) {
+        MMEGO_LAUNCH(lstm_rec_mma_kernel<4>, rgrid, dim3(512), rsm, st, gx, blob, KS, h0, c0, y, hn, cn, S, T);
+    } else if (tpc == 2) {
+        MMEGO_LAUNCH(lstm_rec_mma_kernel<2>, rgrid, dim3(256), rsm, st, gx, blob, KS, h0, c0, y, hn, cn, S, T);
+    } else {
+        MMEGO_LAUNCH(lstm_rec_mma_kernel<1>, rgrid, dim3(128), rsm, st, gx, blob, KS, h0, c0, y, hn, cn, S, T);
+    }
 }
 
 }  // namespace mmego

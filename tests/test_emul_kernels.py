@@ -57,6 +57,11 @@ def test_pipeline_ragged_shapes(handle):
     P.check_pipeline_vs_oracle(handle, B=3, L=5, N=70, n_imu=3, seed=21)
 
 
+def test_pipeline_many_snippets(handle):
+    # enough sequences that the H=64 recurrence runs with 4 tiles per CTA (the emulated device has 4 SMs), ragged tail
+    P.check_pipeline_vs_oracle(handle, B=136, L=2, N=64, n_imu=1, seed=5)
+
+
 def test_errors(handle):
     P.check_errors(handle)
 
