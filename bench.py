@@ -312,6 +312,37 @@ def main():
 
         roofline = lstm_roofline(prof, ms, args.steps, mode)
         stage_ms = {k: round(v["ms"] / args.steps, 3) for k, v in prof.items()}
+
+        def stage_rooflines(prof_, steps_, mode_):
+            """Memory-bound stages: algorithmic HBM bytes per step / CUDA-event span of the stage, against the measured
+            copy bandwidth; the mma.sync stages (point encoders, H=64 LSTMs) as algorithmic TFLOP/s for reference."""
+            planes = 2 if mode_ == 1 else (1 if mode_ == 2 else 0)
+            F_ = B * L
+            rows = F_ * N_IMU
+            act = 2 * planes if planes else 4                       # bytes per activation element (fp16 planes / fp32)
+            hbm_bytes = {
+                "imu.fc1": rows * (15 * 4 + 512 * act),
+                "imu.pool": F_ * (N_IMU * 1024 * act + 1024 * act),
+                "imu.decode": F_ * (1024 * act + 48),
+                "upper.point": F_ * (N_PTS * 6 * 4 + N_PTS * 3 * 4 + 64 * 4 + 48),
+                "assemble_metrics": F_ * ((45 + 24 + 63) * 4 + 63 * 4),
+            }
+            flops = {"upper.point": F_ * 1.57e6, "lower.frame": F_ * 1.40e6, "small_lstm": F_ * (0.524e6 + 0.655e6),
+                     "lower.gcn": F_ * 7.18e6}
+            out = {}
+            for name, v in prof_.items():
+                ms_s = v["ms"] / steps_
+                if ms_s <= 0:
+                    continue
+                e = {"ms": round(ms_s, 3)}
+                if name in hbm_bytes:
+                    gbs = hbm_bytes[name] / (ms_s * 1e-3) / 1e9
+                    e.update({"hbm_bytes": hbm_bytes[name], "gbs": round(gbs, 1), "hbm_frac": round(gbs / peaks["hbm_gbs"], 3)})
+                if name in flops:
+                    e["algorithmic_tflops"] = round(flops[name] / (ms_s * 1e-3) / 1e12, 2)
+                if len(e) > 1:
+                    out[name] = e
+            return out
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -326,6 +357,7 @@ def main():
             "stage_ms_per_step": stage_ms,
             "mpjpe_vs_synthetic_target_cm": rep["mpjpe_cm"],
             "roofline": roofline,
+            "stages": stage_rooflines(prof, args.steps, mode),
         }
         if half:
             ms2, _, prof2, _, _ = half
