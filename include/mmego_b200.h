@@ -128,6 +128,27 @@ int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_h
                      const float* target_host, float* pred_host, double* sums_host, int B, int L, int N, int n_imu,
                      int body_index_mode, int b_offset, int B_global);
 
+/* Snippet builder -- replaces the per-frame arithmetic of the reference's loader (Util/Universal_Util/Dataset_sample.py:
+ * 153-231: range channel and channel reorder :203-208, padding / sub-sampling to N slots :210-223, IMU re-framing
+ * :184-195, R_R0R :182) and its snippet windows (:233-260, as the `starts` list) on raw per-frame sensor data kept
+ * resident on the device (the packed cache of scripts/pack_sample_data.py).  All pointers are DEVICE pointers. */
+typedef struct {
+    const float* points;           /* [P][5] x, y, z, intensity, velocity of every radar point, frame after frame */
+    const long long* pt_start;     /* [F+1] first point of every frame */
+    const double* key;             /* [F][21][3] selected Kinect joints */
+    const double* imu;             /* [F][20][15] raw imu_save_l */
+    const double* R_btc;           /* [F][3][3] */
+    const double* t_R0R;           /* [F][3] */
+    const double* R_ref;           /* [3][3] R_btc of the reference frame (the loader's st == 0 frame) */
+    const double* orientation_ref; /* [3][3] orientation_imu_img of the reference frame */
+} mmego_raw_frames_t;
+/* starts [B]: first source frame of every snippet.  slot_src [B*L*N] (or NULL): source point of every output slot, -1 =
+ * empty; NULL = seeded random placement (the reference uses an unseeded RNG).  Outputs: data [B,L,N,6],
+ * imu [B,L,20,15], key [B,L,21,3], R [B,L,3,3], t [B,L,3], all fp32 as Demo_test.py:95-109 casts them. */
+int mmego_build_snippets(mmego_handle* h, const mmego_raw_frames_t* raw, const long long* starts, const int* slot_src,
+                         unsigned seed, float* data, float* imu, float* key, float* R, float* t, int B, int L, int N,
+                         void* stream);
+
 /* Test hook: the next forward copies the named intermediate tensor into dst (device, `bytes` capacity). */
 int mmego_debug_tap(mmego_handle* h, const char* name, void* dst, size_t bytes);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */

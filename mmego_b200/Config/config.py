@@ -18,6 +18,7 @@ class Config:
     joint_num_lower = 8
     num_action = 13
     IMU_used = True
+    dataset_random_seed = 1
 
     device = "cuda:0" if torch.cuda.is_available() else "cpu"
 
@@ -39,4 +40,6 @@ class Config:
     # frozen batch tensors of Resource/Sample_data (built by the reference loader with np.random.seed(0);
     # oracle/make_golden.py --full-sample)
     sample_frozen_path = os.path.join(_root, "Resource/Sample_data_frozen/sample835_seed0.npz")
+    # raw per-frame cache for the GPU snippet builder (scripts/pack_sample_data.py; not shipped -- 150 MB of .mat input)
+    sample_packed_path = os.path.join(_root, "Resource/Sample_data_packed/raw.npz")
     sample_data_path = os.path.join(_root, "Resource/Sample_data")

@@ -40,6 +40,7 @@ SIGNATURES = {
     "mmego_assemble_metrics": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "mmego_pipeline_forward": (_i, [_vp] + [_vp] * 10 + [_i] * 7 + [_vp, _sz, _vp]),
     "mmego_infer_host": (_i, [_vp] + [_vp] * 6 + [_i] * 7),
+    "mmego_build_snippets": (_i, [_vp, _vp, _vp, _vp, C.c_uint, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mmego_debug_tap": (_i, [_vp, C.c_char_p, _vp, _sz]),
     "mmego_launch_count": (_ll, [_vp]),
     "mmego_profile_begin": (_i, [_vp]),
@@ -54,6 +55,13 @@ PROFILE_SPANS = ("imu.fc1", "imu.lstm_fast", "imu.lstm_slow", "imu.pool", "imu.d
 
 class MMEgoError(RuntimeError):
     pass
+
+
+class RawFramesStruct(C.Structure):
+    """mmego_raw_frames_t of include/mmego_b200.h (device pointers)."""
+    _fields_ = [(n, _vp) for n in ("points", "pt_start", "key", "imu", "R_btc", "t_R0R", "R_ref", "orientation_ref")]
+    DTYPES = dict(points=torch.float32, pt_start=torch.int64, key=torch.float64, imu=torch.float64, R_btc=torch.float64,
+                  t_R0R=torch.float64, R_ref=torch.float64, orientation_ref=torch.float64)
 
 
 class Lib:
@@ -261,6 +269,32 @@ class Handle:
                                                   t.data_ptr(), l.data_ptr(), _ptr(q), B, L, N, body_index_mode, b_offset,
                                                   Bg, ws.data_ptr(), ws.numel(), self._stream()), "lower_forward")
         return l, q
+
+    def build_snippets(self, raw: Mapping[str, torch.Tensor], starts: torch.Tensor, slot_src: Optional[torch.Tensor] = None,
+                       seed: int = 0, L: int = 20, N: int = 128):
+        """raw: the arrays of mmego_raw_frames_t as tensors on this handle's device; starts [B] int64 (first source
+        frame of every snippet); slot_src [B,L,N] int32 or None.  Returns dict(data, imu, key, R, t)."""
+        st = RawFramesStruct()
+        for name, dt in RawFramesStruct.DTYPES.items():
+            st_t = self._t(raw[name], name, dt)
+            setattr(st, name, st_t.data_ptr())
+        starts = self._t(starts, "starts", torch.int64)
+        B = starts.numel()
+        if slot_src is not None:
+            slot_src = self._t(slot_src, "slot_src", torch.int32)
+            if slot_src.numel() != B * L * N:
+                raise MMEgoError(f"slot_src must be [{B},{L},{N}] (got {tuple(slot_src.shape)})")
+        dev = starts.device
+        out = dict(data=torch.empty(B, L, N, 6, dtype=torch.float32, device=dev),
+                   imu=torch.empty(B, L, 20, 15, dtype=torch.float32, device=dev),
+                   key=torch.empty(B, L, 21, 3, dtype=torch.float32, device=dev),
+                   R=torch.empty(B, L, 3, 3, dtype=torch.float32, device=dev),
+                   t=torch.empty(B, L, 3, dtype=torch.float32, device=dev))
+        self._ck(self.lib.dll.mmego_build_snippets(self._h, C.addressof(st), starts.data_ptr(), _ptr(slot_src), seed,
+                                                   out["data"].data_ptr(), out["imu"].data_ptr(), out["key"].data_ptr(),
+                                                   out["R"].data_ptr(), out["t"].data_ptr(), B, L, N, self._stream()),
+                 "build_snippets")
+        return out
 
     def gcn_extract_feature(self, x: torch.Tensor):
         x = self._t(x, "x")

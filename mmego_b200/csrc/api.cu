@@ -1032,6 +1032,22 @@ int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_h
     return MMEGO_OK;
 }
 
+int mmego_build_snippets(mmego_handle* h, const mmego_raw_frames_t* raw, const long long* starts, const int* slot_src,
+                         unsigned seed, float* data, float* imu, float* key, float* R, float* t, int B, int L, int N,
+                         void* stream) {
+    if (int rc = check_dims(h, B, L, N)) return rc;
+    if (!raw || !starts || !data || !imu || !key || !R || !t) return fail(h, MMEGO_EINVAL, "build_snippets: NULL argument");
+    if (!raw->points || !raw->pt_start || !raw->key || !raw->imu || !raw->R_btc || !raw->t_R0R || !raw->R_ref ||
+        !raw->orientation_ref)
+        return fail(h, MMEGO_EINVAL, "build_snippets: NULL array in mmego_raw_frames_t");
+    RawFrames rf{raw->points, raw->pt_start, raw->key, raw->imu, raw->R_btc, raw->t_R0R, raw->R_ref, raw->orientation_ref};
+    Prof p(h, "build_snippets", static_cast<cudaStream_t>(stream));
+    launch_snippet_build(rf, starts, slot_src, seed, data, imu, key, R, t, B, L, N, static_cast<cudaStream_t>(stream));
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches = g_launches;
+    return MMEGO_OK;
+}
+
 int mmego_debug_tap(mmego_handle* h, const char* name, void* dst, size_t bytes) {
     if (!h || !name) return MMEGO_EINVAL;
     if (!dst) { h->taps.erase(name); return MMEGO_OK; }

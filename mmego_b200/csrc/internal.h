@@ -104,6 +104,20 @@ void launch_transform2h(float* pts, const float* R, const float* t, long long F,
 void launch_transform2r(const float* pts, const float* R, const float* t, float* out, long long F, int n,
                         cudaStream_t st);
 
+// snippet builder (snippet.cu): device views of the packed raw cache (scripts/pack_sample_data.py)
+struct RawFrames {
+    const float* points;            // [P][5]  x, y, z, intensity, velocity
+    const long long* pt_start;      // [F+1]
+    const double* key;              // [F][21][3]
+    const double* imu;              // [F][20][15]
+    const double* R_btc;            // [F][3][3]
+    const double* t_R0R;            // [F][3]
+    const double* R_ref;            // [3][3]
+    const double* orientation_ref;  // [3][3]
+};
+void launch_snippet_build(const RawFrames& raw, const long long* starts, const int* slot_src, unsigned seed, float* data,
+                          float* imu, float* key, float* R, float* t, long long B, int L, int N, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------------
 // packed weights
 // ------------------------------------------------------------------------------------------------

@@ -494,3 +494,115 @@ def default_skeleton() -> np.ndarray:
     import os
     p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "skeleton.npy")
     return np.load(p)
+
+
+# ------------------------------------------------------------------------------------------------ snippet builder
+# CPU restatement of what the reference's loader COMPUTES per frame (Util/Universal_Util/Dataset_sample.py:153-231) and
+# of its snippet windows (:233-260), on the packed raw cache written by scripts/pack_sample_data.py.  TEST
+# INFRASTRUCTURE like the rest of this file.  Pinned by tests/test_oracle_golden.py against tensors produced by the
+# reference's own PosePC class (tests/golden/raw_subset.npz).
+R_RI = np.array([[0, 0, 1], [0, -1, 0], [1, 0, 0]], dtype=np.float64)        # Dataset_sample.py:18
+R_TTB = np.array([[0, -1, 0], [-1, 0, 0], [0, 0, -1]], dtype=np.float64)     # Dataset_sample.py:19
+
+
+def snippet_windows(rec_start: np.ndarray, frame_no: int = FRAME_NO) -> np.ndarray:
+    """First-frame index of every snippet, in the loader's order: recording by recording, windows cut from the END of
+    the recording backwards (Dataset_sample.py:233-260)."""
+    starts = []
+    for r in range(len(rec_start) - 1):
+        s, e = int(rec_start[r]), int(rec_start[r + 1])
+        while e - s >= frame_no:
+            starts.append(e - frame_no)
+            e -= frame_no
+    return np.asarray(starts, dtype=np.int64)
+
+
+def slot_hash(seed: int, frame: int, i: int) -> int:
+    """Counter-based 32-bit hash used for the random slot placement (the reference uses the unseeded global numpy RNG,
+    Dataset_sample.py:215-223, which cannot be reproduced; any uniformly random injective placement is equivalent)."""
+    x = (seed * 0x9E3779B1 + frame * 0x85EBCA77 + i * 0xC2B2AE3D + 0x27D4EB2F) & 0xFFFFFFFF
+    x ^= x >> 15
+    x = (x * 0x2C1B3C6D) & 0xFFFFFFFF
+    x ^= x >> 12
+    x = (x * 0x297A2D39) & 0xFFFFFFFF
+    x ^= x >> 15
+    return x
+
+
+def slot_assignment(n: int, pc_no: int, seed: int, frame: int) -> np.ndarray:
+    """slot -> source point (or -1).  n < pc_no: every point lands in a distinct random slot; n >= pc_no: pc_no
+    distinct random points.  Keys are ranked ascending, ties by index."""
+    src = np.full(pc_no, -1, dtype=np.int32)
+    if n < pc_no:
+        keys = [(slot_hash(seed, frame, s), s) for s in range(pc_no)]
+        order = [s for _, s in sorted(keys)]
+        for i in range(n):
+            src[order[i]] = i
+    else:
+        keys = [(slot_hash(seed, frame, p), p) for p in range(n)]
+        order = [p for _, p in sorted(keys)]
+        src[:] = order[:pc_no]
+    return src
+
+
+def build_frame(raw: Mapping[str, np.ndarray], f: int, slot_src: np.ndarray, pc_no: int = PC_NO):
+    """One frame of the loader: radar cloud [pc_no,6] (x,y,z,range,velocity,intensity), re-framed IMU block [20,15],
+    R_R0R [3,3] -- all float32 as Demo_test.py:95-109 casts them."""
+    p = raw["points"][int(raw["pt_start"][f]):int(raw["pt_start"][f + 1])].astype(np.float64)
+    xyzrvi = np.zeros((len(p), 6), dtype=np.float32)
+    xyzrvi[:, 0:3] = p[:, :3]
+    xyzrvi[:, 3] = np.sqrt((p[:, 0] * p[:, 0] + p[:, 1] * p[:, 1]) + p[:, 2] * p[:, 2])      # :204
+    xyzrvi[:, 4] = p[:, 4]                                                                   # :208 ([4:2:-1] = v, i)
+    xyzrvi[:, 5] = p[:, 3]
+    cloud = np.zeros((pc_no, 6), dtype=np.float32)
+    live = slot_src >= 0
+    cloud[live] = xyzrvi[slot_src[live]]
+    imu = raw["imu"][f].copy()
+    R_NI = np.stack([imu[:, :3], imu[:, 3:6], imu[:, 6:9]], axis=2)                           # :186
+    m = R_RI @ (raw["orientation_ref"].T @ R_NI) @ R_RI.T                                    # :187-188
+    imu[:, :3], imu[:, 3:6], imu[:, 6:9] = m[:, 0, :], m[:, 1, :], m[:, 2, :]
+    imu[:, 11] = imu[:, 11] + 9.8                                                            # :192
+    imu[:, 10:12] = -1 * imu[:, 10:12]
+    imu[:, 13:] = -1 * imu[:, 13:]
+    R = R_TTB @ raw["R_ref"] @ raw["R_btc"][f].T @ R_TTB.T                                   # :182
+    return cloud, imu.astype(np.float32), R.astype(np.float32)
+
+
+def build_snippets(raw: Mapping[str, np.ndarray], starts: np.ndarray, slot_src: Optional[np.ndarray] = None,
+                   seed: int = 0, frame_no: int = FRAME_NO, pc_no: int = PC_NO) -> Dict[str, np.ndarray]:
+    B = len(starts)
+    out = dict(data=np.zeros((B, frame_no, pc_no, 6), np.float32), imu=np.zeros((B, frame_no, 20, 15), np.float32),
+               key=np.zeros((B, frame_no, 21, 3), np.float32), R=np.zeros((B, frame_no, 3, 3), np.float32),
+               t=np.zeros((B, frame_no, 3), np.float32), skl=np.repeat(raw["skl"][None].astype(np.float32), B, 0))
+    for b in range(B):
+        for l in range(frame_no):
+            f = int(starts[b]) + l
+            n = int(raw["pt_start"][f + 1] - raw["pt_start"][f])
+            src = slot_src[b, l] if slot_src is not None else slot_assignment(n, pc_no, seed, f)
+            out["data"][b, l], out["imu"][b, l], out["R"][b, l] = build_frame(raw, f, src, pc_no)
+            out["key"][b, l] = raw["key"][f]
+            out["t"][b, l] = raw["t_R0R"][f]
+    return out
+
+
+def recover_slots(raw: Mapping[str, np.ndarray], starts: np.ndarray, data: np.ndarray) -> np.ndarray:
+    """slot -> source point of reference-built clouds (matches xyz + intensity + velocity exactly): lets a test feed the
+    reference's own random placement to the builder."""
+    B, Lf, pc_no, _ = data.shape
+    out = np.full((B, Lf, pc_no), -1, dtype=np.int32)
+    for b in range(B):
+        for l in range(Lf):
+            f = int(starts[b]) + l
+            p = raw["points"][int(raw["pt_start"][f]):int(raw["pt_start"][f + 1])]
+            used = np.zeros(len(p), bool)
+            for s in range(pc_no):
+                row = data[b, l, s]
+                if not row.any():
+                    continue
+                hit = np.nonzero((p[:, 0] == row[0]) & (p[:, 1] == row[1]) & (p[:, 2] == row[2]) & (p[:, 4] == row[4]) &
+                                 (p[:, 3] == row[5]) & ~used)[0]
+                if len(hit) == 0:
+                    raise ValueError(f"snippet {b} frame {l} slot {s}: no raw point matches")
+                out[b, l, s] = hit[0]
+                used[hit[0]] = True
+    return out

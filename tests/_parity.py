@@ -207,3 +207,42 @@ def check_errors(h):
     with pytest.raises(_capi.MMEgoError, match="missing state_dict tensor"):
         h2.set_weights(_capi.NET_UPPER, {"module0.conv1.weight": torch.zeros(8, 6, 1)})
     h2.close()
+
+
+def check_snippet_builder(h):
+    """mmego_build_snippets against tensors built by the REFERENCE's own PosePC class (tests/golden/raw_subset.npz, made
+    by scripts/pack_sample_data.py --fixture) with the reference's random placement fed back in, and against the oracle
+    for the library's own seeded placement."""
+    z = dict(np.load(os.path.join(GOLDEN, "raw_subset.npz")))
+    starts = O.snippet_windows(z["rec_start"])
+    raw = {k: torch.from_numpy(np.ascontiguousarray(z[k])).to(h.device) for k in _capi.RawFramesStruct.DTYPES}
+    st = torch.from_numpy(starts).to(h.device)
+    slots = O.recover_slots(z, starts, z["exp_data"])
+    out = h.build_snippets(raw, st, torch.from_numpy(slots).to(h.device))
+    assert torch.equal(out["data"].cpu(), torch.from_numpy(z["exp_data"]))          # incl. the float64 range channel
+    assert torch.equal(out["key"].cpu(), torch.from_numpy(z["exp_key"]))
+    assert torch.equal(out["t"].cpu(), torch.from_numpy(z["exp_t"]))
+    # 3x3 products in float64 (no FMA contraction) rounded to float32: at most one float32 ulp from numpy's matmul
+    for name, exp in (("imu", "exp_imu"), ("R", "exp_R")):
+        a, b = out[name].cpu(), torch.from_numpy(z[exp])
+        assert float((a - b).abs().max()) <= 1.2e-7 * max(1.0, float(b.abs().max())), name
+        assert float((a != b).float().mean()) < 1e-3, name
+    # seeded placement: identical to the oracle's, every point placed exactly once (n < N) / N distinct points (n >= N)
+    sub = starts[:3]
+    mine = h.build_snippets(raw, torch.from_numpy(sub).to(h.device), None, seed=7)["data"].cpu().numpy()
+    want = O.build_snippets(z, sub, None, seed=7)["data"]
+    assert np.array_equal(mine, want)
+    other = h.build_snippets(raw, torch.from_numpy(sub).to(h.device), None, seed=8)["data"].cpu().numpy()
+    assert not np.array_equal(mine, other)
+    for b in range(len(sub)):
+        for l in range(20):
+            f = int(sub[b]) + l
+            n = int(z["pt_start"][f + 1] - z["pt_start"][f])
+            live = mine[b, l][mine[b, l].any(axis=1)]
+            assert len(live) == min(n, 128)
+            src = z["points"][int(z["pt_start"][f]):int(z["pt_start"][f + 1])]
+            key_live = sorted(map(tuple, live[:, [0, 1, 2, 5, 4]].tolist()))
+            key_src = sorted(map(tuple, src.tolist()))
+            assert all(k in key_src for k in key_live)
+            if n <= 128:
+                assert key_live == key_src

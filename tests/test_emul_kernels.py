@@ -62,6 +62,35 @@ def test_pipeline_many_snippets(handle):
     P.check_pipeline_vs_oracle(handle, B=136, L=2, N=64, n_imu=1, seed=5)
 
 
+def test_snippet_builder(handle):
+    P.check_snippet_builder(handle)
+
+
+def test_posepc_windows_split(handle, tmp_path):
+    """Host logic of the PosePC mirror: windows from the end of each recording, seeded shuffle, 80/20 split."""
+    import numpy as np
+    from mmego_b200.Util.Universal_Util.Dataset_sample import PosePC, snippet_windows
+    from oracle import mmego_oracle as O
+    z = dict(np.load(os.path.join(P.GOLDEN, "raw_subset.npz")))
+    assert np.array_equal(snippet_windows(z["rec_start"], 20), O.snippet_windows(z["rec_start"]))
+    path = os.path.join(tmp_path, "raw.npz")
+    np.savez(path, **{k: z[k] for k in ("points", "pt_start", "key", "imu", "R_btc", "t_R0R", "R_ref", "orientation_ref",
+                                        "rec_start", "skl")})
+    vis = PosePC(train=False, vis=True, packed_path=path, lib_handle=handle)
+    tr = PosePC(train=True, vis=False, packed_path=path, lib_handle=handle)
+    te = PosePC(train=False, vis=False, packed_path=path, lib_handle=handle)
+    assert len(vis) == 12 and len(tr) == 9 and len(te) == 3
+    assert sorted(np.concatenate([tr.starts, te.starts]).tolist()) == sorted(vis.starts.tolist())
+    perm = np.arange(12)
+    np.random.RandomState(1).shuffle(perm)                     # Config.dataset_random_seed of the reference
+    assert np.array_equal(np.concatenate([tr.starts, te.starts]), vis.starts[perm])
+    b = vis.batch([0, 5])
+    assert b["data"].shape == (2, 20, 128, 6) and b["skl"].shape == (2, 20, 3)
+    item = vis[5]
+    assert np.array_equal(item[0], b["data"][1].cpu().numpy())
+    assert np.array_equal(item[1], z["exp_key"][5])
+
+
 def test_errors(handle):
     P.check_errors(handle)
 

@@ -48,6 +48,22 @@ def test_lower_with_ffma_gcn(handle):
         handle.set_option("gcn_gemm", 1)
 
 
+def test_snippet_builder(handle):
+    """GPU snippet builder vs tensors built by the reference's own loader (bit-exact radar clouds, float64 IMU
+    re-framing) and vs the oracle for the seeded placement."""
+    P.check_snippet_builder(handle)
+
+
+@pytest.mark.parametrize("opt", ["point_gemm", "small_lstm_gemm"])
+def test_upper_lower_with_ffma_variants(handle, opt):
+    """The fp32 FFMA versions of the point encoders / H=64 LSTMs stay selectable (A/B numbers in profiles/)."""
+    handle.set_option(opt, 0)
+    try:
+        P.check_upper_lower_golden(handle, "synth3.npz")
+    finally:
+        handle.set_option(opt, 1)
+
+
 def test_transforms(handle):
     P.check_transforms(handle)
     P.check_transforms(handle, F=1000, n=128)

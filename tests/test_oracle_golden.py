@@ -90,3 +90,16 @@ def test_metrics_pin_on_slice(golden_dir):
     e = (g["pred"] - g["target"]).square().sum(-1).sqrt()
     assert abs(rep["mpjpe_cm"] - float(e.mean()) * 100) < 1e-4
     assert np.allclose(rep["per_joint_cm"], e.mean((0, 1)).numpy() * 100, atol=1e-4)
+
+
+def test_snippet_builder_oracle_matches_reference_loader():
+    """oracle.build_snippets (CPU restatement of Dataset_sample.py:153-260) against tensors produced by the reference's
+    own PosePC class on the first three recordings (scripts/pack_sample_data.py --fixture): bit-exact."""
+    import numpy as np
+    z = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "raw_subset.npz")))
+    starts = O.snippet_windows(z["rec_start"])
+    assert len(starts) == len(z["exp_data"]) == 12
+    slots = O.recover_slots(z, starts, z["exp_data"])
+    out = O.build_snippets(z, starts, slots)
+    for a, b in (("data", "exp_data"), ("imu", "exp_imu"), ("key", "exp_key"), ("R", "exp_R"), ("t", "exp_t"), ("skl", "exp_skl")):
+        assert np.array_equal(out[a], z[b]), a
