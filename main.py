@@ -22,6 +22,9 @@ def main():
     p.add_argument("--colab", action="store_true")
     p.add_argument("--imu_surrogate", action="store_true",
                    help="feed IMU_Net's training targets as (R, t) (needed while the IMU checkpoint is missing)")
+    p.add_argument("--from_raw", action="store_true",
+                   help="build the batches on the GPU from the packed raw sensor cache (Resource/Sample_data_packed) "
+                        "instead of reading the frozen tensors")
     a = p.parse_args()
 
     from mmego_b200.Config.config import Config
@@ -41,7 +44,7 @@ def main():
         p.print_help()
         return
     from mmego_b200.Processor.Test.Demo_test import MMEgo
-    MMEgo(imu_surrogate=True if a.imu_surrogate else None).eval_model()
+    MMEgo(imu_surrogate=True if a.imu_surrogate else None, from_raw=a.from_raw).eval_model()
 
 
 if __name__ == "__main__":

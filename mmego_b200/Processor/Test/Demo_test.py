@@ -6,7 +6,9 @@ return tuple (:184).  Differences, all on the host side:
     or the tail is handled by exact sums, so the printed means are the global means the reference computes,
   * error sums are accumulated on the device and read back once, instead of six .item() syncs per batch,
   * the sample set is read from the frozen tensor file built with the reference loader (np.random.seed(0)), because
-    the loader's pad-slot placement uses the unseeded global RNG (Dataset_sample.py:215-223).
+    the loader's pad-slot placement uses the unseeded global RNG (Dataset_sample.py:215-223); with `from_raw=True`
+    (`main.py --infer --from_raw`) the batches are instead built on the GPU from the packed raw sensor cache by
+    mmego_build_snippets (Util/Universal_Util/Dataset_sample.py of this package), seeded placement.
 """
 from __future__ import annotations
 
@@ -22,7 +24,7 @@ from ...pipeline import SUMS_LEN, MMEgoPipeline, report_from_sums
 
 
 class MMEgo:
-    def __init__(self, batch_size=None, device=None, imu_surrogate=None, quiet=False):
+    def __init__(self, batch_size=None, device=None, imu_surrogate=None, quiet=False, from_raw=False):
         self.device = torch.device(device or Config.device)
         if self.device.type != "cuda":
             raise MMEgoError("MMEgo needs a CUDA device (B200); there is no CPU fallback")
@@ -34,15 +36,28 @@ class MMEgo:
         missing = not os.path.exists(Config.model_IMU_path)
         self.imu_surrogate = missing if imu_surrogate is None else bool(imu_surrogate)
         self.quiet = quiet
-        if not os.path.exists(Config.sample_frozen_path):
-            raise FileNotFoundError(Config.sample_frozen_path)
-        z = np.load(Config.sample_frozen_path)
-        self.data = torch.from_numpy(z["data"]).float()
-        self.target = torch.from_numpy(z["target"]).float()
-        self.skl = torch.from_numpy(z["skl"]).float()
-        self.imu = torch.from_numpy(z["imu"]).float()
-        self.R_sur = torch.from_numpy(z["R_sur"]).float()
-        self.t_sur = torch.from_numpy(z["t_sur"]).float()
+        self.from_raw = bool(from_raw)
+        if self.from_raw:
+            # the whole sample set is built on the device from raw sensor frames (one kernel launch); the surrogate
+            # (R, t) are IMU_Net's training targets: R_R0R and the head joint (Train_IMU.py:127,138-139)
+            from ...Util.Universal_Util.Dataset_sample import PosePC
+            t0 = time.time()
+            ds = PosePC(train=False, vis=True, batch_length=self.frame_no, device=self.device)
+            b = ds.batch()
+            torch.cuda.synchronize(self.device)
+            self.build_seconds = time.time() - t0
+            self.data, self.target, self.skl, self.imu = b["data"], b["key"], b["skl"], b["imu"]
+            self.R_sur, self.t_sur = b["R"], b["key"][:, :, 20].contiguous()
+        else:
+            if not os.path.exists(Config.sample_frozen_path):
+                raise FileNotFoundError(Config.sample_frozen_path)
+            z = np.load(Config.sample_frozen_path)
+            self.data = torch.from_numpy(z["data"]).float()
+            self.target = torch.from_numpy(z["target"]).float()
+            self.skl = torch.from_numpy(z["skl"]).float()
+            self.imu = torch.from_numpy(z["imu"]).float()
+            self.R_sur = torch.from_numpy(z["R_sur"]).float()
+            self.t_sur = torch.from_numpy(z["t_sur"]).float()
         if missing and not quiet:
             print("IMU_Net checkpoint not found at %s: %s" % (
                 Config.model_IMU_path,
@@ -58,7 +73,7 @@ class MMEgo:
         with torch.no_grad():
             for s in range(0, n, bs):
                 e = min(n, s + bs)
-                data = self.data[s:e].to(dev, non_blocking=True).contiguous()
+                data = self.data[s:e].to(dev, non_blocking=True).contiguous().clone()   # forward mutates xyz in place
                 target = self.target[s:e].to(dev, non_blocking=True).contiguous()
                 skl = self.skl[s:e].to(dev, non_blocking=True).contiguous()
                 if self.imu_surrogate:

@@ -243,3 +243,22 @@ def test_sample835_surrogate_pin(capsys):
     assert abs(rep["angle_deg"] - float(pin["angle_deg"])) < 5e-3
     assert np.abs(rep["per_joint_cm"] - pin["per_joint_cm"]).max() < 1e-2
     assert len(out) == 6
+
+
+def test_sample835_from_raw_sensor_cache():
+    """The same 835-snippet evaluation with the batches BUILT ON THE GPU from the packed raw sensor frames
+    (mmego_build_snippets, seeded slot placement instead of the reference's unseeded one).  The networks are invariant to
+    the slot order up to summation order and top-64 ties, so the pin holds to the same tolerance."""
+    from mmego_b200.Config.config import Config
+    from mmego_b200.Processor.Test.Demo_test import MMEgo
+    if not os.path.exists(Config.sample_packed_path):
+        pytest.skip("packed raw cache not present (scripts/pack_sample_data.py)")
+    pin = np.load(os.path.join(P.GOLDEN, "sample835_pin.npz"))
+    m = MMEgo(batch_size=167, imu_surrogate=True, quiet=True, from_raw=True)
+    assert m.data.shape == (835, 20, 128, 6) and m.data.is_cuda
+    m.eval_model()
+    rep = m.report
+    print(f"from raw: build {m.build_seconds:.2f} s (incl. cache load), eval {m.seconds:.2f} s, MPJPE {rep['mpjpe_cm']:.6f} cm")
+    assert abs(rep["mpjpe_cm"] - float(pin["mpjpe_cm"])) < 2e-3
+    assert abs(rep["upper_cm"] - float(pin["upper_cm"])) < 1e-3
+    assert abs(rep["lower_cm"] - float(pin["lower_cm"])) < 5e-3
