@@ -31,6 +31,16 @@ KERNEL_NAMES = {0: "gemm_ffma_kernel<128,EPI_LSTM> (fp32 FFMA GEMM + fused LSTM 
                 1: "lstm_tc_step_kernel<3> (tcgen05 fp16x3 split-precision GEMM, TMEM partial sums drained to fp32 registers, fused LSTM cell)",
                 2: "lstm_tc_step_kernel<1> (tcgen05 fp16 GEMM, fused LSTM cell)"}
 UNIT = "frames/s"
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 L, N_PTS, N_IMU = 20, 128, 20
 H = 512
 # algorithmic FLOPs (2*MAC) per frame, SURVEY.md section 8(d)
@@ -138,7 +148,7 @@ def run_reference_arm(args):
                                    "oracle port of the reference's PyTorch-CPU path, fp32, torch threads = all cores"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -156,6 +166,12 @@ def main():
     ap.add_argument("--no-half", action="store_true", help="skip the extra pass in single-pass fp16 mode")
     ap.add_argument("--imu-gemm", type=int, default=None, help="0 fp32 FFMA, 1 tcgen05 fp16x3, 2 tcgen05 fp16 (default: library default)")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything else written to fd 1 while the bench runs (NCCL's version banner is
+    # printed from C) is sent to stderr, and the line is written to the real stdout at the end
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)
@@ -375,7 +391,7 @@ def main():
                                     "sample": f"{args.cpu_snippets} snippets ({args.cpu_snippets * L} frames) of the same "
                                               "synthetic workload, 1 warm-up + 2 timed passes of the oracle port "
                                               "(PyTorch CPU fp32, all host threads)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
