@@ -61,7 +61,8 @@ const char* mmego_last_error(const mmego_handle* h);
  *                         default; 2 = tcgen05 single-pass fp16, fastest, tolerance reported separately;
  *                         0 = fp32 FFMA GEMM),
  *          "gcn_gemm"    (ST-GCN GEMMs: 1 = tcgen05 fp16x3, default; 0 = fp32 FFMA),
- *          "host_chunk"  (mmego_infer_host: snippets per stage of its H2D / compute / D2H pipeline, default 1024),
+ *          "host_chunk"  (mmego_infer_host: snippets per stage of its H2D / compute / D2H pipeline, default 2048; the
+ *                         first stage is an eighth of that so the un-overlappable first copy stays short),
  *          "tc_kb_chunk" (imu_gemm=1: K blocks of 64 accumulated in TMEM before draining into fp32 registers, default 4;
  *                         8 is ~10 % faster and ~1.5x noisier),
  *          "tc_cta_pair" (H=512 LSTM kernel on CTA pairs, cta_group::2 M=256 tiles, default 1). */

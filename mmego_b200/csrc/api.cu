@@ -963,10 +963,25 @@ int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_h
     if (!h->h2d_stream) CUDA_TRY(h, cudaStreamCreate(&h->h2d_stream));
     if (!h->d2h_stream) CUDA_TRY(h, cudaStreamCreate(&h->d2h_stream));
     cudaStream_t st = h->own_stream;
-    // The batch is cut into chunks of `host_chunk` snippets: chunk i+1 is copied to the device while chunk i computes
-    // and chunk i-1's predictions travel back (three streams, two events per chunk).
+    // The batch is cut into chunks of up to `host_chunk` snippets: chunk i+1 is copied to the device while chunk i
+    // computes and chunk i-1's predictions travel back (three streams, two events per chunk).  The FIRST chunk is an
+    // eighth of that: its copy cannot overlap anything, so it is kept short and the pipeline fills early.
     const int Bc = (int)std::min<long long>(B, h->host_chunk);
-    const int nchunks = (B + Bc - 1) / Bc;
+    std::vector<std::pair<size_t, size_t>> chunks;      // (first snippet, count)
+    {
+        size_t b0 = 0;
+        const size_t first = (size_t)Bc / 8;
+        if (first >= 1 && (size_t)B > (size_t)Bc / 2 + first) {
+            chunks.push_back({0, first});
+            b0 = first;
+        }
+        while (b0 < (size_t)B) {
+            const size_t nb = std::min<size_t>(Bc, B - b0);
+            chunks.push_back({b0, nb});
+            b0 += nb;
+        }
+    }
+    const int nchunks = (int)chunks.size();
     const size_t F = (size_t)B * L;
     const size_t ws_bytes = mmego_workspace_bytes(h, MMEGO_STAGE_PIPELINE, Bc, L, N, n_imu);
     Carver c(nullptr);
@@ -1001,7 +1016,7 @@ int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_h
     CUDA_TRY(h, cudaMemcpyAsync(body, initial_body_host, (size_t)B_global * 60 * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
     if (metrics) CUDA_TRY(h, cudaMemsetAsync(sums, 0, MMEGO_SUMS_LEN * sizeof(double), h->h2d_stream));
     for (int i = 0; i < nchunks; ++i) {
-        const size_t b0 = (size_t)i * Bc, nb = std::min<size_t>(Bc, B - b0), f0 = b0 * L, nf = nb * L;
+        const size_t b0 = chunks[i].first, nb = chunks[i].second, f0 = b0 * L, nf = nb * L;
         CUDA_TRY(h, cudaMemcpyAsync(imu + f0 * n_imu * kImuFeat, imu_host + f0 * n_imu * kImuFeat,
                                     nf * n_imu * kImuFeat * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
         CUDA_TRY(h, cudaMemcpyAsync(data + f0 * N * 6, data_host + f0 * N * 6, nf * N * 6 * sizeof(float),
@@ -1012,7 +1027,7 @@ int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_h
         CUDA_TRY(h, cudaEventRecord(h->host_events[2 * i], h->h2d_stream));
     }
     for (int i = 0; i < nchunks; ++i) {
-        const size_t b0 = (size_t)i * Bc, nb = std::min<size_t>(Bc, B - b0), f0 = b0 * L, nf = nb * L;
+        const size_t b0 = chunks[i].first, nb = chunks[i].second, f0 = b0 * L, nf = nb * L;
         CUDA_TRY(h, cudaStreamWaitEvent(st, h->host_events[2 * i], 0));
         int rc = mmego_pipeline_forward(h, imu + f0 * n_imu * kImuFeat, data + f0 * N * 6, body, metrics ? tg + f0 * 63 : nullptr,
                                         pred + f0 * 63, metrics ? reinterpret_cast<double*>(sums) : nullptr, nullptr, nullptr,

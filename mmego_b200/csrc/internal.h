@@ -275,5 +275,5 @@ struct mmego_handle {
     size_t stage_bytes = 0;
     cudaStream_t own_stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> host_events;
-    long long host_chunk = 1024;   // snippets per H2D/compute/D2H pipeline stage of mmego_infer_host
+    long long host_chunk = 2048;   // snippets per H2D/compute/D2H pipeline stage of mmego_infer_host (first stage: 1/8)
 };

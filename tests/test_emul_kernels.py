@@ -120,6 +120,16 @@ def test_infer_host_chunk_pipeline_matches_device_path(handle):
     try:
         pred_h, sums = handle.infer_host(sb["imu"], sb["data"], sb["skl"], tg)
     finally:
-        handle.set_option("host_chunk", 1024)
+        handle.set_option("host_chunk", 2048)
     assert torch.equal(pred_h, pred_d)
     assert sums[43].item() == 12
+    # ramp-up: a short first stage (host_chunk / 8), then full stages, then the tail
+    sb = O.synth_batch(11, L=2, N=64, n_imu=1, seed=4, distinct_skeletons=True)
+    pred_d = handle.pipeline_forward(sb["imu"], sb["data"].clone(), sb["skl"])
+    handle.set_option("host_chunk", 8)
+    try:
+        pred_h, sums = handle.infer_host(sb["imu"], sb["data"], sb["skl"], (pred_d + 0.01).contiguous())
+    finally:
+        handle.set_option("host_chunk", 2048)
+    assert torch.equal(pred_h, pred_d)
+    assert sums[43].item() == 22
