@@ -61,6 +61,8 @@ const char* mmego_last_error(const mmego_handle* h);
  *                         default; 2 = tcgen05 single-pass fp16, fastest, tolerance reported separately;
  *                         0 = fp32 FFMA GEMM),
  *          "gcn_gemm"    (ST-GCN GEMMs: 1 = tcgen05 fp16x3, default; 0 = fp32 FFMA),
+ *          "point_gemm"  (radar point encoders + cross-attention: 1 = mma.sync fp16x3, default; 0 = fp32 FFMA),
+ *          "small_lstm_gemm" (H=64 LSTMs: 1 = mma.sync fp16x3, default; 0 = fp32 FFMA),
  *          "host_chunk"  (mmego_infer_host: snippets per stage of its H2D / compute / D2H pipeline, default 2048; the
  *                         first stage is an eighth of that so the un-overlappable first copy stays short),
  *          "tc_kb_chunk" (imu_gemm=1: K blocks of 64 accumulated in TMEM before draining into fp32 registers, default 4;
@@ -160,7 +162,7 @@ long long mmego_launch_count(const mmego_handle* h);
  * CUDA events on the launching stream.  profile_read synchronises on the recorded events and returns the summed
  * duration, the number of kernel launches and the number of spans of `name`
  * ("imu.fc1", "imu.lstm_fast", "imu.lstm_slow", "imu.pool", "imu.decode", "upper.point", "small_lstm", "upper.head_decode",
- *  "lower.gcn", "lower.frame", "lower.head_decode", "assemble_metrics"). */
+ *  "lower.gcn", "lower.frame", "lower.head_decode", "assemble_metrics", "build_snippets"). */
 int mmego_profile_begin(mmego_handle* h);
 int mmego_profile_read(mmego_handle* h, const char* name, double* total_ms, long long* launches, long long* spans);
 int mmego_profile_end(mmego_handle* h);
