@@ -262,3 +262,38 @@ def test_sample835_from_raw_sensor_cache():
     assert abs(rep["mpjpe_cm"] - float(pin["mpjpe_cm"])) < 2e-3
     assert abs(rep["upper_cm"] - float(pin["upper_cm"])) < 1e-3
     assert abs(rep["lower_cm"] - float(pin["lower_cm"])) < 5e-3
+
+
+def test_full_size_properties_b4096(handle):
+    """BASELINE.json's full size (B = 4096, L = 20, N = 128, n_imu = 20), through size-independent properties: the pass
+    is bit-deterministic; a snippet's prediction does not depend on its 4095 batch-mates (checked against a 4-snippet
+    call, which the oracle tests pin); the tensor-core (mma.sync) and fp32 FFMA versions of the point encoders and H=64
+    LSTMs agree within the position tolerance on all 81,920 frames; the error sums equal a host recomputation."""
+    from mmego_b200 import synth
+    B = 4096
+    sb = synth.batch(B, seed=1234)
+    imu, skl = sb["imu"].cuda(), sb["skl"].cuda()
+    data = sb["data"].cuda()
+    p1 = handle.pipeline_forward(imu, data.clone(), skl)
+    target = (p1 + 0.01).contiguous()
+    sums = torch.zeros(_capi.SUMS_LEN, dtype=torch.float64, device="cuda")
+    p2 = handle.pipeline_forward(imu, data.clone(), skl, target, sums)
+    assert torch.equal(p1, p2)
+    assert torch.isfinite(p1).all()
+    idx = torch.tensor([0, 1023, 2048, 4095])
+    small = handle.pipeline_forward(imu[idx].contiguous(), data[idx].contiguous(), skl[idx].contiguous())
+    assert P.maxerr(small, p1[idx]) < 3e-6
+    s = sums.cpu().numpy()
+    assert s[43] == B * 20
+    want = (p1.double() - target.double()).norm(dim=-1).sum(dim=(0, 1)).cpu().numpy()       # per-joint sums
+    assert np.allclose(s[0:21], want, rtol=1e-6)
+    handle.set_option("point_gemm", 0)
+    handle.set_option("small_lstm_gemm", 0)
+    try:
+        p3 = handle.pipeline_forward(imu, data.clone(), skl)
+    finally:
+        handle.set_option("point_gemm", 1)
+        handle.set_option("small_lstm_gemm", 1)
+    err = P.maxerr(p3, p1)
+    print(f"B=4096: mma.sync vs FFMA point/LSTM kernels max |d pred| = {err:.2e} m")
+    assert err < P.POS_TOL
