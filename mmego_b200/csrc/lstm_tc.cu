@@ -116,9 +116,24 @@ __device__ __forceinline__ float tanh_fast(float x) {
     const float big = fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * x)), 1.0f);
     return fabsf(x) < 0.25f ? p : big;
 }
+// Single-pass fp16 mode only: MUFU.TANH (relative error 2^-11, the precision h is stored with in that mode) for all five
+// gate functions, sigmoid(x) = 0.5 tanh(x/2) + 0.5 -- 5 SFU instructions per cell instead of 10.
+__device__ __forceinline__ float tanh_mufu(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <bool HALF>
 __device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po, float cprev, float& cn, float& h) {
-    cn = fmaf(sigmoid_fast(pf), cprev, sigmoid_fast(pi) * tanh_fast(pg));
-    h = sigmoid_fast(po) * tanh_fast(cn);
+    if (HALF) {
+        const float si = fmaf(0.5f, tanh_mufu(0.5f * pi), 0.5f), sf = fmaf(0.5f, tanh_mufu(0.5f * pf), 0.5f);
+        const float so = fmaf(0.5f, tanh_mufu(0.5f * po), 0.5f);
+        cn = fmaf(sf, cprev, si * tanh_mufu(pg));
+        h = so * tanh_mufu(cn);
+    } else {
+        cn = fmaf(sigmoid_fast(pf), cprev, sigmoid_fast(pi) * tanh_fast(pg));
+        h = sigmoid_fast(po) * tanh_fast(cn);
+    }
 }
 
 template <int NPASS, int NCTA, int BN>
@@ -378,7 +393,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
                         const float pg = fmaf(acc[2][j], p.out_scale, bias[2 * kUnitsPerTile + j]);
                         const float po = fmaf(acc[3][j], p.out_scale, bias[3 * kUnitsPerTile + j]);
                         float cn, hh;
-                        lstm_cell(pi, pf, pg, po, cprev[2 * j2 + e], cn, hh);
+                        lstm_cell<NPASS == 1>(pi, pf, pg, po, cprev[2 * j2 + e], cn, hh);
                         hv2[e] = hh * kActScale;
                         if (ok) __stcs(cbase + (long long)j * p.Spad, cn);
                     }
