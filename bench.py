@@ -270,21 +270,38 @@ def main():
     # ---- end to end through the host-buffer entry point (H2D + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
+        # caller-owned pinned result buffers, as a serving loop would keep them (a fresh 20 MB pinned allocation per call
+        # costs ~10 ms)
+        out_pred = torch.empty(B, L, 21, 3, dtype=torch.float32).pin_memory()
+        out_sums = torch.zeros(SUMS_LEN, dtype=torch.float64).pin_memory()
         for _ in range(2):
-            pipe.infer_host(imu_h, data_h, skl_h, target_h)
+            pipe.infer_host(imu_h, data_h, skl_h, target_h, out_pred=out_pred, out_sums=out_sums)
         barrier()
+        k2 = max(3, min(args.steps, 8))
+        step_s = []
         t0 = time.perf_counter()
-        k2 = max(2, min(args.steps, 5))
         for _ in range(k2):
-            pred_h, sums_h = pipe.infer_host(imu_h, data_h, skl_h, target_h)
+            ts = time.perf_counter()
+            pred_h, sums_h = pipe.infer_host(imu_h, data_h, skl_h, target_h, out_pred=out_pred, out_sums=out_sums)   # synchronous on return
+            step_s.append(time.perf_counter() - ts)
         barrier()
         dt = torch.tensor([(time.perf_counter() - t0) / k2], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         h2d = sum(t.numel() * t.element_size() for t in (imu_h, data_h, skl_h, target_h))
         d2h = pred_h.numel() * 4 + SUMS_LEN * 8
+        # host-to-device bandwidth of this box (one pinned 256 MB copy), to read the e2e figure against
+        probe = torch.empty(64 << 20, dtype=torch.float32).pin_memory()
+        probe_d = torch.empty_like(probe, device=dev)
+        probe_d.copy_(probe, non_blocking=True)
+        torch.cuda.synchronize()
+        tp = time.perf_counter()
+        probe_d.copy_(probe, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbs = probe.numel() * 4 / (time.perf_counter() - tp) / 1e9
         e2e = {"value": frames / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "ms_per_step": float(dt.item()) * 1e3, "steps": k2,
+               "step_ms_rank0": [round(x * 1e3, 2) for x in step_s], "h2d_gbs_rank0": round(h2d_gbs, 1),
                "api": "mmego_infer_host (pinned host buffers)"}
 
     half = None

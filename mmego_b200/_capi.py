@@ -355,8 +355,11 @@ class Handle:
             b_offset, Bg, ws.data_ptr(), ws.numel(), self._stream()), "pipeline_forward")
         return pred
 
-    def infer_host(self, imu, data, initial_body, target=None, body_index_mode=BODY_REF, b_offset=0, B_global=None):
-        """HOST tensors in, HOST tensors out (the call a reference-side binding makes per batch)."""
+    def infer_host(self, imu, data, initial_body, target=None, body_index_mode=BODY_REF, b_offset=0, B_global=None,
+                   out_pred=None, out_sums=None):
+        """HOST tensors in, HOST tensors out (the call a reference-side binding makes per batch).  `out_pred`
+        [B,L,21,3] float32 / `out_sums` [46] float64: caller-owned (ideally pinned) result buffers; allocated per call
+        when omitted (a fresh pinned allocation costs ~10 ms per 20 MB)."""
         for nm, v in (("imu", imu), ("data", data), ("initial_body", initial_body), ("target", target)):
             if v is not None and (v.is_cuda or v.dtype != torch.float32 or not v.is_contiguous()):
                 raise MMEgoError(f"{nm} must be a contiguous float32 HOST tensor")
@@ -364,8 +367,20 @@ class Handle:
         n = imu.shape[2]
         Bg = B if B_global is None else B_global
         pin = self.require_cuda
-        pred = torch.empty(B, L, 21, 3, dtype=torch.float32, pin_memory=pin)
-        sums = torch.zeros(SUMS_LEN, dtype=torch.float64, pin_memory=pin) if target is not None else None
+        if out_pred is not None:
+            if out_pred.is_cuda or out_pred.dtype != torch.float32 or not out_pred.is_contiguous() or out_pred.numel() != B * L * 63:
+                raise MMEgoError(f"out_pred must be a contiguous float32 HOST tensor of {B * L * 63} elements")
+            pred = out_pred
+        else:
+            pred = torch.empty(B, L, 21, 3, dtype=torch.float32, pin_memory=pin)
+        sums = None
+        if target is not None:
+            if out_sums is not None:
+                if out_sums.is_cuda or out_sums.dtype != torch.float64 or out_sums.numel() != SUMS_LEN:
+                    raise MMEgoError(f"out_sums must be a float64 HOST tensor of {SUMS_LEN} elements")
+                sums = out_sums
+            else:
+                sums = torch.zeros(SUMS_LEN, dtype=torch.float64, pin_memory=pin)
         self._ck(self.lib.dll.mmego_infer_host(self._h, imu.data_ptr(), data.data_ptr(), initial_body.data_ptr(),
                                                _ptr(target), pred.data_ptr(), _ptr(sums), B, L, N, n, body_index_mode,
                                                b_offset, Bg), "infer_host")

@@ -964,19 +964,38 @@ int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_h
     if (!h->d2h_stream) CUDA_TRY(h, cudaStreamCreate(&h->d2h_stream));
     cudaStream_t st = h->own_stream;
     // The batch is cut into chunks of up to `host_chunk` snippets: chunk i+1 is copied to the device while chunk i
-    // computes and chunk i-1's predictions travel back (three streams, two events per chunk).  The FIRST chunk is an
-    // eighth of that: its copy cannot overlap anything, so it is kept short and the pipeline fills early.
+    // computes and chunk i-1's predictions travel back (three streams, two events per chunk).  The FIRST chunk is short
+    // (its copy cannot overlap anything, so the pipeline should fill early), and every chunk size is picked so that
+    // the work items of the dominant kernel (H=512 LSTM step: 16 per pair of 128-sequence tiles) fill whole rounds of
+    // the sm_count/2 CTA pairs -- a 2048-snippet chunk would leave the last of its 35 rounds 40 % empty.
     const int Bc = (int)std::min<long long>(B, h->host_chunk);
     std::vector<std::pair<size_t, size_t>> chunks;      // (first snippet, count)
     {
+        const long long pairs = std::max(1, h->sm_count / 2);
+        auto efficiency = [&](long long nb) {
+            const long long items = ((nb * L + 255) / 256) * 16;
+            const long long rounds = (items + pairs - 1) / pairs;
+            return (double)items / (double)(rounds * pairs) * ((double)nb * L / (double)(((nb * L + 255) / 256) * 256));
+        };
+        auto best = [&](long long lo, long long hi) {       // most efficient size in [lo, hi], larger wins ties
+            long long arg = hi;
+            double e = -1.0;
+            for (long long nb = hi; nb >= lo && nb >= 1; --nb) {
+                const double v = efficiency(nb);
+                if (v > e + 1e-9) { e = v; arg = nb; }
+            }
+            return arg;
+        };
         size_t b0 = 0;
         const size_t first = (size_t)Bc / 8;
         if (first >= 1 && (size_t)B > (size_t)Bc / 2 + first) {
-            chunks.push_back({0, first});
-            b0 = first;
+            const size_t f = Bc >= 512 ? (size_t)best(Bc / 16, Bc / 4) : first;
+            chunks.push_back({0, f});
+            b0 = f;
         }
         while (b0 < (size_t)B) {
-            const size_t nb = std::min<size_t>(Bc, B - b0);
+            size_t nb = std::min<size_t>(Bc, B - b0);
+            if (B - b0 > (size_t)Bc && Bc >= 512) nb = (size_t)best(Bc - Bc / 8, Bc);
             chunks.push_back({b0, nb});
             b0 += nb;
         }

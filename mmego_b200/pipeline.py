@@ -82,10 +82,12 @@ class MMEgoPipeline:
         return self.handle.pipeline_forward(imu, data, skl, target, sums, self.body_mode, b_offset, B_global, outs,
                                             want_pred)
 
-    def infer_host(self, imu, data, skl, target=None, b_offset: int = 0, B_global: Optional[int] = None):
-        """Host tensors in, (pred, sums) host tensors out; copies are part of the call."""
+    def infer_host(self, imu, data, skl, target=None, b_offset: int = 0, B_global: Optional[int] = None,
+                   out_pred=None, out_sums=None):
+        """Host tensors in, (pred, sums) host tensors out; copies are part of the call.  out_pred / out_sums: optional
+        caller-owned pinned result buffers (reused across calls)."""
         self._sync()
-        return self.handle.infer_host(imu, data, skl, target, self.body_mode, b_offset, B_global)
+        return self.handle.infer_host(imu, data, skl, target, self.body_mode, b_offset, B_global, out_pred, out_sums)
 
 
 def shard_bounds(B: int, world: int, rank: int) -> Tuple[int, int]:
