@@ -297,12 +297,29 @@ __global__ void __launch_bounds__(NT, 4) lower_frame_mma_kernel(float* __restric
         }
         __syncthreads();
         // ---- B1: rank select (equal keys: the lower slot wins) ---------------------------------------------------
+        // rank(p) = #{q < p: key[q] >= key[p]} + #{q > p: key[q] > key[p]}; keys are read four at a time (broadcast
+        // 16-byte loads), one compare per key: with 'x >= k' for slots below p and 'x > k' above, the tie rule needs no
+        // second compare.
         for (int p = tid; p < N; p += NT) {
             const float kx = s.key[p];
             int rank = 0;
-            for (int q = 0; q < N; ++q) {
+            const int n4 = N & ~3;
+            for (int q = 0; q < n4; q += 4) {
+                const float4 k4 = *reinterpret_cast<const float4*>(s.key + q);
+                if (q + 3 < p) {
+                    rank += (k4.x >= kx) + (k4.y >= kx) + (k4.z >= kx) + (k4.w >= kx);
+                } else if (q > p) {
+                    rank += (k4.x > kx) + (k4.y > kx) + (k4.z > kx) + (k4.w > kx);
+                } else {                                  // the group that contains p
+                    rank += (q < p ? k4.x >= kx : (q > p && k4.x > kx));
+                    rank += (q + 1 < p ? k4.y >= kx : (q + 1 > p && k4.y > kx));
+                    rank += (q + 2 < p ? k4.z >= kx : (q + 2 > p && k4.z > kx));
+                    rank += (q + 3 < p ? k4.w >= kx : (q + 3 > p && k4.w > kx));
+                }
+            }
+            for (int q = n4; q < N; ++q) {
                 const float kq = s.key[q];
-                rank += (kq > kx || (kq == kx && q < p)) ? 1 : 0;
+                rank += (q < p ? kq >= kx : (q > p && kq > kx));
             }
             if (rank < kLowerPts) s.sel[rank] = p;
         }

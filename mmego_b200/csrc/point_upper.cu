@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(MT, 2) upper_point_mma_kernel(float* __restric
             S = fmaf(sc, s.part[parity][w][65], S);
             if (tid < 64) G = fmaf(sc, s.part[parity][w][tid], G);
         }
-        const float inv = 1.0f / S;
+        const float inv = __fdividef(1.0f, S);      // S in [1, N]; no IEEE slow path between warp-wide MMAs (see lstm_small.cu)
         if (tid < 64) gout[f * 64 + tid] = G * inv;
         if (gwf)
             for (int p = tid; p < N; p += MT) gwf[p] = expf(gwf[p] - M) * inv;
