@@ -37,7 +37,9 @@ struct Cfg {
     static constexpr int W_TILE = BN * BK * 2;
     static constexpr int STAGE_BYTES = 2 * (A_TILE + W_TILE);
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int BIAS_LD = BN + 1;                               // padded: rows r % rowmod hit distinct banks
+    static constexpr int BIAS_BYTES = 16 * BIAS_LD * 4;                  // bias table [rowmod <= 16][BN] in shared memory
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + BIAS_BYTES;
     static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;    // 64, 128, 256: powers of two
     static constexpr int COLS_PER_THREAD = BN / 4;                       // 8, 16, 32
 };
@@ -95,6 +97,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant_
     if (warp == 1) {
         tmem_alloc(tmem_holder, C::TMEM_COLS);
         tmem_relinquish();
+    }
+    // bias table in shared memory: with rowmod > 0 (the graph conv's per-joint bias) every lane of an epilogue warp needs a
+    // different table row, and reading it from global was a 15-sector gather per load that throttled the LSU
+    // (ncu: lg_throttle 7.5, 2.6 M requests x 14.7 sectors on the N=128 graph conv)
+    float* sbias = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+    {
+        const int rows = p.rowmod > 0 ? p.rowmod : 1;
+        for (int i = threadIdx.x; i < rows * BN; i += kThreads) sbias[(i / BN) * C::BIAS_LD + (i % BN)] = p.bias[i];
     }
     tc_fence_before();
     __syncthreads();
@@ -207,11 +217,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant_
             }
             const int r = r0 + q * 32 + lane;          // row inside the snippet
             if (r < p.RP) {
-                const float* bias = p.bias + (p.rowmod > 0 ? (r % p.rowmod) * p.N : 0) + col0;
+                const float* bias = sbias + (p.rowmod > 0 ? (r % p.rowmod) * C::BIAS_LD : 0) + col0;
                 float v[CPT];
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) {
-                    float x = fmaf(acc[j], p.out_scale, __ldg(bias + j));
+                    float x = fmaf(acc[j], p.out_scale, bias[j]);
                     v[j] = p.relu ? fmaxf(x, 0.f) : x;
                 }
                 if (p.out_hi) {
