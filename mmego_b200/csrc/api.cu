@@ -557,6 +557,11 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
         h->point_gemm = (int)value;
         return MMEGO_OK;
     }
+    if (!strcmp(key, "head_gemm")) {
+        if (value < 0 || value > 1) return fail(h, MMEGO_EINVAL, "head_gemm must be 0 (fp32 FFMA) or 1 (mma.sync fp16x3)");
+        h->head_gemm = (int)value;
+        return MMEGO_OK;
+    }
     if (!strcmp(key, "small_lstm_gemm")) {
         if (value < 0 || value > 1) return fail(h, MMEGO_EINVAL, "small_lstm_gemm must be 0 (fp32 FFMA) or 1 (mma.sync fp16x3)");
         h->small_lstm_gemm = (int)value;
@@ -642,6 +647,12 @@ int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const 
             }
             ok &= upload(h, pack_linear(sd.get("mlpHead.fc1.weight", 128 * 128), sd.get("mlpHead.fc1.bias", 128), 128, {128}), W.fc1);
             ok &= upload(h, pack_linear(sd.get("mlpHead.fc2.weight", 87 * 128), sd.get("mlpHead.fc2.bias", 87), 87, {128}), W.fc2);
+            {
+                const std::vector<float> hb = pack_head_mma({{sd.get("mlpHead.fc1.weight", 128 * 128), sd.get("mlpHead.fc1.bias", 128), 128, 128},
+                                                             {sd.get("mlpHead.fc2.weight", 87 * 128), sd.get("mlpHead.fc2.bias", 87), 87, 128}});
+                if (hb.size() != upper_head_mma_words()) return fail(h, MMEGO_ESHAPE, "set_weights: head layout mismatch");
+                ok &= upload(h, hb, W.head_mma);
+            }
             W.ready = ok;
         } else if (net == MMEGO_NET_LOWER) {
             LowerWeights& W = h->lower;
@@ -680,6 +691,13 @@ int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const 
             ok &= upload(h, pack_linear(sd.get("fusion.fc0.weight", 128 * 173), sd.get("fusion.fc0.bias", 128), 128, {128, 45}), W.fc0);
             ok &= upload(h, pack_linear(sd.get("fusion.fc1.weight", 64 * 128), sd.get("fusion.fc1.bias", 64), 64, {128}), W.fc1);
             ok &= upload(h, pack_linear(sd.get("fusion.fc2.weight", 42 * 64), sd.get("fusion.fc2.bias", 42), 42, {64}), W.fc2);
+            {
+                const std::vector<float> hb = pack_head_mma({{sd.get("fusion.fc0.weight", 128 * 173), sd.get("fusion.fc0.bias", 128), 128, 173},
+                                                             {sd.get("fusion.fc1.weight", 64 * 128), sd.get("fusion.fc1.bias", 64), 64, 128},
+                                                             {sd.get("fusion.fc2.weight", 42 * 64), sd.get("fusion.fc2.bias", 42), 42, 64}});
+                if (hb.size() != lower_head_mma_words()) return fail(h, MMEGO_ESHAPE, "set_weights: head layout mismatch");
+                ok &= upload(h, hb, W.head_mma);
+            }
             W.ready = ok;
         } else {
             return fail(h, MMEGO_EINVAL, "set_weights: unknown net %d", net);
@@ -791,8 +809,12 @@ int mmego_upper_forward(mmego_handle* h, float* x, const float* h0, const float*
     const float* hs = run_small_lstm(h, W.lstm, w.g, 64, h0, c0, hn, cn, B, L, w.lstm, st);   // :339
     tap(h, "upper.lstm", hs, (size_t)F * 128 * 4, st);
     Prof p(h, "upper.head_decode", st);
-    linear(h, W.fc1, hs, 128, w.h1, 128, F, 1, st);                                     // :351-353
-    linear(h, W.fc2, w.h1, 128, w.o, 87, F, 0, st);
+    if (h->head_gemm) {
+        launch_upper_head_mma(hs, W.head_mma.p, w.o, F, h->sm_count, st);                // :351-353
+    } else {
+        linear(h, W.fc1, hs, 128, w.h1, 128, F, 1, st);
+        linear(h, W.fc2, w.h1, 128, w.o, 87, F, 0, st);
+    }
     tap(h, "upper.o", w.o, (size_t)F * 87 * 4, st);
     launch_upper_decode(w.o, initial_body, R, t, l, q, F, L, body_index_mode, (long long)b_offset * L, B_global, st);   // :355-387
     CUDA_TRY(h, cudaGetLastError());
@@ -846,14 +868,16 @@ int mmego_lower_forward(mmego_handle* h, const float* upper_l, float* x, const f
     const float* hs = run_small_lstm(h, W.lstm, w.ak, 192, nullptr, nullptr, nullptr, nullptr, B, L, w.lstm, st);   // :117
     tap(h, "lower.lstm", hs, (size_t)F * 128 * 4, st);
     Prof p(h, "lower.head_decode", st);
-    {
+    if (h->head_gemm) {
+        launch_lower_head_mma(hs, w.uh, W.head_mma.p, w.o, F, h->sm_count, st);           // :119-124
+    } else {
         GemmArgs a = gemm_begin(W.fc0, w.f0, 128, F, 1);                                  // :119-121
         gemm_seg(a, W.fc0, hs, 128);
         gemm_seg(a, W.fc0, w.uh, 45);
         run_gemm(h, a, EPI_STORE, st);
+        linear(h, W.fc1, w.f0, 128, w.f1, 64, F, 1, st);                                  // :122-123
+        linear(h, W.fc2, w.f1, 64, w.o, 42, F, 0, st);                                    // :124
     }
-    linear(h, W.fc1, w.f0, 128, w.f1, 64, F, 1, st);                                      // :122-123
-    linear(h, W.fc2, w.f1, 64, w.o, 42, F, 0, st);                                        // :124
     tap(h, "lower.o", w.o, (size_t)F * 42 * 4, st);
     launch_lower_decode(w.o, initial_body, R, t, l, q, F, L, body_index_mode, (long long)b_offset * L, B_global, st);   // :126-135, 235-238
     CUDA_TRY(h, cudaGetLastError());

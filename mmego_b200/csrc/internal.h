@@ -82,6 +82,11 @@ void launch_upper_point_mma(float* x, const float* R, const float* t, const floa
 void launch_lstm_small_mma(const float* x, long long ldx, int In, const float* blob, float* gx, const float* h0,
                            const float* c0, float* y, float* hn, float* cn, int S, int T, int sm_count,
                            cudaStream_t st);
+void launch_upper_head_mma(const float* x, const float* blob, float* o, long long F, int sm_count, cudaStream_t st);
+void launch_lower_head_mma(const float* hs, const float* uh, const float* blob, float* o, long long F, int sm_count,
+                           cudaStream_t st);
+size_t upper_head_mma_words();
+size_t lower_head_mma_words();
 size_t lower_frame_smem_bytes();
 int lower_frame_max_points();
 void launch_lower_frame(float* x, const float* R, const float* t, const float* kfeat, const float* wblob, float* ak,
@@ -185,6 +190,7 @@ struct UpperWeights {
     DevBuf point_mma;  // the same network as mma.sync fragments (UpperMmaLayout)
     PackedSmallLstmLayer lstm[3];
     PackedGemm fc1, fc2;
+    DevBuf head_mma;   // mlpHead.fc1/fc2 as mma.sync fragments (pack_head_mma)
 };
 struct GcnLayerWeights {
     DevBuf ahat;       // [2][15][15]
@@ -203,6 +209,7 @@ struct LowerWeights {
     PackedGemm fcn;
     PackedSmallLstmLayer lstm[3];
     PackedGemm fc0, fc1, fc2;
+    DevBuf head_mma;   // fusion.fc0/fc1/fc2 as mma.sync fragments
 };
 
 // host-side packing (pack.cpp; pure C++, unit-tested on CPU)
@@ -262,6 +269,7 @@ struct mmego_handle {
     int tc_cta_pair = 1;      // H=512 LSTM kernel: 1 = CTA pairs (cta_group::2, M = 256)
     int gcn_gemm = 0;         // ST-GCN GEMMs: 0 = fp32 FFMA, 1 = tcgen05 fp16x3 (default when available)
     int point_gemm = 1;       // point encoders + cross attention: 0 = fp32 FFMA, 1 = mma.sync fp16x3 (default)
+    int head_gemm = 1;        // fully connected heads: 0 = fp32 FFMA GEMMs, 1 = one fused mma.sync kernel per head (default)
     int small_lstm_gemm = 1;  // H=64 LSTMs: 0 = fp32 FFMA, 1 = mma.sync fp16x3 (default)
     int tc_kb_chunk0 = 8;     // ... of the first two chunks of every tile
     int tc_kb_chunk = 4;      // fp16x3 mode: K blocks (of 64) per TMEM partial accumulation (see lstm_tc.cu)

@@ -360,6 +360,26 @@ std::vector<float> pack_imu_fc1_mma(const HostPackedGemm& g) {
     return v;
 }
 
+// Fully connected heads for heads_mma.cu: layers given as (W [N][K] row-major, b [N]); blob = per layer frags | bias
+// (padded to 8 NT), then the out scales [3].  Offsets must match HeadLayout in heads_mma.cu.
+std::vector<float> pack_head_mma(const std::vector<HeadLayerSpec>& layers) {
+    size_t total = 0;
+    for (const HeadLayerSpec& L : layers) total += (size_t)mma_frag_words((L.K + 15) / 16, (L.N + 7) / 8) + (size_t)(L.N + 7) / 8 * 8;
+    const size_t os = total;
+    total = (total + 3 + 3) / 4 * 4;
+    std::vector<float> v(total, 0.f);
+    size_t off = 0;
+    for (size_t l = 0; l < layers.size(); ++l) {
+        const HeadLayerSpec& L = layers[l];
+        const int KS = (L.K + 15) / 16, NT = (L.N + 7) / 8;
+        v[os + l] = pack_mma_weight(L.W, L.K, iota_map(L.K, KS * 16), iota_map(L.N, NT * 8), &v[off]);
+        off += (size_t)mma_frag_words(KS, NT);
+        for (int o = 0; o < L.N; ++o) v[off + o] = L.b[o];
+        off += (size_t)NT * 8;
+    }
+    return v;
+}
+
 std::vector<float> pack_data_bn(const StateDict& sd, const std::string& gp) {
     BnAffine a = bn_affine(sd, gp + "data_bn", 45);
     std::vector<float> v(90);

@@ -43,6 +43,12 @@ HostSmallLstm pack_small_lstm(const StateDict& sd, const std::string& prefix, in
 
 std::vector<float> pack_small_lstm_mma(const StateDict& sd, const std::string& prefix, int layer, int In);
 std::vector<float> pack_imu_fc1_mma(const HostPackedGemm& fc1);
+struct HeadLayerSpec {
+    const float* W;   // [N][K] row-major (torch nn.Linear.weight)
+    const float* b;   // [N]
+    int N, K;
+};
+std::vector<float> pack_head_mma(const std::vector<HeadLayerSpec>& layers);
 std::vector<float> pack_upper_point(const StateDict& sd);
 std::vector<float> pack_lower_frame(const StateDict& sd);
 // mma.sync (fp16 hi/lo fragment) packing of the folded blobs above (point_layout.h: UpperMmaLayout / LowerMmaLayout)

@@ -54,7 +54,7 @@ def test_snippet_builder(handle):
     P.check_snippet_builder(handle)
 
 
-@pytest.mark.parametrize("opt", ["point_gemm", "small_lstm_gemm"])
+@pytest.mark.parametrize("opt", ["point_gemm", "small_lstm_gemm", "head_gemm"])
 def test_upper_lower_with_ffma_variants(handle, opt):
     """The fp32 FFMA versions of the point encoders / H=64 LSTMs stay selectable (A/B numbers in profiles/)."""
     handle.set_option(opt, 0)
@@ -287,13 +287,13 @@ def test_full_size_properties_b4096(handle):
     assert s[43] == B * 20
     want = (p1.double() - target.double()).norm(dim=-1).sum(dim=(0, 1)).cpu().numpy()       # per-joint sums
     assert np.allclose(s[0:21], want, rtol=1e-6)
-    handle.set_option("point_gemm", 0)
-    handle.set_option("small_lstm_gemm", 0)
+    for o in ("point_gemm", "small_lstm_gemm", "head_gemm"):
+        handle.set_option(o, 0)
     try:
         p3 = handle.pipeline_forward(imu, data.clone(), skl)
     finally:
-        handle.set_option("point_gemm", 1)
-        handle.set_option("small_lstm_gemm", 1)
+        for o in ("point_gemm", "small_lstm_gemm", "head_gemm"):
+            handle.set_option(o, 1)
     err = P.maxerr(p3, p1)
     print(f"B=4096: mma.sync vs FFMA point/LSTM kernels max |d pred| = {err:.2e} m")
     assert err < P.POS_TOL
