@@ -40,11 +40,12 @@ class PosePC:
     len(ds) / ds.starts follow the reference's ordering rules: vis=True keeps recording order; otherwise snippets are
     shuffled with RandomState(Config.dataset_random_seed) and split 80/20 (train / test).  `ds.batch(indices)` builds
     the tensors of those snippets on the device; `ds[i]` returns one snippet's tuple like the reference's __getitem__
-    (numpy, via a device round trip -- for compatibility, not for speed)."""
+    (numpy, via a device round trip -- for compatibility, not for speed; fields the cache does not hold are zeros)."""
 
     def __init__(self, train=True, vis=False, batch_length=None, packed_path: Optional[str] = None, device=None,
                  seed: int = 0, lib_handle=None):
         self.frame_no = int(batch_length or Config.frame_no)
+        self.vis, self.train = bool(vis), bool(train)
         self.pc_no = Config.pc_no
         self.seed = int(seed)
         path = packed_path or Config.sample_packed_path
@@ -76,5 +77,12 @@ class PosePC:
         return out
 
     def __getitem__(self, index):
+        """One snippet in the order of the reference's __getitem__ (Dataset_sample.py:73-94):
+        (ti, label, skl, imu, ground, foot_contact, R_R0R, t_R0R[, R_RtW with vis=True]).  ground, foot_contact and R_RtW
+        are not in the packed cache (the inference path never reads them) and come back as zeros of the right shape."""
         o = self.batch([index])
-        return tuple(o[k][0].cpu().numpy() for k in ("data", "key", "skl", "imu", "R", "t"))
+        g = {k: v[0].cpu().numpy() for k, v in o.items()}
+        L = self.frame_no
+        item = (g["data"], g["key"], g["skl"], g["imu"], np.zeros((L, 1, 4), np.float32), np.zeros((L, 2, 2), np.int64), g["R"],
+                g["t"].reshape(L, 1, 3))
+        return item + (np.zeros((L, 3, 3), np.float32),) if self.vis else item

@@ -235,7 +235,7 @@ struct MmaCarve {
 __host__ __device__ inline MmaCarve lower_mma_carve(unsigned char* base, int N) {
     MmaCarve c;
     size_t off = 0;
-    auto take = [&](size_t n) { unsigned char* p = base + off; off += (n + 15) & ~size_t(15); return p; };
+    auto take = [&](size_t n) { unsigned char* p = base ? base + off : nullptr; off += (n + 15) & ~size_t(15); return p; };
     c.w = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * kSmemWeightWords));
     c.Kf = reinterpret_cast<float*>(take(sizeof(float) * 16 * KF_LD));
     c.vp = reinterpret_cast<float*>(take(sizeof(float) * 16 * 64));

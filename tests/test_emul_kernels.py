@@ -87,8 +87,10 @@ def test_posepc_windows_split(handle, tmp_path):
     b = vis.batch([0, 5])
     assert b["data"].shape == (2, 20, 128, 6) and b["skl"].shape == (2, 20, 3)
     item = vis[5]
+    assert len(item) == 9 and len(te[0]) == 8                 # the reference's tuple lengths (vis / test)
     assert np.array_equal(item[0], b["data"][1].cpu().numpy())
     assert np.array_equal(item[1], z["exp_key"][5])
+    assert np.array_equal(item[6], z["exp_R"][5]) and item[7].shape == (20, 1, 3)
 
 
 def test_errors(handle):
