@@ -207,6 +207,19 @@ def check_errors(h):
     with pytest.raises(_capi.MMEgoError, match="missing state_dict tensor"):
         h2.set_weights(_capi.NET_UPPER, {"module0.conv1.weight": torch.zeros(8, 6, 1)})
     h2.close()
+    for opt in ("point_gemm", "small_lstm_gemm", "head_gemm", "gcn_gemm"):
+        with pytest.raises(_capi.MMEgoError):
+            h.set_option(opt, 7)
+    # snippet builder: a raw-frame table with a missing array, a slot table of the wrong size
+    z = dict(np.load(os.path.join(GOLDEN, "raw_subset.npz")))
+    raw = {k: torch.from_numpy(np.ascontiguousarray(z[k])).to(h.device) for k in _capi.RawFramesStruct.DTYPES}
+    st = torch.zeros(1, dtype=torch.int64, device=h.device)
+    with pytest.raises(KeyError):
+        h.build_snippets({k: v for k, v in raw.items() if k != "imu"}, st)
+    with pytest.raises(_capi.MMEgoError, match="slot_src"):
+        h.build_snippets(raw, st, torch.zeros(5, dtype=torch.int32, device=h.device))
+    with pytest.raises(_capi.MMEgoError):
+        h.build_snippets(dict(raw, points=raw["points"].double()), st)          # wrong dtype
 
 
 def check_snippet_builder(h):
