@@ -336,7 +336,7 @@ void launch_lstm_small_mma(const float* x, long long ldx, int In, const float* b
         cudaFuncSetAttribute(lstm_rec_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem + 2 * 4 * 8192);
     }
     const long long tiles = (M + 63) / 64;
-    const long long per_slab = sm_count > 0 ? sm_count : 1;     // 4 slabs x sm_count CTAs: 2-4 resident CTAs per SM (smem: KS x 8 KB each)
+    const long long per_slab = sm_count >= 2 ? sm_count / 2 : 1;   // 4 slabs x sm_count/2 persistent CTAs (twice as many measured 10 % slower)
     dim3 pgrid((unsigned)(tiles < per_slab ? tiles : per_slab), 4);
     if (KS == 4) {
         MMEGO_LAUNCH(lstm_proj_mma_kernel<4>, pgrid, dim3(PROJ_NT), psmem, st, x, ldx, blob, gx, M);
