@@ -63,6 +63,7 @@ const char* mmego_last_error(const mmego_handle* h);
  *          "gcn_gemm"    (ST-GCN GEMMs: 1 = tcgen05 fp16x3, default; 0 = fp32 FFMA),
  *          "point_gemm"  (radar point encoders + cross-attention: 1 = mma.sync fp16x3, default; 0 = fp32 FFMA),
  *          "small_lstm_gemm" (H=64 LSTMs: 1 = mma.sync fp16x3, default; 0 = fp32 FFMA),
+ *          "gcn_kb_chunk" (gcn_gemm=1: K blocks of 64 accumulated in TMEM before draining into fp32 registers, default 4),
  *          "head_gemm"   (fully connected heads: 1 = one fused mma.sync kernel per head, default; 0 = fp32 FFMA GEMMs),
  *          "host_chunk"  (mmego_infer_host: snippets per stage of its H2D / compute / D2H pipeline, default 2048; the
  *                         first stage is an eighth of that so the un-overlappable first copy stays short),

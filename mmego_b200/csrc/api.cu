@@ -557,6 +557,11 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
         h->point_gemm = (int)value;
         return MMEGO_OK;
     }
+    if (!strcmp(key, "gcn_kb_chunk")) {
+        if (value < 0 || value > 64) return fail(h, MMEGO_EINVAL, "gcn_kb_chunk must be in 0..64");
+        h->gcn_kb_chunk = (int)value;
+        return MMEGO_OK;
+    }
     if (!strcmp(key, "head_gemm")) {
         if (value < 0 || value > 1) return fail(h, MMEGO_EINVAL, "head_gemm must be 0 (fp32 FFMA) or 1 (mma.sync fp16x3)");
         h->head_gemm = (int)value;

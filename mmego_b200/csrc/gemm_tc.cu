@@ -540,7 +540,7 @@ int tc_gcn_gemm(mmego_handle* h, const TcGemmW& w, const void* a0hi, const void*
     p.kb0 = (c0 + BK - 1) / BK;
     p.kb1 = a1hi ? (c1 + BK - 1) / BK : 0;
     p.shift_step = kGcnV;
-    p.kb_chunk = h->tc_kb_chunk > 0 ? h->tc_kb_chunk : (p.n0 * p.kb0 + p.kb1);
+    p.kb_chunk = h->gcn_kb_chunk > 0 ? h->gcn_kb_chunk : (p.n0 * p.kb0 + p.kb1);
     p.bias = w.bias;
     p.rowmod = rowmod;
     p.relu = relu;

@@ -269,6 +269,7 @@ struct mmego_handle {
     int tc_cta_pair = 1;      // H=512 LSTM kernel: 1 = CTA pairs (cta_group::2, M = 256)
     int gcn_gemm = 0;         // ST-GCN GEMMs: 0 = fp32 FFMA, 1 = tcgen05 fp16x3 (default when available)
     int point_gemm = 1;       // point encoders + cross attention: 0 = fp32 FFMA, 1 = mma.sync fp16x3 (default)
+    int gcn_kb_chunk = 4;     // ST-GCN tcgen05 GEMMs: K blocks of 64 accumulated in TMEM before draining into fp32 registers (0 = all)
     int head_gemm = 1;        // fully connected heads: 0 = fp32 FFMA GEMMs, 1 = one fused mma.sync kernel per head (default)
     int small_lstm_gemm = 1;  // H=64 LSTMs: 0 = fp32 FFMA, 1 = mma.sync fp16x3 (default)
     int tc_kb_chunk0 = 8;     // ... of the first two chunks of every tile
