@@ -289,7 +289,7 @@ int imu_chunk_forward_tc(mmego_handle* h, const float* imu, float* R, float* t, 
     auto lo = [&](void* const* planes) { return npass == 3 ? planes[1] : nolo; };
     {
         Prof p(h, "imu.fc1", st);
-        tc_imu_fc1(imu, W.fc1_mma.p, w.u[0], lo(w.u), S * n, h->sm_count, st);                               // Net/IMU_Net.py:79
+        tc_imu_fc1(imu, W.fc1_mma.p, w.u[0], lo(w.u), S * n, h->sm_count, h->tc_lo_drop, st);                               // Net/IMU_Net.py:79
     }
     auto tap_split = [&](const char* name, void* const* planes, long long elems) {
         auto it = h->taps.find(name);
@@ -309,7 +309,7 @@ int imu_chunk_forward_tc(mmego_handle* h, const float* imu, float* R, float* t, 
     tap_split("imu.f", w.y1, S * n * 2 * kImuH);
     {
         Prof p(h, "imu.pool", st);
-        tc_imu_pool(w.y1[0], lo(w.y1), W.attn.p, w.s[0], lo(w.s), S, n, st);              // :82-83
+        tc_imu_pool(w.y1[0], lo(w.y1), W.attn.p, w.s[0], lo(w.s), S, n, h->tc_lo_drop, st);              // :82-83
     }
     tap_split("imu.s", w.s, S * 2 * kImuH);
     {
@@ -572,6 +572,31 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
         h->small_lstm_gemm = (int)value;
         return MMEGO_OK;
     }
+    if (!strcmp(key, "tc_lo_drop")) {
+        if (value < 0 || value > 6) return fail(h, MMEGO_EINVAL, "tc_lo_drop must be in 0..6");
+#ifndef MMEGO_EMUL
+        // the packed weight planes are rounded in place: the option can only grow once weights are loaded
+        if (h->imu.tc_ready && value < h->tc_lo_drop_w)
+            return fail(h, MMEGO_ESTATE, "tc_lo_drop: the packed weights are already rounded to fewer bits; reload IMU_Net first");
+        h->tc_lo_drop = (int)value;
+        if (h->imu.tc_ready && value > h->tc_lo_drop_w) {
+            cudaSetDevice(h->device);
+            for (int l = 0; l < 2; ++l) {
+                tc_round_lo_weights(h->imu.tc_fast[l], h->tc_lo_drop, nullptr);
+                tc_round_lo_weights(h->imu.tc_slow[l], h->tc_lo_drop, nullptr);
+            }
+            if (cudaDeviceSynchronize() != cudaSuccess) return fail(h, MMEGO_ECUDA, "tc_lo_drop: rounding the weight planes failed");
+            h->tc_lo_drop_w = h->tc_lo_drop;
+        }
+#else
+        h->tc_lo_drop = (int)value;
+#endif
+        return MMEGO_OK;
+    }
+    if (!strcmp(key, "tc_pdl")) {
+        h->tc_pdl = value != 0;
+        return MMEGO_OK;
+    }
     if (!strcmp(key, "tc_kb_chunk0")) {
         if (value < 0 || value > 64) return fail(h, MMEGO_EINVAL, "tc_kb_chunk0 must be in 0..64");
         h->tc_kb_chunk0 = (int)value;
@@ -634,6 +659,15 @@ int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const 
                     t = t && tc_pack_layer(h, sd, "rnn_slow.", l, 2 * H, W.tc_slow[l]);
                 }
                 W.tc_ready = t;
+                h->tc_lo_drop_w = 0;
+                if (t && h->tc_lo_drop > 0) {
+                    for (int l = 0; l < 2; ++l) {
+                        tc_round_lo_weights(W.tc_fast[l], h->tc_lo_drop, nullptr);
+                        tc_round_lo_weights(W.tc_slow[l], h->tc_lo_drop, nullptr);
+                    }
+                    if (cudaDeviceSynchronize() != cudaSuccess) return fail(h, MMEGO_ECUDA, "set_weights: rounding the weight planes failed");
+                    h->tc_lo_drop_w = h->tc_lo_drop;
+                }
             }
             if (h->imu_gemm != 0 && !W.tc_ready) return fail(h, MMEGO_ESTATE, "set_weights: tensor-core packing of IMU_Net failed");
 #endif

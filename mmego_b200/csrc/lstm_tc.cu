@@ -55,6 +55,14 @@ constexpr uint32_t kTmemCols = 512;
 // while the lo part (residual, ~2^-12 of the value) stays a NORMAL fp16 for |value| >= 1e-3 -- unscaled, the residual of
 // a typical h ~ 0.05 would be a denormal and lose most of its 11 bits.
 constexpr float kActScale = 256.0f, kActInv = 1.0f / 256.0f;
+// Residual ("lo") planes need far fewer than fp16's 11 significant bits: with d low mantissa bits rounded away a value
+// keeps 11 + (11 - d) bits.  The tensor core's power draw depends on the operand bits (scripts/ubench/tcgen05_rate.cu:
+// +5.6 % / +10.7 % MMA rate under the power cap with 5 / 8 low mantissa bits of ONE operand cleared), and the kernel is
+// power-limited, so shorter residuals are faster.  Two fp16 per 32-bit word: add half an ulp of the kept precision, mask.
+// (A carry out of the mantissa rounds up into the exponent, which is the correct result; residuals are never near inf.)
+__host__ __device__ inline uint32_t lo_round_add(int drop) { return drop > 0 ? 0x00010001u << (drop - 1) : 0u; }
+__host__ __device__ inline uint32_t lo_round_mask(int drop) { return ~(((1u << drop) - 1u) * 0x00010001u); }
+__device__ __forceinline__ uint32_t lo_round(uint32_t w, uint32_t add, uint32_t mask) { return (w + add) & mask; }
 
 // NCTA = 2: a CTA pair (cta_group::2) shares one 256 x 256 accumulator tile pair: each CTA stages its own 128 sequences
 // of A and HALF of the weight tile, so a stage is 64 KB instead of 96 KB (3-deep ring instead of 2) and the weight bytes
@@ -89,6 +97,8 @@ struct StepParams {
     unsigned long long* stats;   // dbg & 4, MMA thread: [3] work items, [4] cycles waiting for the epilogue, [5] waiting for TMA,
                          // [6] total cycles
     int dbg;             // experiment switches (results are wrong when set): 1 = skip the cell math and stores, 2 = skip the TMEM drains
+    int pdl;             // launched with programmatic stream serialization: wait for the previous grid after the prologue
+    uint32_t lo_add, lo_mask;   // rounding of the residual plane to fewer mantissa bits (two fp16 per word), see lo_round()
 };
 
 // Gate non-linearities straight on the SFU instructions (MUFU.EX2 / MUFU.RCP, one instruction each; the CUDA
@@ -197,6 +207,13 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
     if (NCTA == 2) cluster_sync_all();      // the peer's barriers must be initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    if (p.pdl) {
+        // Programmatic dependent launch: everything above (barriers, TMEM, bias -- weights only) ran while the previous
+        // timestep's last CTAs were still finishing; h_{t-1} and the cell state are read only after that grid has
+        // completed and flushed.  The next step may start ITS prologue as soon as this grid's CTAs leave their SMs.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
 
     // register re-balancing: the control warpgroup keeps 32 registers per thread (the CTA pool must balance: 128 x (96-32) = 512 x (112-96)), the 16 epilogue warps (64 fp32
     // accumulators per thread) grow to 112
@@ -401,7 +418,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
                     const float2 back = __half22float2(hh2);
                     const __half2 ll2 = __floats2half2_rn(hv2[0] - back.x, hv2[1] - back.y);
                     ph[j2] = *reinterpret_cast<const uint32_t*>(&hh2);
-                    pl[j2] = *reinterpret_cast<const uint32_t*>(&ll2);
+                    pl[j2] = lo_round(*reinterpret_cast<const uint32_t*>(&ll2), p.lo_add, p.lo_mask);
                 }
                 if (ok) {
                     *reinterpret_cast<uint4*>(p.out_hi + o + half * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -437,7 +454,7 @@ __device__ __forceinline__ void store_split(__half* hi, __half* lo, long long i,
 constexpr int FC1_WORDS = mma_frag_words(1, 64);
 __global__ void __launch_bounds__(256) imu_fc1_mma_kernel(const float* __restrict__ imu, const float* __restrict__ blob,
                                                           __half* __restrict__ uhi, __half* __restrict__ ulo,
-                                                          long long rows) {
+                                                          long long rows, uint32_t lo_add, uint32_t lo_mask) {
     extern __shared__ __align__(16) uint32_t fsm[];    // frags [64][32] uint4 | bias [512]
     for (int i = threadIdx.x * 4; i < FC1_WORDS + kImuH; i += 256 * 4)
         *reinterpret_cast<uint4*>(fsm + i) = *reinterpret_cast<const uint4*>(blob + i);
@@ -472,6 +489,8 @@ __global__ void __launch_bounds__(256) imu_fc1_mma_kernel(const float* __restric
             for (int j = 0; j < 4; ++j) {
                 frag::split2(fminf(out[j][0] * kActScale, 65000.f), fminf(out[j][1] * kActScale, 65000.f), h0[j], l0[j]);
                 frag::split2(fminf(out[j][2] * kActScale, 65000.f), fminf(out[j][3] * kActScale, 65000.f), h1[j], l1[j]);
+                l0[j] = lo_round(l0[j], lo_add, lo_mask);
+                l1[j] = lo_round(l1[j], lo_add, lo_mask);
             }
             const long long ca = ra * kImuH + 32 * q + 8 * tq, cb = rb * kImuH + 32 * q + 8 * tq;
             if (la) {
@@ -547,7 +566,7 @@ __global__ void __launch_bounds__(POOL_WARPS * 32) imu_pool_split_kernel(const _
                                                                         const __half* __restrict__ ylo,
                                                                         const float* __restrict__ attn,
                                                                         __half* __restrict__ shi, __half* __restrict__ slo,
-                                                                        long long F, int n) {
+                                                                        long long F, int n, uint32_t lo_add, uint32_t lo_mask) {
     const int lane = threadIdx.x & 31;
     const long long f = (long long)blockIdx.x * POOL_WARPS + (threadIdx.x >> 5);
     if (f >= F) return;
@@ -596,7 +615,12 @@ __global__ void __launch_bounds__(POOL_WARPS * 32) imu_pool_split_kernel(const _
         }
         const long long o = f * 1024 + i * 256 + lane * 8;
         *reinterpret_cast<uint4*>(shi + o) = *reinterpret_cast<const uint4*>(hi);
-        if (slo) *reinterpret_cast<uint4*>(slo + o) = *reinterpret_cast<const uint4*>(lo);
+        if (slo) {
+            uint4 lw = *reinterpret_cast<const uint4*>(lo);
+            lw.x = lo_round(lw.x, lo_add, lo_mask); lw.y = lo_round(lw.y, lo_add, lo_mask);
+            lw.z = lo_round(lw.z, lo_add, lo_mask); lw.w = lo_round(lw.w, lo_add, lo_mask);
+            *reinterpret_cast<uint4*>(slo + o) = lw;
+        }
     }
 }
 
@@ -626,44 +650,62 @@ __global__ void __launch_bounds__(256) imu_decode_split_kernel(const __half* __r
     if (threadIdx.x < 9) sw[9 * 1024 + threadIdx.x] = fc2[9 * 1024 + threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    for (long long f = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); f < F; f += (long long)gridDim.x * 8) {
-        float x[32];
+    // two frames per warp and iteration: every 16-byte weight read from shared memory feeds both (the kernel was bound by
+    // shared-memory bandwidth: 36 KB of weights per 4 KB frame)
+    for (long long f0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 2; f0 < F; f0 += (long long)gridDim.x * 16) {
+        const int nf = f0 + 1 < F ? 2 : 1;
+        float x[2][32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint2 a = *reinterpret_cast<const uint2*>(ghi + f * 1024 + i * 128 + lane * 4);
-            float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
-            float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
-            if (glo) {
-                const uint2 b = *reinterpret_cast<const uint2*>(glo + f * 1024 + i * 128 + lane * 4);
-                const float2 q0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x));
-                const float2 q1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
-                p0.x += q0.x; p0.y += q0.y; p1.x += q1.x; p1.y += q1.y;
+        for (int e = 0; e < 2; ++e) {
+            const long long f = e < nf ? f0 + e : f0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint2 a = *reinterpret_cast<const uint2*>(ghi + f * 1024 + i * 128 + lane * 4);
+                float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
+                float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+                if (glo) {
+                    const uint2 b = *reinterpret_cast<const uint2*>(glo + f * 1024 + i * 128 + lane * 4);
+                    const float2 q0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x));
+                    const float2 q1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
+                    p0.x += q0.x; p0.y += q0.y; p1.x += q1.x; p1.y += q1.y;
+                }
+                x[e][i * 4] = p0.x * kActInv; x[e][i * 4 + 1] = p0.y * kActInv;
+                x[e][i * 4 + 2] = p1.x * kActInv; x[e][i * 4 + 3] = p1.y * kActInv;
             }
-            x[i * 4] = p0.x * kActInv; x[i * 4 + 1] = p0.y * kActInv;
-            x[i * 4 + 2] = p1.x * kActInv; x[i * 4 + 3] = p1.y * kActInv;
         }
-        float T9[9];
+        float T9[2][9];
 #pragma unroll
         for (int o = 0; o < 9; ++o) {
-            float a = 0.f;
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 wv = *reinterpret_cast<const float4*>(sw + o * 1024 + i * 128 + lane * 4);
-                a = fmaf(wv.x, x[i * 4], a);
-                a = fmaf(wv.y, x[i * 4 + 1], a);
-                a = fmaf(wv.z, x[i * 4 + 2], a);
-                a = fmaf(wv.w, x[i * 4 + 3], a);
+                a0 = fmaf(wv.x, x[0][i * 4], a0);
+                a0 = fmaf(wv.y, x[0][i * 4 + 1], a0);
+                a0 = fmaf(wv.z, x[0][i * 4 + 2], a0);
+                a0 = fmaf(wv.w, x[0][i * 4 + 3], a0);
+                a1 = fmaf(wv.x, x[1][i * 4], a1);
+                a1 = fmaf(wv.y, x[1][i * 4 + 1], a1);
+                a1 = fmaf(wv.z, x[1][i * 4 + 2], a1);
+                a1 = fmaf(wv.w, x[1][i * 4 + 3], a1);
             }
 #pragma unroll
-            for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
-            T9[o] = a + sw[9 * 1024 + o];
+            for (int sft = 16; sft > 0; sft >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, sft);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
+            }
+            T9[0][o] = a0 + sw[9 * 1024 + o];
+            T9[1][o] = a1 + sw[9 * 1024 + o];
         }
-        if (lane == 0) {
-            float mm[9];
-            ortho6d_cols(T9, 1e-8f, mm);
+        if (lane < nf) {
+            const long long f = f0 + lane;
+            float tt[9], mm[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) tt[k] = lane == 0 ? T9[0][k] : T9[1][k];
+            ortho6d_cols(tt, 1e-8f, mm);
 #pragma unroll
             for (int k = 0; k < 9; ++k) R[f * 9 + k] = mm[k];
-            t[f * 3] = T9[6]; t[f * 3 + 1] = T9[7]; t[f * 3 + 2] = T9[8];
+            t[f * 3] = tt[6]; t[f * 3 + 1] = tt[7]; t[f * 3 + 2] = tt[8];
         }
     }
 }
@@ -673,6 +715,12 @@ __global__ void unsplit_kernel(const __half* __restrict__ hi, const __half* __re
                                long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (__half2float(hi[i]) + (lo ? __half2float(lo[i]) : 0.f)) * kActInv;
+}
+
+// rounds a packed residual plane (weights) in place, see lo_round()
+__global__ void lo_round_kernel(uint32_t* __restrict__ w, long long nwords, uint32_t add, uint32_t mask) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nwords) w[i] = lo_round(w[i], add, mask);
 }
 
 // ---------------------------------------------------------------------------------------------- tensor maps
@@ -793,13 +841,15 @@ void launch_step(int grid, cudaStream_t st, const CUtensorMap& mXhi, const CUten
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = Cfg<NPASS, NCTA, BN>::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = NCTA;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = p.pdl ? 2 : 1;
     cudaLaunchKernelEx(&cfg, lstm_tc_step_kernel<NPASS, NCTA, BN>, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
 }
 
@@ -834,6 +884,9 @@ int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const
     p.out_scale = lw.out_scale;
     const int chunk_opt = h->tc_kb_chunk;
     p.dbg = h->tc_dbg;
+    p.pdl = h->tc_pdl;
+    p.lo_add = lo_round_add(h->tc_lo_drop);
+    p.lo_mask = lo_round_mask(h->tc_lo_drop);
     if ((p.dbg & 4) && !h->tc_stats) {
         cudaMalloc(&h->tc_stats, 8 * sizeof(unsigned long long));
         cudaMemset(h->tc_stats, 0, 8 * sizeof(unsigned long long));
@@ -860,7 +913,14 @@ int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const
     return 0;
 }
 
-void tc_imu_fc1(const float* imu, const float* fc1_mma, void* uhi, void* ulo, long long rows, int sm_count,
+void tc_round_lo_weights(const TcLstmLayer& lw, int drop, cudaStream_t st) {
+    const long long nwords = (long long)2 * 4 * kImuH * lw.K / 2;
+    if (drop <= 0 || !lw.v[0].wlo) return;
+    lo_round_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(static_cast<uint32_t*>(lw.v[0].wlo), nwords,
+                                                                      lo_round_add(drop), lo_round_mask(drop));
+}
+
+void tc_imu_fc1(const float* imu, const float* fc1_mma, void* uhi, void* ulo, long long rows, int sm_count, int lo_drop,
                 cudaStream_t st) {
     if (rows <= 0) return;
     const int smem = (FC1_WORDS + kImuH) * 4;
@@ -871,15 +931,16 @@ void tc_imu_fc1(const float* imu, const float* fc1_mma, void* uhi, void* ulo, lo
     if (blocks > 4LL * sm_count) blocks = 4LL * sm_count;
     ++g_launches;
     imu_fc1_mma_kernel<<<(unsigned)blocks, 256, smem, st>>>(imu, fc1_mma, static_cast<__half*>(uhi),
-                                                            static_cast<__half*>(ulo), rows);
+                                                            static_cast<__half*>(ulo), rows, lo_round_add(lo_drop),
+                                                            lo_round_mask(lo_drop));
 }
 void tc_imu_pool(const void* yhi, const void* ylo, const float* attn, void* shi, void* slo, long long F, int n,
-                 cudaStream_t st) {
+                 int lo_drop, cudaStream_t st) {
     if (F <= 0) return;
     ++g_launches;
     imu_pool_split_kernel<<<(unsigned)((F + POOL_WARPS - 1) / POOL_WARPS), POOL_WARPS * 32, 0, st>>>(
         static_cast<const __half*>(yhi), static_cast<const __half*>(ylo), attn, static_cast<__half*>(shi),
-        static_cast<__half*>(slo), F, n);
+        static_cast<__half*>(slo), F, n, lo_round_add(lo_drop), lo_round_mask(lo_drop));
 }
 void tc_imu_decode(const void* ghi, const void* glo, const float* fc2, float* R, float* t, long long F, cudaStream_t st) {
     if (F <= 0) return;
@@ -890,7 +951,7 @@ void tc_imu_decode(const void* ghi, const void* glo, const float* fc2, float* R,
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long blocks = (F + 7) / 8;
+    long long blocks = (F + 15) / 16;
     if (blocks > 2LL * sms) blocks = 2LL * sms;
     ++g_launches;
     imu_decode_split_kernel<<<(unsigned)blocks, 256, smem, st>>>(static_cast<const __half*>(ghi),
