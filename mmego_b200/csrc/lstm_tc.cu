@@ -146,7 +146,7 @@ __device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po
     }
 }
 
-template <int NPASS, int NCTA, int BN>
+template <int NPASS, int NCTA, int BN, bool MUFU_CELL = (NPASS == 1)>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtensorMap mXlo,
                     const __grid_constant__ CUtensorMap mYhi, const __grid_constant__ CUtensorMap mYlo,
@@ -410,7 +410,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
                         const float pg = fmaf(acc[2][j], p.out_scale, bias[2 * kUnitsPerTile + j]);
                         const float po = fmaf(acc[3][j], p.out_scale, bias[3 * kUnitsPerTile + j]);
                         float cn, hh;
-                        lstm_cell<NPASS == 1>(pi, pf, pg, po, cprev[2 * j2 + e], cn, hh);
+                        lstm_cell<MUFU_CELL>(pi, pf, pg, po, cprev[2 * j2 + e], cn, hh);
                         hv2[e] = hh * kActScale;
                         if (ok) __stcs(cbase + (long long)j * p.Spad, cn);
                     }
@@ -829,12 +829,12 @@ bool tc_pack_layer(mmego_handle* h, const StateDict& sd, const std::string& pref
     return pack_variant(h, sd, prefix, layer, In, 64, out.v[0], &out.out_scale);
 }
 
-template <int NPASS, int NCTA, int BN>
+template <int NPASS, int NCTA, int BN, bool MUFU_CELL = (NPASS == 1)>
 void launch_step(int grid, cudaStream_t st, const CUtensorMap& mXhi, const CUtensorMap& mXlo, const CUtensorMap& mYhi,
                  const CUtensorMap& mYlo, const CUtensorMap& mWhi, const CUtensorMap& mWlo, const StepParams& p) {
     static bool attr_set[64] = {false};
     if (first_use_on_device(attr_set))
-        cudaFuncSetAttribute(lstm_tc_step_kernel<NPASS, NCTA, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(lstm_tc_step_kernel<NPASS, NCTA, BN, MUFU_CELL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg<NPASS, NCTA, BN>::SMEM_BYTES);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -850,7 +850,7 @@ void launch_step(int grid, cudaStream_t st, const CUtensorMap& mXhi, const CUten
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = p.pdl ? 2 : 1;
-    cudaLaunchKernelEx(&cfg, lstm_tc_step_kernel<NPASS, NCTA, BN>, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
+    cudaLaunchKernelEx(&cfg, lstm_tc_step_kernel<NPASS, NCTA, BN, MUFU_CELL>, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
 }
 
 // One bidirectional layer: x planes [S][T][In] -> y planes [S][T][1024]; cstate [2][512][Spad] fp32 scratch.
