@@ -69,7 +69,14 @@ const char* mmego_last_error(const mmego_handle* h);
  *                         first stage is an eighth of that so the un-overlappable first copy stays short),
  *          "tc_kb_chunk" (imu_gemm=1: K blocks of 64 accumulated in TMEM before draining into fp32 registers, default 4;
  *                         8 is ~10 % faster and ~1.5x noisier),
- *          "tc_cta_pair" (H=512 LSTM kernel on CTA pairs, cta_group::2 M=256 tiles, default 1). */
+ *          "tc_cta_pair" (H=512 LSTM kernel on CTA pairs, cta_group::2 M=256 tiles, default 1),
+ *          "tc_pdl"      (H=512 LSTM timestep launches use programmatic dependent launch: the prologue of step t+1
+ *                         overlaps the tail of step t, default 1),
+ *          "tc_lo_drop"  (imu_gemm=1: low mantissa bits rounded away in the residual (lo) fp16 planes of the H=512 LSTM
+ *                         operands, 0..6, default 4 = 7 significant bits kept: the tensor core draws less power on
+ *                         shorter operands and the kernel is power-limited; results are unchanged within the fp32-grade
+ *                         tolerance up to 4.  The packed weight planes are rounded in place, so once IMU_Net is loaded
+ *                         the value can only grow until the weights are loaded again). */
 int mmego_set_option(mmego_handle* h, const char* key, long long value);
 
 /* Replaces IMUNet.load / UpperNet.load / LowerNet.load (Net/IMU_Net.py:106-114, Net/Upper_Net.py:400-404,

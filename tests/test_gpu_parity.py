@@ -297,3 +297,32 @@ def test_full_size_properties_b4096(handle):
     err = P.maxerr(p3, p1)
     print(f"B=4096: mma.sync vs FFMA point/LSTM kernels max |d pred| = {err:.2e} m")
     assert err < P.POS_TOL
+
+
+def test_lstm_residual_rounding_and_pdl_options():
+    """tc_lo_drop (residual planes rounded to fewer mantissa bits, default 4) and tc_pdl (programmatic dependent launch,
+    default 1): every setting up to the default stays inside the fp32-grade tolerance against the reference's golden
+    vectors, PDL on/off is bit-identical, and the one-way rule of the in-place weight rounding is enforced."""
+    results = {}
+    for drop in (0, 4):
+        h = _capi.Handle()
+        h.set_option("tc_lo_drop", drop)
+        h.set_weights(_capi.NET_IMU, P.O.synth_imu_state_dict(0))
+        er, et = P.check_imu_golden(h, "synth")
+        g = P.golden("imu_seed0.npz")
+        R1, t1 = h.imu_forward(P.dev(h, g["imu_real"][:1]))
+        h.set_option("tc_pdl", 0)
+        R0, t0 = h.imu_forward(P.dev(h, g["imu_real"][:1]))
+        h.set_option("tc_pdl", 1)
+        assert torch.equal(R0, R1) and torch.equal(t0, t1)
+        results[drop] = (er, et, R1.clone())
+        print(f"tc_lo_drop={drop}: golden max err R {er:.2e} t {et:.2e}")
+        if drop == 4:
+            with pytest.raises(_capi.MMEgoError, match="already rounded"):
+                h.set_option("tc_lo_drop", 2)
+            with pytest.raises(_capi.MMEgoError):
+                h.set_option("tc_lo_drop", 7)
+            h.set_option("tc_lo_drop", 5)           # growing is allowed (weights re-rounded in place)
+        h.close()
+    assert not torch.equal(results[0][2], results[4][2])      # the option really changes the operands
+    assert float((results[0][2] - results[4][2]).abs().max()) < 2e-5
