@@ -322,7 +322,7 @@ def main():
             fl_fast += N_IMU * (lstm_step_flops(bc * L, H) + lstm_step_flops(bc * L, 2 * H))
         peak = peaks["bf16_sustained"]
         # DRAM bytes of one rnn_fast layer-1 step launch at M = 40,960 from `ncu --set full` (profiles/r01final_ncu_summary.txt)
-        NCU_TRAFFIC = {1: 1.463e9, 2: None, 0: None}
+        NCU_TRAFFIC = {1: 1.245e9, 2: None, 0: None}     # profiles/r01lo4_ncu_summary.txt (was 1.463e9 in r01final)
 
         def lstm_roofline(prof_, ms_, steps_, mode_):
             lst = prof_.get("imu.lstm_fast", dict(ms=0.0, launches=0))
