@@ -112,7 +112,8 @@ def test_pipeline_larger_batch_multi_tile(handle):
     print(errs)
 
 
-@pytest.mark.parametrize("B,L,N,n", [(3, 5, 70, 3), (1, 1, 64, 1), (2, 40, 256, 20), (5, 20, 512, 7)])
+@pytest.mark.parametrize("B,L,N,n", [(3, 5, 70, 3), (1, 1, 64, 1), (2, 40, 256, 20), (5, 20, 512, 7), (9, 7, 64, 40),
+                                     (130, 3, 96, 2), (2, 80, 128, 5)])
 def test_pipeline_ragged_and_sweep_shapes(handle, B, L, N, n):
     """Shapes away from Config/config.py (ragged tiles; N, L up to 4x).  With few IMU samples per frame (n = 1..7) the
     stand-in IMU_Net's 6D vectors shrink to norm ~0.02, so the Gram-Schmidt step amplifies fp32-level noise ~50x: the
