@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(NT) lower_frame_kernel(float* __restrict__ x, 
             xf[p * 6 + 2] = nz;
             float* pp = s.pts + p * 6;
             pp[0] = nx; pp[1] = ny; pp[2] = nz; pp[3] = v1.y; pp[4] = v2.x; pp[5] = v2.y;
-            s.key[p] = nx;
+            s.key[p] = nx == nx ? nx : INFINITY;     // NaN sorts first, as in torch.sort(descending): keeps the ranks a permutation
         }
         __syncthreads();
         for (int p = tid; p < N; p += NT) {
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(NT, 4) lower_frame_mma_kernel(float* __restric
                 *reinterpret_cast<float2*>(pp) = make_float2(nx, ny);
                 *reinterpret_cast<float2*>(pp + 2) = make_float2(nz, v1.y);
                 *reinterpret_cast<float2*>(pp + 4) = v2;
-                s.key[p] = nx;
+                s.key[p] = nx == nx ? nx : INFINITY;     // NaN sorts first, as in torch.sort(descending): keeps the ranks a permutation
             }
         }
         __syncthreads();

@@ -259,3 +259,31 @@ def check_snippet_builder(h):
             assert all(k in key_src for k in key_live)
             if n <= 128:
                 assert key_live == key_src
+
+
+def check_nan_inputs_do_not_corrupt(h):
+    """A NaN in one snippet's radar cloud / head pose must stay inside that snippet: the top-64 select indexes shared
+    memory with data-derived ranks, so its keys have to remain totally ordered (NaN first, as torch.sort(descending=True)
+    does at Net/Lower_Net.py:218) -- otherwise ranks collide, slots of the selection stay unwritten and the gather
+    reads through stale indices."""
+    g = golden("synth3.npz")
+    skl, R, t = dev(h, g["skl"]), dev(h, g["R"]).clone(), dev(h, g["t"]).clone()
+    h0 = torch.zeros(6, 3, 64, device=h.device)
+
+    def run(data, R_, t_):
+        x = dev(h, data.clone())
+        l = h.upper_forward(x, h0, h0.clone(), skl, R_, t_)[0]
+        return l, h.lower_forward(l, x, skl, R_, t_)[0]
+
+    l_ref, ll_ref = run(g["data"], R, t)
+    bad = g["data"].clone()
+    bad[1, 3, 5, 0] = float("nan")            # one point of snippet 1, frame 3
+    bad[1, 4, :, :3] = float("nan")           # every point of frame 4
+    Rb = R.clone()
+    Rb[1, 6] = float("nan")                   # NaN head pose for frame 6: every key of that frame is NaN
+    l_bad, ll_bad = run(bad, Rb, t)
+    for b in (0, 2):                          # the other snippets are untouched, bit for bit
+        assert torch.equal(l_bad[b], l_ref[b]) and torch.equal(ll_bad[b], ll_ref[b])
+    assert torch.isnan(ll_bad[1]).any()
+    l_again, ll_again = run(g["data"], R, t)  # and the handle still works
+    assert torch.equal(ll_again, ll_ref) and torch.equal(l_again, l_ref)

@@ -40,6 +40,10 @@ def test_gcn(handle):
     P.check_gcn_golden(handle)
 
 
+def test_nan_inputs_stay_in_their_snippet(handle):
+    P.check_nan_inputs_do_not_corrupt(handle)
+
+
 def test_transforms(handle):
     P.check_transforms(handle)
 

@@ -127,6 +127,10 @@ def test_errors(handle):
     P.check_errors(handle)
 
 
+def test_nan_inputs_stay_in_their_snippet(handle):
+    P.check_nan_inputs_do_not_corrupt(handle)
+
+
 def test_imu_chunking_is_invisible(handle):
     """IMU_Net processes snippets in workspace chunks; results must not depend on the chunk size."""
     from oracle import mmego_oracle as O
