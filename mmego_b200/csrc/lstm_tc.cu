@@ -452,7 +452,7 @@ __device__ __forceinline__ void store_split(__half* hi, __half* lo, long long i,
 // for the split/pack/store epilogue: a warp owns 16 rows, one k-step, 64 n-tiles; the column permutation of
 // pack_imu_fc1_mma gives every lane 8 consecutive channels per row = one 16-byte store per plane.
 constexpr int FC1_WORDS = mma_frag_words(1, 64);
-__global__ void __launch_bounds__(256) imu_fc1_mma_kernel(const float* __restrict__ imu, const float* __restrict__ blob,
+__global__ void __launch_bounds__(256, 4) imu_fc1_mma_kernel(const float* __restrict__ imu, const float* __restrict__ blob,
                                                           __half* __restrict__ uhi, __half* __restrict__ ulo,
                                                           long long rows, uint32_t lo_add, uint32_t lo_mask) {
     extern __shared__ __align__(16) uint32_t fsm[];    // frags [64][32] uint4 | bias [512]
@@ -463,23 +463,34 @@ __global__ void __launch_bounds__(256) imu_fc1_mma_kernel(const float* __restric
     const uint4* wf = reinterpret_cast<const uint4*>(fsm);
     const float* bias = reinterpret_cast<const float*>(fsm + FC1_WORDS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tq = lane & 3;
-    for (long long r0 = ((long long)blockIdx.x * 8 + warp) * 16; r0 < rows; r0 += (long long)gridDim.x * 128) {
+    // the 8 input values of a lane's fragment (rows g / g+8, channels 2tq, 2tq+1, 2tq+8, 2tq+9): the NEXT row tile's
+    // are fetched before the current tile's 16 channel groups are computed (the loads were the kernel's main stall)
+    auto load_in = [&](long long r0, float* v) {
         const long long ra = r0 + g, rb = r0 + g + 8;
         const bool la = ra < rows, lb = rb < rows;
         const float* pa = imu + ra * kImuFeat;
         const float* pb = imu + rb * kImuFeat;
+        const int c = 2 * tq;
+        v[0] = la ? pa[c] : 0.f; v[1] = la ? pa[c + 1] : 0.f;
+        v[2] = lb ? pb[c] : 0.f; v[3] = lb ? pb[c + 1] : 0.f;
+        v[4] = la ? pa[c + 8] : 0.f; v[5] = (la && c + 9 < kImuFeat) ? pa[c + 9] : 0.f;
+        v[6] = lb ? pb[c + 8] : 0.f; v[7] = (lb && c + 9 < kImuFeat) ? pb[c + 9] : 0.f;
+    };
+    const long long rstride = (long long)gridDim.x * 128;
+    float vin[8];
+    {
+        const long long rfirst = ((long long)blockIdx.x * 8 + warp) * 16;
+        if (rfirst < rows) load_in(rfirst, vin);
+    }
+    for (long long r0 = ((long long)blockIdx.x * 8 + warp) * 16; r0 < rows; r0 += rstride) {
+        const long long ra = r0 + g, rb = r0 + g + 8;
+        const bool la = ra < rows, lb = rb < rows;
         uint32_t ah[1][4], al[1][4];
-        {
-            const int c = 2 * tq;
-            const float a0 = la ? pa[c] : 0.f, a1 = la ? pa[c + 1] : 0.f;
-            const float b0 = lb ? pb[c] : 0.f, b1 = lb ? pb[c + 1] : 0.f;
-            const float a2 = la ? pa[c + 8] : 0.f, a3 = (la && c + 9 < kImuFeat) ? pa[c + 9] : 0.f;
-            const float b2 = lb ? pb[c + 8] : 0.f, b3 = (lb && c + 9 < kImuFeat) ? pb[c + 9] : 0.f;
-            frag::split2(a0, a1, ah[0][0], al[0][0]);
-            frag::split2(b0, b1, ah[0][1], al[0][1]);
-            frag::split2(a2, a3, ah[0][2], al[0][2]);
-            frag::split2(b2, b3, ah[0][3], al[0][3]);
-        }
+        frag::split2(vin[0], vin[1], ah[0][0], al[0][0]);
+        frag::split2(vin[2], vin[3], ah[0][1], al[0][1]);
+        frag::split2(vin[4], vin[5], ah[0][2], al[0][2]);
+        frag::split2(vin[6], vin[7], ah[0][3], al[0][3]);
+        if (r0 + rstride < rows) load_in(r0 + rstride, vin);
 #pragma unroll 2
         for (int q = 0; q < 16; ++q) {
             float out[4][4];
