@@ -62,6 +62,38 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic_from_profiles(kernel_substr="lstm_tc_step_kernel<3"):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel, read from the NEWEST
+    committed `ncu --set full` summary under profiles/ (scripts/ncu_summary.py output) that holds a capture of it; among
+    that file's launches the one with the most traffic is the rnn_fast layer-1 step (M = 40,960, K = 1536)."""
+    import glob
+    import re
+    best = None
+    for path in glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.txt")):
+        m = re.match(r"r(\d+)", os.path.basename(path))
+        rnd = int(m.group(1)) if m else 0
+        top, cur = None, None
+        for ln in open(path, errors="replace"):
+            if ln.startswith("Kernel Name"):
+                cur = {"hit": kernel_substr in ln, "rd": None, "wr": None}
+            elif cur is not None and cur["hit"]:
+                f = ln.split()
+                if ln.startswith("dram__bytes_read.sum ") or ln.startswith("dram__bytes_write.sum "):
+                    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(f[-1], None)
+                    if mult is not None:
+                        cur["rd" if "read" in f[0] else "wr"] = float(f[1].replace(",", "")) * mult
+                    if cur["rd"] is not None and cur["wr"] is not None:
+                        tot = cur["rd"] + cur["wr"]
+                        if top is None or tot > top:
+                            top = tot
+                        cur = None
+        if top is not None:
+            key = (rnd, os.path.getmtime(path), os.path.basename(path))
+            if best is None or key > best[0]:
+                best = (key, top, os.path.relpath(path, ROOT))
+    return (best[1], best[2]) if best else (None, None)
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -107,51 +139,182 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_pass(snippets: int, steps: int, warmup: int):
-    """The reference's algorithm on the host cores: the oracle port (oracle/mmego_oracle.py; the reference is pure
-    PyTorch-on-CPU and its repository does not travel to the GPU box), all threads, fp32."""
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def cpu_model_name():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def load_checkpoints():
     import torch
-    from oracle import mmego_oracle as O
+    base = os.path.join(ROOT, "Resource", "Pretrained_model")
+    up = torch.load(os.path.join(base, "Upper_Net", "epoch451_batch20frame20lr3e-05.pth"), map_location="cpu", weights_only=True)
+    lo = torch.load(os.path.join(base, "Lower_Net", "epoch161_batch20frame20lr0.0003.pth"), map_location="cpu", weights_only=True)
+    return up, lo
+
+
+class ReferenceChain:
+    """The reference's OWN nn.Module classes (vendored, unmodified, into the git-ignored baseline/_ref/ by
+    scripts/vendor_reference.py), chained as Processor/Test/Demo_test.py:106-123 on the host cores."""
+    kind = "reference"
+
+    def __init__(self):
+        import types
+        import torch
+        for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.animation", "seaborn", "imageio",
+                     "imageio.v2", "mpl_toolkits", "mpl_toolkits.mplot3d"):
+            sys.modules.setdefault(name, types.ModuleType(name))       # plotting imports of Utils.py; absent in this image
+        sys.path.insert(0, REF_DIR)
+        from Net.IMU_Net import IMUNet          # noqa: E402  (baseline/_ref)
+        from Net.Lower_Net import LowerNet      # noqa: E402
+        from Net.Upper_Net import UpperNet      # noqa: E402
+        from Config.config import Config        # noqa: E402
+        from mmego_b200 import synth
+        self.torch, self.Config = torch, Config
+        up_sd, lo_sd = load_checkpoints()
+        self.imu = IMUNet(15, 9, 512, 2, True, 0.1)                     # Demo_test.py:54
+        self.imu.load_state_dict(synth.imu_state_dict(0))               # the checkpoint blob is missing upstream
+        self.upper, self.lower = UpperNet(), LowerNet(64)
+        self.upper.load_state_dict(up_sd)
+        self.lower.load_state_dict(lo_sd)
+        for m in (self.imu, self.upper, self.lower):
+            m.eval()
+
+    def __call__(self, imu, data, skl):
+        torch, Config = self.torch, self.Config
+        B, L = data.shape[:2]
+        data = data.clone()                                             # the nets transform the cloud in place
+        h0 = torch.zeros((6, B, 64), dtype=torch.float32)
+        c0 = torch.zeros((6, B, 64), dtype=torch.float32)
+        R_p, t_p = self.imu(imu)                                        # Demo_test.py:111
+        R, t = R_p.clone().detach(), t_p.clone().detach()
+        upper, _, _, _, _ = self.upper(data, h0, c0, skl, R, t)         # :114
+        upper_l = upper.clone().detach()
+        lower_l, _ = self.lower(upper_l, data, h0, c0, h0, c0, skl, R, t)   # :118
+        pred = torch.zeros((B, L, 21, 3), dtype=torch.float32)
+        pred[:, :, Config.upper_joint_map, :] = upper_l                 # :121-123
+        pred[:, :, Config.lower_joint_map, :] = lower_l
+        return pred
+
+
+class PortChain:
+    """Fallback when baseline/_ref/ is absent: the oracle port of the same chain (oracle/mmego_oracle.py)."""
+    kind = "port"
+
+    def __init__(self):
+        from mmego_b200 import synth
+        from oracle import mmego_oracle as O
+        self.O, self.imu_sd = O, synth.imu_state_dict(0)
+        self.up, self.lo = load_checkpoints()
+
+    def __call__(self, imu, data, skl):
+        return self.O.pipeline(self.imu_sd, self.up, self.lo, imu, data, skl)["pred"]
+
+
+def make_cpu_chain():
+    if os.path.isdir(os.path.join(REF_DIR, "Net")):
+        return ReferenceChain()
+    return PortChain()
+
+
+def cpu_reference_pass(snippets: int, steps: int, warmup: int, batch1_snippets: int = 0):
+    """Times the reference's CPU path on a bounded sample of the synthetic workload: `snippets` per step in ONE batched call
+    (B = 128 is the best CPU throughput observed), and optionally `batch1_snippets` snippets one at a time
+    (B = 1, the reference's own DataLoader setting, Processor/Test/Demo_test.py:61).  All host threads, fp32, no_grad."""
+    import torch
+    from mmego_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sb = O.synth_batch(snippets, seed=1234)
-    up = torch.load(os.path.join(ROOT, "Resource/Pretrained_model/Upper_Net/epoch451_batch20frame20lr3e-05.pth"),
-                    map_location="cpu", weights_only=True)
-    lo = torch.load(os.path.join(ROOT, "Resource/Pretrained_model/Lower_Net/epoch161_batch20frame20lr0.0003.pth"),
-                    map_location="cpu", weights_only=True)
-    imu_sd = O.synth_imu_state_dict(0)
+    chain = make_cpu_chain()
+    sb = synth.batch(snippets, seed=1234)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.pipeline(imu_sd, up, lo, sb["imu"], sb["data"], sb["skl"])
+            chain(sb["imu"], sb["data"], sb["skl"])
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
+        b1 = None
+        if batch1_snippets > 0:
+            chain(sb["imu"][:1], sb["data"][:1], sb["skl"][:1])
+            t0 = time.perf_counter()
+            for j in range(batch1_snippets):
+                chain(sb["imu"][j:j + 1], sb["data"][j:j + 1], sb["skl"][j:j + 1])
+            dt1 = (time.perf_counter() - t0) / batch1_snippets
+            b1 = {"value": L / dt1, "unit": UNIT, "ms_per_snippet": dt1 * 1e3, "snippets": batch1_snippets,
+                  "what": "batch = 1 snippet per call (the reference's own setting, Demo_test.py:61)"}
     dt = sum(times) / len(times)
-    return snippets * L / dt, dt, cores
+    return dict(fps=snippets * L / dt, dt=dt, best_fps=snippets * L / min(times), cores=cores, kind=chain.kind, batch1=b1,
+                cpu=cpu_model_name())
+
+
+def cpu_sample_text(r, snippets, steps, warmup):
+    what = ("the reference's own IMUNet/UpperNet/LowerNet classes (baseline/_ref, unmodified) chained as Demo_test.py:111-123"
+            if r["kind"] == "reference" else "oracle port of the reference's PyTorch-CPU path (baseline/_ref absent)")
+    return (f"{snippets} snippets ({snippets * L} frames) of the same synthetic workload per step in one batched call, "
+            f"{warmup} warm-up + {steps} timed steps; {what}; PyTorch CPU fp32, torch threads = {r['cores']} ({r['cpu']})")
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""          # the reference's Config picks cuda:0 when it sees one; this arm is the CPU path
     snippets = args.cpu_snippets
-    fps, dt, cores = cpu_reference_pass(snippets, max(1, min(args.steps, 3)), 1)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    r = cpu_reference_pass(snippets, steps, warmup, batch1_snippets=16)
+    fps = r["fps"]
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": r["dt"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"full pipeline, B={args.batch}, L={L}, N={N_PTS}, n_imu={N_IMU} (config 3 of BASELINE.json)",
-                   "note": "each step is a bounded sample of that workload"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{snippets} snippets ({snippets * L} frames) of the same synthetic workload per step, "
-                                   "oracle port of the reference's PyTorch-CPU path, fp32, torch threads = all cores"},
+                   "note": f"each step is a bounded sample of that workload: {snippets} snippets in one batched CPU call"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                         "sample": cpu_sample_text(r, snippets, steps, warmup), "best_step_value": r["best_fps"],
+                         "batch1": r["batch1"]},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+SURROGATE_PIN_CM = 2.660650576      # reference classes, 835 sample snippets, IMU_Net's training targets as (R, t) (SURVEY 8c)
+
+
+def config1_record(dev):
+    """Config 1 of BASELINE.json (the 835 real sample snippets through the drop-in `MMEgo().eval_model()`):
+    MPJPE with the surrogate head pose (the IMU_Net checkpoint is missing upstream; pin = the reference's own classes),
+    and the wall-clock it/s of the full chain INCLUDING IMU_Net at batch 167 and at the reference's batch 1."""
+    import numpy as np
+    import torch
+    from mmego_b200.Config.config import Config
+    from mmego_b200.Processor.Test.Demo_test import MMEgo
+    if not os.path.exists(Config.sample_frozen_path):
+        return None
+    m = MMEgo(batch_size=167, device=dev, imu_surrogate=True, quiet=True)
+    m.eval_model()
+    rec = {"workload": "835 sample snippets x 20 frames (Resource/Sample_data, frozen tensors), MMEgo().eval_model()",
+           "mpjpe_surrogate_cm": m.report["mpjpe_cm"], "mpjpe_surrogate_pin_cm": SURROGATE_PIN_CM,
+           "upper_cm": m.report["upper_cm"], "lower_cm": m.report["lower_cm"], "angle_deg": m.report["angle_deg"],
+           "pin_note": "IMU_Net's training targets as (R, t); README's 3.893 cm needs the missing IMU_Net checkpoint"}
+    for bs, key in ((167, "batch167"), (1, "batch1")):
+        mm = MMEgo(batch_size=bs, device=dev, imu_surrogate=False, quiet=True)
+        mm.eval_model()                      # warm-up (weight packing, allocator)
+        mm.eval_model()
+        n = int(mm.data.shape[0])
+        rec[key] = {"it_per_s": n / mm.seconds, "frames_per_s": n * 20 / mm.seconds, "ms_per_snippet": mm.seconds / n * 1e3,
+                    "what": f"full chain incl. IMU_Net (seeded stand-in weights), host tensors in, batch = {bs} snippet(s) per call"}
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,8 +323,9 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="snippets per GPU (config 3: 4096)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-snippets", type=int, default=256, help="snippets per CPU-baseline pass (bounded sample)")
+    ap.add_argument("--cpu-snippets", type=int, default=128, help="snippets per CPU-baseline step (bounded sample; 128 = best CPU batch)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-config1", action="store_true", help="skip the 835-sample-snippet record (config 1)")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (repeatable)")
     ap.add_argument("--no-half", action="store_true", help="skip the extra pass in single-pass fp16 mode")
     ap.add_argument("--imu-gemm", type=int, default=None, help="0 fp32 FFMA, 1 tcgen05 fp16x3, 2 tcgen05 fp16 (default: library default)")
@@ -321,8 +485,9 @@ def main():
             bc = min(chunk, B - c * chunk)
             fl_fast += N_IMU * (lstm_step_flops(bc * L, H) + lstm_step_flops(bc * L, 2 * H))
         peak = peaks["bf16_sustained"]
-        # DRAM bytes of one rnn_fast layer-1 step launch at M = 40,960 from `ncu --set full` (profiles/r01final_ncu_summary.txt)
-        NCU_TRAFFIC = {1: 1.245e9, 2: None, 0: None}     # profiles/r01lo4_ncu_summary.txt (was 1.463e9 in r01final)
+        # DRAM bytes of one rnn_fast layer-1 step launch at M = 40,960: read from the newest ncu --set full summary in profiles/
+        traffic_bytes, traffic_src = ncu_traffic_from_profiles()
+        NCU_TRAFFIC = {1: traffic_bytes, 2: None, 0: None}
 
         def lstm_roofline(prof_, ms_, steps_, mode_):
             lst = prof_.get("imu.lstm_fast", dict(ms=0.0, launches=0))
@@ -334,7 +499,7 @@ def main():
             return {"bound": "tensor", "kernel": "H=512 LSTM timestep launch (rnn_fast): " + KERNEL_NAMES[mode_],
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": NCU_TRAFFIC.get(mode_) if B >= 2048 else None,
-                    "traffic_note": "ncu dram read+write of a layer-1 step launch (M=40,960); algorithmic bytes 1.03e9",
+                    "traffic_note": f"ncu dram read+write of a layer-1 step launch (M=40,960) from {traffic_src}; algorithmic bytes 1.03e9",
                     "peak_source": peaks["source"] + ", sustained dense bf16 (kernel timed inside a long step)",
                     "avg_launch_ms": per_launch_ms, "launches": lst["launches"], "flops_per_launch": per_launch_flops,
                     "mma_passes": passes, "tensor_pipe_tflops_issued": ach * passes,
@@ -389,6 +554,7 @@ def main():
             "algorithmic_tflops": FLOPS_PER_FRAME["total"] * frames / (ms_per_step * 1e-3) / 1e12,
             "stage_ms_per_step": stage_ms,
             "mpjpe_vs_synthetic_target_cm": rep["mpjpe_cm"],
+            "mpjpe_surrogate_cm": None, "config1": None,
             "roofline": roofline,
             "stages": stage_rooflines(prof, args.steps, mode),
         }
@@ -402,12 +568,16 @@ def main():
                 "stage_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in prof2.items()}}
         if e2e:
             line["e2e"] = e2e
+        if world == 1 and not args.no_config1:
+            c1 = config1_record(dev)
+            if c1:
+                line["config1"] = c1
+                line["mpjpe_surrogate_cm"] = c1["mpjpe_surrogate_cm"]
+                line["mpjpe_surrogate_pin_cm"] = SURROGATE_PIN_CM
         if not args.no_cpu_baseline and world == 1:
-            fps, dt_cpu, cores = cpu_reference_pass(args.cpu_snippets, 2, 1)
-            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_snippets} snippets ({args.cpu_snippets * L} frames) of the same "
-                                              "synthetic workload, 1 warm-up + 2 timed passes of the oracle port "
-                                              "(PyTorch CPU fp32, all host threads)"}
+            r = cpu_reference_pass(args.cpu_snippets, 3, 1, batch1_snippets=8)
+            line["cpu_baseline"] = {"value": r["fps"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                    "sample": cpu_sample_text(r, args.cpu_snippets, 3, 1), "batch1": r["batch1"]}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

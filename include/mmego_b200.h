@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define MMEGO_ABI_VERSION 1
+#define MMEGO_ABI_VERSION 2
 
 enum {
     MMEGO_OK = 0,
@@ -68,7 +68,8 @@ const char* mmego_last_error(const mmego_handle* h);
  *          "host_chunk"  (mmego_infer_host: snippets per stage of its H2D / compute / D2H pipeline, default 2048; the
  *                         first stage is an eighth of that so the un-overlappable first copy stays short),
  *          "tc_kb_chunk" (imu_gemm=1: K blocks of 64 accumulated in TMEM before draining into fp32 registers, default 4;
- *                         8 is ~10 % faster and ~1.5x noisier),
+ *                         longer chunks are NOT faster -- the MMA work is the limit -- and ~1.5x noisier at 8,
+ *                         profiles/r01_lstm_chunk_accuracy.txt),
  *          "tc_cta_pair" (H=512 LSTM kernel on CTA pairs, cta_group::2 M=256 tiles, default 1),
  *          "tc_pdl"      (H=512 LSTM timestep launches use programmatic dependent launch: the prologue of step t+1
  *                         overlaps the tail of step t, default 1),
@@ -153,6 +154,7 @@ typedef struct {
     const double* t_R0R;           /* [F][3] */
     const double* R_ref;           /* [3][3] R_btc of the reference frame (the loader's st == 0 frame) */
     const double* orientation_ref; /* [3][3] orientation_imu_img of the reference frame */
+    long long n_frames;            /* F; a snippet window that leaves [0, F) yields all-zero frames (never an out-of-bounds read) */
 } mmego_raw_frames_t;
 /* starts [B]: first source frame of every snippet.  slot_src [B*L*N] (or NULL): source point of every output slot, -1 =
  * empty; NULL = seeded random placement (the reference uses an unseeded RNG).  Outputs: data [B,L,N,6],
@@ -175,7 +177,8 @@ long long mmego_launch_count(const mmego_handle* h);
 int mmego_profile_begin(mmego_handle* h);
 int mmego_profile_read(mmego_handle* h, const char* name, double* total_ms, long long* launches, long long* spans);
 int mmego_profile_end(mmego_handle* h);
-/* Cycle counters of the tensor-core LSTM kernel's instrumentation (option "tc_dbg" bit 2; diagnostics only). */
+/* Cycle counters of the tensor-core LSTM kernel's instrumentation.  The instrumentation (option "tc_dbg") is compiled
+ * only into test builds (-DMMEGO_DEBUG_SWITCHES); the product library rejects the option and returns zeros here. */
 int mmego_debug_stats(mmego_handle* h, unsigned long long* out8, int reset);
 
 #ifdef __cplusplus

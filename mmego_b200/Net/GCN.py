@@ -40,12 +40,12 @@ class Model(NativeNet):
     def _sync(self, device):
         from ..engine import get_handle
         h = get_handle(device)
-        key = self._weights_key()
-        if self._packed_handle is not h or key != self._packed_key:
+        key = (id(self), self._weights_key())
+        if h.weights_owner.get(self._net_id) != key:         # the NET_LOWER slot may hold a LowerNet's (or another GCN's) set
             sd = dict(self._rest)
             sd.update({"keyEncoder.gcn." + k: v for k, v in self.state_dict().items()})
             h.set_weights(self._net_id, sd)
-            self._packed_key, self._packed_handle = key, h
+            h.weights_owner[self._net_id] = key
         return h
 
     def extract_feature(self, x):

@@ -3,7 +3,11 @@
 Same constructor-less surface (`MMEgo().eval_model()`), same five printed lines (Demo_test.py:176-180) and the same
 return tuple (:184).  Differences, all on the host side:
   * batches of `Config.batch_size` snippets instead of the hard-coded 1 (Demo_test.py:61); all batches are equal-sized
-    or the tail is handled by exact sums, so the printed means are the global means the reference computes,
+    or the tail is handled by exact sums, so the printed means are the global means the reference computes.  The
+    reference's loop feeds ONE snippet per call, so its ForKinematics' `initial_body[r % B]` (B = 1) is that snippet's
+    own skeleton: the driver therefore runs the networks in per-snippet body-index mode (`initial_body[r // L]`), which
+    is identical to the reference at batch 1 for any batch size here -- also on multi-subject data, where replaying
+    `r % B` with B > 1 would hand frames the skeletons of other snippets,
   * error sums are accumulated on the device and read back once, instead of six .item() syncs per batch,
   * the sample set is read from the frozen tensor file built with the reference loader (np.random.seed(0)), because
     the loader's pad-slot placement uses the unseeded global RNG (Dataset_sample.py:215-223); with `from_raw=True`
@@ -30,7 +34,7 @@ class MMEgo:
             raise MMEgoError("MMEgo needs a CUDA device (B200); there is no CPU fallback")
         self.batch_size = int(batch_size or Config.batch_size)
         self.frame_no = Config.frame_no
-        self.pipe = MMEgoPipeline(self.device)
+        self.pipe = MMEgoPipeline(self.device, body_index_mode="per_snippet")
         # With the IMU_Net checkpoint absent (it is missing from the reference mount) the only way to reproduce an
         # accuracy figure is the surrogate of SURVEY.md section 8(c): IMU_Net's own training targets as (R, t).
         missing = not os.path.exists(Config.model_IMU_path)

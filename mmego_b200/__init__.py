@@ -4,6 +4,6 @@
 Host code is Python/PyTorch (device memory, streams, torch.distributed); all compute is hand-written CUDA in
 ``csrc/`` reached through the C ABI of ``include/mmego_b200.h`` (``_capi.py``).  No CPU fallback.
 """
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 __all__ = ["ABI_VERSION"]

@@ -59,7 +59,8 @@ class MMEgoError(RuntimeError):
 
 class RawFramesStruct(C.Structure):
     """mmego_raw_frames_t of include/mmego_b200.h (device pointers)."""
-    _fields_ = [(n, _vp) for n in ("points", "pt_start", "key", "imu", "R_btc", "t_R0R", "R_ref", "orientation_ref")]
+    _fields_ = [(n, _vp) for n in ("points", "pt_start", "key", "imu", "R_btc", "t_R0R", "R_ref", "orientation_ref")] + \
+               [("n_frames", _ll)]
     DTYPES = dict(points=torch.float32, pt_start=torch.int64, key=torch.float64, imu=torch.float64, R_btc=torch.float64,
                   t_R0R=torch.float64, R_ref=torch.float64, orientation_ref=torch.float64)
 
@@ -122,6 +123,7 @@ class Handle:
         self._h = hp
         self._ws: Optional[torch.Tensor] = None
         self._keep = []
+        self.weights_owner: Dict[int, object] = {}     # net id -> (module id, tensor versions) of the packed set (engine.NativeNet)
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -171,6 +173,7 @@ class Handle:
         names = (C.c_char_p * n)(*[k.encode() for k, _ in items])
         ptrs = (_vp * n)(*[v.data_ptr() for _, v in items])
         numels = (_ll * n)(*[v.numel() for _, v in items])
+        self.weights_owner.pop(net, None)              # a direct upload invalidates any module's claim on this slot
         self._ck(self.lib.dll.mmego_set_weights(self._h, net, names, ptrs, numels, n), "set_weights")
 
     def workspace_bytes(self, stage: int, B: int, L: int, N: int, n_imu: int) -> int:
@@ -278,8 +281,11 @@ class Handle:
         for name, dt in RawFramesStruct.DTYPES.items():
             st_t = self._t(raw[name], name, dt)
             setattr(st, name, st_t.data_ptr())
+        st.n_frames = int(raw["pt_start"].numel()) - 1
         starts = self._t(starts, "starts", torch.int64)
         B = starts.numel()
+        if B and (int(starts.min()) < 0 or int(starts.max()) + L > st.n_frames):
+            raise MMEgoError(f"starts must keep every {L}-frame window inside the {st.n_frames} raw frames")
         if slot_src is not None:
             slot_src = self._t(slot_src, "slot_src", torch.int32)
             if slot_src.numel() != B * L * N:
@@ -345,6 +351,7 @@ class Handle:
         Bg = B if B_global is None else B_global
         target = self._t(target, "target")
         sums = self._t(sums, "sums", torch.float64)
+        self._check_batch(imu, x, body, target, sums, Bg, b_offset)
         dev = x.device
         pred = torch.empty(B, L, 21, 3, dtype=torch.float32, device=dev) if want_pred else None
         o = outs if outs is not None else {}
@@ -354,6 +361,24 @@ class Handle:
             _ptr(o.get("R")), _ptr(o.get("t")), _ptr(o.get("upper_l")), _ptr(o.get("lower_l")), B, L, N, n, body_index_mode,
             b_offset, Bg, ws.data_ptr(), ws.numel(), self._stream()), "pipeline_forward")
         return pred
+
+    @staticmethod
+    def _check_batch(imu, x, body, target, sums, Bg, b_offset):
+        """The C entry points trust the sizes they are given: everything they will read is checked here."""
+        if x.dim() != 4 or x.shape[-1] != 6:
+            raise MMEgoError(f"data must be [B,L,N,6] (got {tuple(x.shape)})")
+        B, L = x.shape[:2]
+        if imu.dim() != 4 or imu.shape[-1] != 15 or tuple(imu.shape[:2]) != (B, L):
+            raise MMEgoError(f"imu must be [{B},{L},n_imu,15] to match data (got {tuple(imu.shape)})")
+        if b_offset < 0 or Bg < b_offset + B:
+            raise MMEgoError(f"bad shard: b_offset {b_offset} + B {B} exceeds B_global {Bg}")
+        if body.dim() != 3 or body.shape[0] < Bg or tuple(body.shape[1:]) != (20, 3):
+            raise MMEgoError(f"initial_body must be [{Bg},20,3] -- one skeleton per snippet of the GLOBAL batch "
+                             f"(got {tuple(body.shape)})")
+        if target is not None and target.numel() != B * L * 63:
+            raise MMEgoError(f"target must be [{B},{L},21,3] (got {tuple(target.shape)})")
+        if sums is not None and sums.numel() < SUMS_LEN:
+            raise MMEgoError(f"sums must hold {SUMS_LEN} float64")
 
     def infer_host(self, imu, data, initial_body, target=None, body_index_mode=BODY_REF, b_offset=0, B_global=None,
                    out_pred=None, out_sums=None):
@@ -366,6 +391,7 @@ class Handle:
         B, L, N, _ = data.shape
         n = imu.shape[2]
         Bg = B if B_global is None else B_global
+        self._check_batch(imu, data, initial_body, target, None, Bg, b_offset)
         pin = self.require_cuda
         if out_pred is not None:
             if out_pred.is_cuda or out_pred.dtype != torch.float32 or not out_pred.is_contiguous() or out_pred.numel() != B * L * 63:

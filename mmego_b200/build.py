@@ -1,6 +1,10 @@
 """Builds libmmego_b200.so (hand-written sm_100a CUDA behind the C ABI of include/mmego_b200.h) IN-TREE.
 
-    python -m mmego_b200.build [--force] [--verbose]
+    python -m mmego_b200.build [--force] [--verbose] [--variant product|ffma]
+
+`--variant ffma` builds the TEST-ONLY library tests/_variant_build/libmmego_b200_ffma.so from the same sources with
+-DMMEGO_WITH_FFMA -DMMEGO_DEBUG_SWITCHES: it additionally holds the first-generation fp32 FFMA kernels (exact-fp32 A/B
+references used by tests/test_gpu_parity.py) and the tc_dbg experiment switches.  The product library has neither.
 
 nvcc cross-compiles for sm_100a without a GPU; the resulting .so sits next to this file
 (mmego_b200/lib/libmmego_b200.so), is git-ignored and travels to the GPU box with the snapshot.
@@ -38,7 +42,15 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: libmmego_b200 cannot be built (there is no CPU fallback)")
 
 
-def _digest() -> str:
+VARIANTS = {
+    "product": dict(flags=[], libdir=LIBDIR, lib=LIB),
+    "ffma": dict(flags=["-DMMEGO_WITH_FFMA", "-DMMEGO_DEBUG_SWITCHES"],
+                 libdir=os.path.join(ROOT, "tests", "_variant_build"),
+                 lib=os.path.join(ROOT, "tests", "_variant_build", "libmmego_b200_ffma.so")),
+}
+
+
+def _digest(extra=()) -> str:
     h = hashlib.sha256()
     for name in SOURCES + HEADERS:
         p = os.path.join(CSRC, name)
@@ -46,15 +58,15 @@ def _digest() -> str:
             h.update(name.encode())
             with open(p, "rb") as f:
                 h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(list(NVCC_FLAGS) + list(extra)).encode())
     return h.hexdigest()
 
 
-def _compile(nvcc: str, src: str, verbose: bool) -> str:
-    obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
-    cmd = [nvcc, *NVCC_FLAGS, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
+def _compile(nvcc: str, src: str, verbose: bool, objdir: str = OBJDIR, extra=()) -> str:
+    obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
-    log = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".ptxas.log")
+    log = os.path.join(objdir, os.path.splitext(src)[0] + ".ptxas.log")
     with open(log, "w") as f:
         f.write(r.stdout + r.stderr)
     if r.returncode != 0:
@@ -64,32 +76,36 @@ def _compile(nvcc: str, src: str, verbose: bool) -> str:
     return obj
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(OBJDIR, exist_ok=True)
-    stamp = os.path.join(LIBDIR, "build.sha256")
-    dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
-        return LIB
+def build(force: bool = False, verbose: bool = False, variant: str = "product") -> str:
+    v = VARIANTS[variant]
+    libdir, lib, extra = v["libdir"], v["lib"], v["flags"]
+    objdir = os.path.join(libdir, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    stamp = os.path.join(libdir, "build.sha256")
+    dig = _digest(extra)
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return lib
     nvcc = _nvcc()
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(lambda s: _compile(nvcc, s, verbose), srcs))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+        objs = list(ex.map(lambda s: _compile(nvcc, s, verbose, objdir, extra), srcs))
+    cmd = [nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
            "-cudart", "static", "-ldl", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as f:
         f.write(dig)
-    return LIB
+    return lib
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--variant", default="product", choices=sorted(VARIANTS))
     a = ap.parse_args()
-    print(build(a.force, a.verbose))
+    print(build(a.force, a.verbose, a.variant))
 
 
 if __name__ == "__main__":

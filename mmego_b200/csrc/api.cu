@@ -9,7 +9,19 @@
 #include "pack.h"
 
 namespace mmego {
-long long g_launches = 0;
+thread_local long long t_launches = 0;
+
+// frees a device allocation owned by the handle (re-packing weights replaces buffers; nothing may pile up until destroy)
+void handle_free(mmego_handle* h, void* p) {
+    if (!p) return;
+    for (size_t i = 0; i < h->owned.size(); ++i)
+        if (h->owned[i] == p) {
+            h->owned[i] = h->owned.back();
+            h->owned.pop_back();
+            break;
+        }
+    cudaFree(p);
+}
 }
 
 using namespace mmego;
@@ -34,9 +46,35 @@ int fail(mmego_handle* h, int code, const char* fmt, ...) {
         if (e__ != cudaSuccess) return fail((h), MMEGO_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
     } while (0)
 
+// Per-call bookkeeping of an API entry point: selects the handle's device for the duration of the call (a process that
+// drives several GPUs may have another one current) and credits the kernels launched by THIS call to THIS handle.
+// Entry points nest (pipeline_forward -> imu_forward ...): only the outermost one counts.
+struct Entry {
+    mmego_handle* h;
+    long long t0;
+    int prev_dev = -1;
+    bool outer = false;
+    explicit Entry(mmego_handle* h_) : h(h_), t0(t_launches) {
+        if (!h) return;
+        outer = h->entry_depth++ == 0;
+        int cur = -1;
+        if (outer && cudaGetDevice(&cur) == cudaSuccess && cur != h->device) {
+            prev_dev = cur;
+            cudaSetDevice(h->device);
+        }
+    }
+    ~Entry() {
+        if (!h) return;
+        --h->entry_depth;
+        if (outer) h->launches += t_launches - t0;
+        if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    }
+};
+
 // ---------------------------------------------------------------------------------------------- device buffers
 bool upload(mmego_handle* h, const std::vector<float>& v, DevBuf& out) {
-    if (out.p && out.n != v.size()) {   // re-pack with a different size: drop the old buffer
+    if (out.p && out.n != v.size()) {   // re-pack with a different size: release the old buffer
+        handle_free(h, out.p);
         out.p = nullptr;
     }
     if (!out.p) {
@@ -67,7 +105,8 @@ struct Carver {
     }
 };
 
-// ---------------------------------------------------------------------------------------------- GEMM helpers
+#ifdef MMEGO_FFMA_GEN
+// ---------------------------------------------------------------------------------------------- GEMM helpers (fp32 FFMA generation)
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 GemmArgs gemm_begin(const PackedGemm& w, float* c, long long ldc, long long M, int relu) {
@@ -117,6 +156,8 @@ void linear(mmego_handle* h, const PackedGemm& w, const float* a, long long lda,
     run_gemm(h, g, EPI_STORE, st);
 }
 
+#endif  // MMEGO_FFMA_GEN
+
 void tap(mmego_handle* h, const char* name, const void* src, size_t bytes, cudaStream_t st) {
     auto it = h->taps.find(name);
     if (it == h->taps.end()) return;
@@ -137,14 +178,14 @@ struct Prof {
         sp.name = name;
         if (cudaEventCreate(&sp.e0) != cudaSuccess || cudaEventCreate(&sp.e1) != cudaSuccess) return;
         cudaEventRecord(sp.e0, st);
-        l0 = g_launches;
+        l0 = t_launches;
         h->prof.push_back(sp);
         idx = h->prof.size() - 1;
     }
     ~Prof() {
         if (idx == (size_t)-1) return;
         cudaEventRecord(h->prof[idx].e1, st);
-        h->prof[idx].launches = g_launches - l0;
+        h->prof[idx].launches = t_launches - l0;
     }
 };
 
@@ -166,7 +207,10 @@ const float* run_small_lstm(mmego_handle* h, const PackedSmallLstmLayer* layers,
     long long ld = in_ld;
     Prof prof(h, "small_lstm", st);
     for (int l = 0; l < 3; ++l) {
-        if (h->small_lstm_gemm) {
+#ifdef MMEGO_FFMA_GEN
+        if (h->small_lstm_gemm)
+#endif
+        {
             const size_t so = (size_t)l * 2 * S * kSmallH;
             launch_lstm_small_mma(cur, ld, layers[l].in, layers[l].mma.p, w.gx, h0 ? h0 + so : nullptr,
                                   c0 ? c0 + so : nullptr, w.y[l & 1], hn ? hn + so : nullptr, cn ? cn + so : nullptr,
@@ -179,17 +223,20 @@ const float* run_small_lstm(mmego_handle* h, const PackedSmallLstmLayer* layers,
             tap(h, yn[l], cur, (size_t)S * T * 128 * 4, st);
             continue;
         }
+#ifdef MMEGO_FFMA_GEN
         linear(h, layers[l].ih, cur, ld, w.gx, 512, S * T, 0, st);
         const size_t so = (size_t)l * 2 * S * kSmallH;
         launch_lstm_small(w.gx, layers[l].whh.p, h0 ? h0 + so : nullptr, c0 ? c0 + so : nullptr, w.y[l & 1],
                           hn ? hn + so : nullptr, cn ? cn + so : nullptr, (int)S, T, st);
         cur = w.y[l & 1];
         ld = 128;
+#endif
     }
     return cur;
 }
 
-// ---------------------------------------------------------------------------------------------- IMU_Net schedule
+#ifdef MMEGO_FFMA_GEN
+// ---------------------------------------------------------------------------------------------- IMU_Net schedule (fp32 FFMA generation)
 struct ImuWs {
     float *u, *y0, *y1, *cst, *s, *z0, *z1;
 };
@@ -256,6 +303,8 @@ int imu_chunk_forward(mmego_handle* h, const float* imu, float* R, float* t, lon
     }
     return MMEGO_OK;
 }
+
+#endif  // MMEGO_FFMA_GEN
 
 #ifndef MMEGO_EMUL
 // ---------------------------------------------------------------------------------------------- IMU_Net on tensor cores
@@ -375,6 +424,7 @@ void plan_lower(Carver& c, long long B, int L, LowerWs& w, bool tc) {
     w.o = c.f(F * 42);
 }
 
+#ifdef MMEGO_FFMA_GEN
 // GCN.Model.extract_feature body on channel-last rows; y0 [F*15, 3] (data_bn already applied) -> kf [B][64][L*15]
 void run_gcn(mmego_handle* h, const float* y0, int B, int L, const LowerWs& w, cudaStream_t st) {
     const LowerWeights& W = h->lower;
@@ -403,6 +453,7 @@ void run_gcn(mmego_handle* h, const float* y0, int B, int L, const LowerWs& w, c
     a.f6_period = L * kGcnV;
     run_gemm(h, a, EPI_F6, st, 64);
 }
+#endif  // MMEGO_FFMA_GEN
 
 #ifndef MMEGO_EMUL
 // ST-GCN on tensor cores: y0 planes [F*15][8] (data_bn applied) -> kf fp32 [B][64][L*15]
@@ -452,8 +503,10 @@ size_t imu_ws_bytes(const mmego_handle* h, long long Bc, int L, int n) {
         return s.off;
     }
 #endif
+#ifdef MMEGO_FFMA_GEN
     ImuWs w;
     plan_imu(s, Bc, L, n, w);
+#endif
     (void)h;
     return s.off;
 }
@@ -489,8 +542,14 @@ int mmego_create(mmego_handle** out, int device) {
 #ifdef MMEGO_EMUL
     h->imu_gemm = 0;
 #else
-    h->imu_gemm = tc_supported() ? 1 : 0;      // default: tcgen05 fp16x3 (fp32-grade); 0 = FFMA fp32; 2 = tcgen05 fp16
+    h->imu_gemm = tc_supported() ? 1 : 0;      // default: tcgen05 fp16x3 (fp32-grade); 2 = tcgen05 fp16; 0 = fp32 FFMA (test builds)
     h->gcn_gemm = tc_supported() ? 1 : 0;
+#ifndef MMEGO_FFMA_GEN
+    if (!tc_supported()) {
+        delete h;
+        return fail(nullptr, MMEGO_EARCH, "cuTensorMapEncodeTiled is not available from this driver: the tensor-core kernels cannot run (there is no fallback path)");
+    }
+#endif
 #endif
     *out = h;
     return MMEGO_OK;
@@ -501,6 +560,11 @@ int mmego_destroy(mmego_handle* h) {
     cudaSetDevice(h->device);
     for (void* p : h->owned) cudaFree(p);
     if (h->stage_dev) cudaFree(h->stage_dev);
+    if (h->tc_stats) cudaFree(h->tc_stats);
+    for (ProfSpan& sp : h->prof) {
+        if (sp.e0) cudaEventDestroy(sp.e0);
+        if (sp.e1) cudaEventDestroy(sp.e1);
+    }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
@@ -512,6 +576,7 @@ int mmego_destroy(mmego_handle* h) {
 const char* mmego_last_error(const mmego_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
 int mmego_set_option(mmego_handle* h, const char* key, long long value) {
+    Entry entry(h);
     if (!h || !key) return MMEGO_EINVAL;
     if (!strcmp(key, "imu_chunk")) {
         if (value <= 0) return fail(h, MMEGO_EINVAL, "imu_chunk must be positive");
@@ -520,6 +585,9 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
     }
     if (!strcmp(key, "imu_gemm")) {
         if (value < 0 || value > 2) return fail(h, MMEGO_EINVAL, "imu_gemm must be 0 (fp32 FFMA), 1 (tcgen05 fp16x3) or 2 (tcgen05 fp16)");
+#ifndef MMEGO_FFMA_GEN
+        if (value == 0) return fail(h, MMEGO_EINVAL, "imu_gemm=0: the fp32 FFMA kernel generation is not part of the product library (test builds: -DMMEGO_WITH_FFMA)");
+#endif
 #ifdef MMEGO_EMUL
         if (value != 0) return fail(h, MMEGO_EINVAL, "imu_gemm=%lld needs the sm_100a build", value);
 #else
@@ -530,8 +598,12 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
         return MMEGO_OK;
     }
     if (!strcmp(key, "tc_dbg")) {
-        h->tc_dbg = (int)value;
+#ifdef MMEGO_DEBUG_SWITCHES
+        h->tc_dbg = (int)value;      // experiment switches of lstm_tc.cu (some make the kernel skip work): test builds only
         return MMEGO_OK;
+#else
+        return fail(h, MMEGO_EINVAL, "tc_dbg exists only in builds with -DMMEGO_DEBUG_SWITCHES (it is not part of the product library)");
+#endif
     }
     if (!strcmp(key, "tc_cta_pair")) {
         h->tc_cta_pair = value != 0;
@@ -549,11 +621,17 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
 #else
         if (value != 0 && !tc_supported()) return fail(h, MMEGO_EARCH, "gcn_gemm=1: cuTensorMapEncodeTiled is not available");
 #endif
+#ifndef MMEGO_FFMA_GEN
+        if (value == 0) return fail(h, MMEGO_EINVAL, "gcn_gemm=0: the fp32 FFMA kernel generation is not part of the product library (test builds: -DMMEGO_WITH_FFMA)");
+#endif
         h->gcn_gemm = (int)value;
         return MMEGO_OK;
     }
     if (!strcmp(key, "point_gemm")) {
         if (value < 0 || value > 1) return fail(h, MMEGO_EINVAL, "point_gemm must be 0 (fp32 FFMA) or 1 (mma.sync fp16x3)");
+#ifndef MMEGO_FFMA_GEN
+        if (value == 0) return fail(h, MMEGO_EINVAL, "point_gemm=0: the fp32 FFMA kernel generation is not part of the product library (test builds: -DMMEGO_WITH_FFMA)");
+#endif
         h->point_gemm = (int)value;
         return MMEGO_OK;
     }
@@ -564,11 +642,17 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
     }
     if (!strcmp(key, "head_gemm")) {
         if (value < 0 || value > 1) return fail(h, MMEGO_EINVAL, "head_gemm must be 0 (fp32 FFMA) or 1 (mma.sync fp16x3)");
+#ifndef MMEGO_FFMA_GEN
+        if (value == 0) return fail(h, MMEGO_EINVAL, "head_gemm=0: the fp32 FFMA kernel generation is not part of the product library (test builds: -DMMEGO_WITH_FFMA)");
+#endif
         h->head_gemm = (int)value;
         return MMEGO_OK;
     }
     if (!strcmp(key, "small_lstm_gemm")) {
         if (value < 0 || value > 1) return fail(h, MMEGO_EINVAL, "small_lstm_gemm must be 0 (fp32 FFMA) or 1 (mma.sync fp16x3)");
+#ifndef MMEGO_FFMA_GEN
+        if (value == 0) return fail(h, MMEGO_EINVAL, "small_lstm_gemm=0: the fp32 FFMA kernel generation is not part of the product library (test builds: -DMMEGO_WITH_FFMA)");
+#endif
         h->small_lstm_gemm = (int)value;
         return MMEGO_OK;
     }
@@ -607,15 +691,12 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
         h->tc_kb_chunk = (int)value;
         return MMEGO_OK;
     }
-    if (!strcmp(key, "tc_precise_act")) {
-        h->tc_precise_act = value != 0;
-        return MMEGO_OK;
-    }
     return fail(h, MMEGO_EINVAL, "unknown option '%s'", key);
 }
 
 int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const float* const* ptrs_host,
                       const long long* numels, int n) {
+    Entry entry(h);
     if (!h || !names || !ptrs_host || !numels || n < 0) return MMEGO_EINVAL;
     cudaSetDevice(h->device);
     StateDict sd;
@@ -631,9 +712,13 @@ int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const 
             const int H = kImuH;
             {
                 const HostPackedGemm fc1 = pack_linear(sd.get("fc1.weight", H * kImuFeat), sd.get("fc1.bias", H), H, {kImuFeat});
-                ok &= upload(h, fc1, W.fc1) && upload(h, pack_imu_fc1_mma(fc1), W.fc1_mma);
+                ok &= upload(h, pack_imu_fc1_mma(fc1), W.fc1_mma);
+#ifdef MMEGO_FFMA_GEN
+                ok &= upload(h, fc1, W.fc1);
+#endif
             }
-            for (int l = 0; l < 2; ++l) {
+#ifdef MMEGO_FFMA_GEN
+            for (int l = 0; l < 2; ++l) {       // 92 MB of fp32 GEMM-format weights: only where the FFMA kernels exist
                 HostBigLstm f = pack_big_lstm(sd, "rnn_fast.", l, l == 0 ? H : 2 * H, H);
                 HostBigLstm s = pack_big_lstm(sd, "rnn_slow.", l, 2 * H, H);
                 for (int d = 0; d < 2; ++d) {
@@ -641,6 +726,7 @@ int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const 
                     ok &= upload(h, s.dir[d], W.slow[l].dir[d]);
                 }
             }
+#endif
             std::vector<float> attn(2 * H + 4, 0.f);
             memcpy(attn.data(), sd.get("attn.weight", 2 * H), sizeof(float) * 2 * H);
             attn[2 * H] = sd.get("attn.bias", 1)[0];
@@ -782,6 +868,7 @@ size_t mmego_workspace_bytes(const mmego_handle* h, int stage, int B, int L, int
 
 int mmego_imu_forward(mmego_handle* h, const float* imu, float* R, float* t, int B, int L, int n_imu, void* ws,
                       size_t ws_bytes, void* stream) {
+    Entry entry(h);
     if (int rc = check_dims(h, B, L, 1)) return rc;
     if (!imu || !R || !t || !ws) return fail(h, MMEGO_EINVAL, "imu_forward: NULL argument");
     if (!h->imu.ready) return fail(h, MMEGO_ESTATE, "imu_forward: IMU_Net weights were never set");
@@ -803,10 +890,10 @@ int mmego_imu_forward(mmego_handle* h, const float* imu, float* R, float* t, int
                 return rc;
         }
         CUDA_TRY(h, cudaGetLastError());
-        h->launches = g_launches;
-        return MMEGO_OK;
+            return MMEGO_OK;
     }
 #endif
+#ifdef MMEGO_FFMA_GEN
     ImuWs w;
     plan_imu(c, Bc, L, n_imu, w);
     for (long long b0 = 0; b0 < B; b0 += Bc) {
@@ -815,14 +902,18 @@ int mmego_imu_forward(mmego_handle* h, const float* imu, float* R, float* t, int
                           n_imu, w, st);
     }
     CUDA_TRY(h, cudaGetLastError());
-    h->launches = g_launches;
     return MMEGO_OK;
+#else
+    (void)st; (void)c; (void)Bc;
+    return fail(h, MMEGO_ESTATE, "imu_forward: no kernel path for imu_gemm=%d in this build", h->imu_gemm);
+#endif
 }
 
 int mmego_upper_forward(mmego_handle* h, float* x, const float* h0, const float* c0, const float* initial_body,
                         const float* R, const float* t, float* l, float* q, float* global_w, float* hn, float* cn,
                         int B, int L, int N, int body_index_mode, int b_offset, int B_global, void* ws,
                         size_t ws_bytes, void* stream) {
+    Entry entry(h);
     if (int rc = check_dims(h, B, L, N)) return rc;
     if (!x || !initial_body || !R || !t || !l || !ws) return fail(h, MMEGO_EINVAL, "upper_forward: NULL argument");
     if (!h->upper.ready) return fail(h, MMEGO_ESTATE, "upper_forward: Upper_Net weights were never set");
@@ -839,31 +930,34 @@ int mmego_upper_forward(mmego_handle* h, float* x, const float* h0, const float*
     const UpperWeights& W = h->upper;
     {
         Prof p(h, "upper.point", st);
-        if (h->point_gemm)                                                               // Upper_Net.py:379-381 (+gpointnet)
-            launch_upper_point_mma(x, R, t, W.point_mma.p, w.g, global_w, F, N, h->sm_count, st);
-        else
+#ifdef MMEGO_FFMA_GEN
+        if (!h->point_gemm)
             launch_upper_point(x, R, t, W.point.p, w.g, global_w, F, N, h->sm_count, st);
+        else
+#endif
+            launch_upper_point_mma(x, R, t, W.point_mma.p, w.g, global_w, F, N, h->sm_count, st);   // Upper_Net.py:379-381 (+gpointnet)
     }
     tap(h, "upper.g", w.g, (size_t)F * 64 * 4, st);
     const float* hs = run_small_lstm(h, W.lstm, w.g, 64, h0, c0, hn, cn, B, L, w.lstm, st);   // :339
     tap(h, "upper.lstm", hs, (size_t)F * 128 * 4, st);
     Prof p(h, "upper.head_decode", st);
-    if (h->head_gemm) {
-        launch_upper_head_mma(hs, W.head_mma.p, w.o, F, h->sm_count, st);                // :351-353
-    } else {
+#ifdef MMEGO_FFMA_GEN
+    if (!h->head_gemm) {
         linear(h, W.fc1, hs, 128, w.h1, 128, F, 1, st);
         linear(h, W.fc2, w.h1, 128, w.o, 87, F, 0, st);
-    }
+    } else
+#endif
+        launch_upper_head_mma(hs, W.head_mma.p, w.o, F, h->sm_count, st);                // :351-353
     tap(h, "upper.o", w.o, (size_t)F * 87 * 4, st);
     launch_upper_decode(w.o, initial_body, R, t, l, q, F, L, body_index_mode, (long long)b_offset * L, B_global, st);   // :355-387
     CUDA_TRY(h, cudaGetLastError());
-    h->launches = g_launches;
     return MMEGO_OK;
 }
 
 int mmego_lower_forward(mmego_handle* h, const float* upper_l, float* x, const float* initial_body, const float* R,
                         const float* t, float* l, float* q, int B, int L, int N, int body_index_mode, int b_offset,
                         int B_global, void* ws, size_t ws_bytes, void* stream) {
+    Entry entry(h);
     if (int rc = check_dims(h, B, L, N)) return rc;
     if (!upper_l || !x || !initial_body || !R || !t || !l || !ws) return fail(h, MMEGO_EINVAL, "lower_forward: NULL argument");
     if (!h->lower.ready) return fail(h, MMEGO_ESTATE, "lower_forward: Lower_Net weights were never set");
@@ -889,43 +983,50 @@ int mmego_lower_forward(mmego_handle* h, const float* upper_l, float* x, const f
         if (run_gcn_tc(h, B, L, w, st)) return fail(h, MMEGO_ECUDA, "lower_forward: tensor-core ST-GCN launch failed");
 #endif
     } else {
+#ifdef MMEGO_FFMA_GEN
         float* y0 = w.y[1];   // layer 0 writes y[0], so y[1] is free to hold the 3-channel input
         Prof p(h, "lower.gcn", st);
         launch_gcn_prep(upper_l, R, t, W.data_bn.p, w.uh, y0, F, st);                     // Lower_Net.py:229, GCN.py:339-344
         run_gcn(h, y0, B, L, w, st);
+#else
+        return fail(h, MMEGO_ESTATE, "lower_forward: no ST-GCN kernel path in this build");
+#endif
     }
     tap(h, "lower.uh", w.uh, (size_t)F * 45 * 4, st);
     tap(h, "lower.K", w.kf, (size_t)F * kGcnV * 64 * 4, st);
     {
         Prof p(h, "lower.frame", st);
-        if (h->point_gemm)                                                                // :191-192, 216-227, 231, 104-116
-            launch_lower_frame_mma(x, R, t, w.kf, W.frame_mma.p, w.ak, F, N, h->sm_count, st);
-        else
+#ifdef MMEGO_FFMA_GEN
+        if (!h->point_gemm)
             launch_lower_frame(x, R, t, w.kf, W.frame.p, w.ak, F, N, h->sm_count, st);
+        else
+#endif
+            launch_lower_frame_mma(x, R, t, w.kf, W.frame_mma.p, w.ak, F, N, h->sm_count, st);   // :191-192, 216-227, 231, 104-116
     }
     tap(h, "lower.ak", w.ak, (size_t)F * 192 * 4, st);
     const float* hs = run_small_lstm(h, W.lstm, w.ak, 192, nullptr, nullptr, nullptr, nullptr, B, L, w.lstm, st);   // :117
     tap(h, "lower.lstm", hs, (size_t)F * 128 * 4, st);
     Prof p(h, "lower.head_decode", st);
-    if (h->head_gemm) {
-        launch_lower_head_mma(hs, w.uh, W.head_mma.p, w.o, F, h->sm_count, st);           // :119-124
-    } else {
+#ifdef MMEGO_FFMA_GEN
+    if (!h->head_gemm) {
         GemmArgs a = gemm_begin(W.fc0, w.f0, 128, F, 1);                                  // :119-121
         gemm_seg(a, W.fc0, hs, 128);
         gemm_seg(a, W.fc0, w.uh, 45);
         run_gemm(h, a, EPI_STORE, st);
         linear(h, W.fc1, w.f0, 128, w.f1, 64, F, 1, st);                                  // :122-123
         linear(h, W.fc2, w.f1, 64, w.o, 42, F, 0, st);                                    // :124
-    }
+    } else
+#endif
+        launch_lower_head_mma(hs, w.uh, W.head_mma.p, w.o, F, h->sm_count, st);           // :119-124
     tap(h, "lower.o", w.o, (size_t)F * 42 * 4, st);
     launch_lower_decode(w.o, initial_body, R, t, l, q, F, L, body_index_mode, (long long)b_offset * L, B_global, st);   // :126-135, 235-238
     CUDA_TRY(h, cudaGetLastError());
-    h->launches = g_launches;
     return MMEGO_OK;
 }
 
 int mmego_gcn_extract_feature(mmego_handle* h, const float* x, float* out, int B, int T, void* ws, size_t ws_bytes,
                               void* stream) {
+    Entry entry(h);
     if (int rc = check_dims(h, B, T, 1)) return rc;
     if (!x || !out || !ws) return fail(h, MMEGO_EINVAL, "gcn_extract_feature: NULL argument");
     if (!h->lower.ready) return fail(h, MMEGO_ESTATE, "gcn_extract_feature: Lower_Net weights were never set");
@@ -943,44 +1044,47 @@ int mmego_gcn_extract_feature(mmego_handle* h, const float* x, float* out, int B
         if (run_gcn_tc(h, B, T, w, st)) return fail(h, MMEGO_ECUDA, "gcn_extract_feature: tensor-core launch failed");
 #endif
     } else {
+#ifdef MMEGO_FFMA_GEN
         float* y0 = w.y[1];
         launch_gcn_prep_raw(x, h->lower.data_bn.p, y0, B, T, st);
         run_gcn(h, y0, B, T, w, st);
+#else
+        return fail(h, MMEGO_ESTATE, "gcn_extract_feature: no ST-GCN kernel path in this build");
+#endif
     }
     CUDA_TRY(h, cudaMemcpyAsync(out, w.kf, (size_t)B * T * kGcnV * 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(h, cudaGetLastError());
-    h->launches = g_launches;
     return MMEGO_OK;
 }
 
 int mmego_transform2h(mmego_handle* h, float* points, const float* R, const float* t, long long F, int n, int D,
                       void* stream) {
+    Entry entry(h);
     if (!h) return MMEGO_EINVAL;
     if (!points || !R || !t || F < 0 || n <= 0 || D < 3) return fail(h, MMEGO_EINVAL, "transform2h: bad argument");
     launch_transform2h(points, R, t, F, n, D, static_cast<cudaStream_t>(stream));
     CUDA_TRY(h, cudaGetLastError());
-    h->launches = g_launches;
     return MMEGO_OK;
 }
 
 int mmego_transform2r(mmego_handle* h, const float* points, const float* R, const float* t, float* out, long long F,
                       int n, void* stream) {
+    Entry entry(h);
     if (!h) return MMEGO_EINVAL;
     if (!points || !R || !t || !out || F < 0 || n <= 0) return fail(h, MMEGO_EINVAL, "transform2r: bad argument");
     launch_transform2r(points, R, t, out, F, n, static_cast<cudaStream_t>(stream));
     CUDA_TRY(h, cudaGetLastError());
-    h->launches = g_launches;
     return MMEGO_OK;
 }
 
 int mmego_assemble_metrics(mmego_handle* h, const float* upper_l, const float* lower_l, const float* target,
                            float* pred, double* sums, int B, int L, void* stream) {
+    Entry entry(h);
     if (int rc = check_dims(h, B, L, 1)) return rc;
     if (!upper_l || !lower_l) return fail(h, MMEGO_EINVAL, "assemble_metrics: NULL argument");
     Prof p(h, "assemble_metrics", static_cast<cudaStream_t>(stream));
     launch_assemble_metrics(upper_l, lower_l, target, pred, sums, (long long)B * L, static_cast<cudaStream_t>(stream));
     CUDA_TRY(h, cudaGetLastError());
-    h->launches = g_launches;
     return MMEGO_OK;
 }
 
@@ -988,6 +1092,7 @@ int mmego_pipeline_forward(mmego_handle* h, const float* imu, float* x, const fl
                            float* pred, double* sums, float* R_out, float* t_out, float* upper_out, float* lower_out,
                            int B, int L, int N, int n_imu, int body_index_mode, int b_offset, int B_global, void* ws,
                            size_t ws_bytes, void* stream) {
+    Entry entry(h);
     if (int rc = check_dims(h, B, L, N)) return rc;
     if (!imu || !x || !initial_body || !ws) return fail(h, MMEGO_EINVAL, "pipeline_forward: NULL argument");
     if (ws_bytes < mmego_workspace_bytes(h, MMEGO_STAGE_PIPELINE, B, L, N, n_imu))
@@ -1019,6 +1124,7 @@ int mmego_pipeline_forward(mmego_handle* h, const float* imu, float* x, const fl
 int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_host, const float* initial_body_host,
                      const float* target_host, float* pred_host, double* sums_host, int B, int L, int N, int n_imu,
                      int body_index_mode, int b_offset, int B_global) {
+    Entry entry(h);
     if (int rc = check_dims(h, B, L, N)) return rc;
     if (!imu_host || !data_host || !initial_body_host) return fail(h, MMEGO_EINVAL, "infer_host: NULL argument");
     cudaSetDevice(h->device);
@@ -1132,16 +1238,18 @@ int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_h
 int mmego_build_snippets(mmego_handle* h, const mmego_raw_frames_t* raw, const long long* starts, const int* slot_src,
                          unsigned seed, float* data, float* imu, float* key, float* R, float* t, int B, int L, int N,
                          void* stream) {
+    Entry entry(h);
     if (int rc = check_dims(h, B, L, N)) return rc;
     if (!raw || !starts || !data || !imu || !key || !R || !t) return fail(h, MMEGO_EINVAL, "build_snippets: NULL argument");
     if (!raw->points || !raw->pt_start || !raw->key || !raw->imu || !raw->R_btc || !raw->t_R0R || !raw->R_ref ||
         !raw->orientation_ref)
         return fail(h, MMEGO_EINVAL, "build_snippets: NULL array in mmego_raw_frames_t");
-    RawFrames rf{raw->points, raw->pt_start, raw->key, raw->imu, raw->R_btc, raw->t_R0R, raw->R_ref, raw->orientation_ref};
+    if (raw->n_frames <= 0) return fail(h, MMEGO_EINVAL, "build_snippets: mmego_raw_frames_t.n_frames must be positive");
+    RawFrames rf{raw->points, raw->pt_start, raw->key, raw->imu, raw->R_btc, raw->t_R0R, raw->R_ref, raw->orientation_ref,
+                 raw->n_frames};
     Prof p(h, "build_snippets", static_cast<cudaStream_t>(stream));
     launch_snippet_build(rf, starts, slot_src, seed, data, imu, key, R, t, B, L, N, static_cast<cudaStream_t>(stream));
     CUDA_TRY(h, cudaGetLastError());
-    h->launches = g_launches;
     return MMEGO_OK;
 }
 
@@ -1152,7 +1260,7 @@ int mmego_debug_tap(mmego_handle* h, const char* name, void* dst, size_t bytes) 
     return MMEGO_OK;
 }
 
-long long mmego_launch_count(const mmego_handle* h) { return h ? g_launches : 0; }
+long long mmego_launch_count(const mmego_handle* h) { return h ? h->launches : 0; }
 
 int mmego_profile_begin(mmego_handle* h) {
     if (!h) return MMEGO_EINVAL;

@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(DT) assemble_metrics_kernel(const float* __res
     if (tid < kSumsLen && s.acc[tid] != 0.0) atomicAdd(&sums[tid], s.acc[tid]);
 }
 
+#ifdef MMEGO_FFMA_GEN   // fp32 FFMA generation: emulator suite and -DMMEGO_WITH_FFMA test builds only (not in the product library)
 // ------------------------------------------------------------------------------------------------
 // IMU_Net tail
 // ------------------------------------------------------------------------------------------------
@@ -359,6 +360,8 @@ __global__ void __launch_bounds__(256) imu_decode_kernel(const float* __restrict
     }
 }
 
+#endif  // MMEGO_FFMA_GEN
+
 // ------------------------------------------------------------------------------------------------
 // rigid transforms (Utils.py:274-292) as standalone ops for the drop-in Util module
 // ------------------------------------------------------------------------------------------------
@@ -416,6 +419,7 @@ void launch_assemble_metrics(const float* up, const float* lo, const float* tg, 
     MMEGO_LAUNCH(assemble_metrics_kernel, dim3((unsigned)((F + FPB - 1) / FPB)), dim3(DT), sizeof(MetricsSmem), st, up,
                  lo, tg, pred, sums, F);
 }
+#ifdef MMEGO_FFMA_GEN   // fp32 FFMA generation: emulator suite and -DMMEGO_WITH_FFMA test builds only (not in the product library)
 void launch_imu_pool(const float* y, const float* attn, float* out, long long F, int n, cudaStream_t st) {
     if (F <= 0) return;
     MMEGO_LAUNCH(imu_pool_kernel, dim3((unsigned)F), dim3(PW), 0, st, y, attn, out, F, n);
@@ -424,6 +428,8 @@ void launch_imu_decode(const float* g, const float* fc2, float* R, float* t, lon
     if (F <= 0) return;
     MMEGO_LAUNCH(imu_decode_kernel, dim3((unsigned)((F + 7) / 8)), dim3(256), 0, st, g, fc2, R, t, F);
 }
+#endif  // MMEGO_FFMA_GEN
+
 void launch_transform2h(float* pts, const float* R, const float* t, long long F, int n, int D, cudaStream_t st) {
     const long long total = F * n;
     if (total <= 0) return;

@@ -4,6 +4,7 @@
 // nine row-shifted K segments plus the residual 1x1 conv as a tenth.
 #include "internal.h"
 
+#ifdef MMEGO_FFMA_GEN   // fp32 FFMA generation: emulator suite and -DMMEGO_WITH_FFMA test builds only (not in the product library)
 namespace mmego {
 
 namespace {
@@ -99,3 +100,4 @@ void launch_gcn_agg(const float* y, const float* ahat, float* ya, long long F, i
 }
 
 }  // namespace mmego
+#endif  // MMEGO_FFMA_GEN

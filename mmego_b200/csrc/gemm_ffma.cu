@@ -11,6 +11,7 @@
 // gate-interleaved LSTM weight packing one thread holds the i,f,g,o pre-activations of the same hidden unit.
 #include "internal.h"
 
+#ifdef MMEGO_FFMA_GEN   // fp32 FFMA generation: emulator suite and -DMMEGO_WITH_FFMA test builds only (not in the product library)
 namespace mmego {
 
 namespace {
@@ -210,3 +211,4 @@ void launch_gemm(const GemmBatch& b, int nz, int bn, int epi, cudaStream_t st) {
 }
 
 }  // namespace mmego
+#endif  // MMEGO_FFMA_GEN

@@ -465,7 +465,7 @@ void launch_gemm_tc(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtens
         cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
     const int total = p.B * p.rtiles;
     const int grid = total < sm_count ? total : sm_count;
-    ++g_launches;
+    ++t_launches;
     gemm_tc_kernel<BN><<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(a0h, a0l, a1h, a1l, wh, wl, p);
 }
 
@@ -506,6 +506,12 @@ bool tc_pack_gemm(mmego_handle* h, const HostPackedGemm& g, TcGemmW& out) {
         h->owned.push_back(*dst);
         return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
     };
+    // a re-pack (load_state_dict, in-place weight edit) replaces the planes: release the previous ones first
+    handle_free(h, out.whi);
+    handle_free(h, out.wlo);
+    handle_free(h, out.bias);
+    out.whi = out.wlo = nullptr;
+    out.bias = nullptr;
     void *dhi = nullptr, *dlo = nullptr, *db = nullptr;
     if (!up(hi.data(), hi.size() * 2, &dhi) || !up(lo.data(), lo.size() * 2, &dlo) ||
         !up(g.bias.data(), g.bias.size() * 4, &db))
@@ -563,14 +569,14 @@ void tc_gcn_prep(const float* upper, const float* R, const float* t, const float
                  long long F, cudaStream_t st) {
     const long long total = F * kGcnV;
     if (total <= 0) return;
-    ++g_launches;
+    ++t_launches;
     gcn_prep_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(upper, R, t, bn, uh, static_cast<__half*>(yhi),
                                                                            static_cast<__half*>(ylo), F);
 }
 void tc_gcn_prep_raw(const float* x, const float* bn, void* yhi, void* ylo, int B, int T, cudaStream_t st) {
     const long long total = (long long)B * T * kGcnV;
     if (total <= 0) return;
-    ++g_launches;
+    ++t_launches;
     gcn_prep_raw_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, bn, static_cast<__half*>(yhi),
                                                                                static_cast<__half*>(ylo), B, T);
 }
@@ -582,7 +588,7 @@ void tc_gcn_agg(const void* yhi, const void* ylo, const float* ahat, void* ohi, 
     const __half* il = static_cast<const __half*>(ylo);
     __half* oh = static_cast<__half*>(ohi);
     __half* ol = static_cast<__half*>(olo);
-    ++g_launches;
+    ++t_launches;
     if ((C == 32 || C == 64) && CS == C && OS == 2 * C) {
         const int fpb = 256 / (kGcnV * (C / 8));
         long long blocks = (F + fpb - 1) / fpb;

@@ -10,9 +10,16 @@
 
 struct mmego_handle;
 
+// The first-generation fp32 FFMA kernels (exact-fp32 references for A/B numbers, and what the CPU emulator suite runs
+// where the tensor-core paths cannot be emulated) are compiled only into the emulator build and into the test-only
+// library variant (-DMMEGO_WITH_FFMA, tests/_variant_build/).  The product library holds ONE kernel set.
+#if defined(MMEGO_EMUL) || defined(MMEGO_WITH_FFMA)
+#define MMEGO_FFMA_GEN 1
+#endif
+
 namespace mmego {
 
-extern long long g_launches;   // kernels launched by this library (all handles)
+extern thread_local long long t_launches;   // kernels launched by the calling thread (credited to a handle by api.cu: Entry)
 
 // ------------------------------------------------------------------------------------------------
 // model constants (Config/config.py:16-24 of the reference)
@@ -61,6 +68,8 @@ struct GemmBatch {
 };
 // bn: tile width (32, 64, 128); nz: 1 or 2 problems (blockIdx.z)
 void launch_gemm(const GemmBatch& b, int nz, int bn, int epi, cudaStream_t st);
+
+void handle_free(mmego_handle* h, void* p);   // cudaFree + forget a device buffer owned by the handle (api.cu)
 
 // per-device one-shot flag (kernel attributes such as the dynamic shared memory limit are per device)
 inline bool first_use_on_device(bool* flags) {
@@ -119,6 +128,7 @@ struct RawFrames {
     const double* t_R0R;            // [F][3]
     const double* R_ref;            // [3][3]
     const double* orientation_ref;  // [3][3]
+    long long n_frames;             // F
 };
 void launch_snippet_build(const RawFrames& raw, const long long* starts, const int* slot_src, unsigned seed, float* data,
                           float* imu, float* key, float* R, float* t, long long B, int L, int N, cudaStream_t st);
@@ -252,7 +262,8 @@ void tc_gcn_agg(const void* yhi, const void* ylo, const float* ahat, void* ohi, 
 struct ProfSpan {
     std::string name;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    long long launches = 0;
+    long long launches = 0;   // kernels launched by calls on THIS handle
+    int entry_depth = 0;
 };
 
 struct mmego_handle {
@@ -261,10 +272,10 @@ struct mmego_handle {
     int device = 0;
     int sm_count = 148;
     std::string err;
-    long long launches = 0;
+    long long launches = 0;   // kernels launched by calls on THIS handle
+    int entry_depth = 0;
     long long imu_chunk = 2048;
     int imu_gemm = -1;        // -1: pick at first use (1 when the tcgen05 path is available, else 0)
-    int tc_precise_act = 0;
     void* tc_stats = nullptr; // device counters of the dbg & 4 instrumentation
     int tc_dbg = 0;           // experiment switches of lstm_tc.cu (never set in product use)
     int tc_cta_pair = 1;      // H=512 LSTM kernel: 1 = CTA pairs (cta_group::2, M = 256)

@@ -23,10 +23,11 @@ using LL = LowerFrameLayout;
 constexpr int NT = 128;
 // BasePointNet's folded weights (W1..B3, 2.8k floats) in constant memory: immediate FFMA operands, as in point_upper.cu.
 // The three 64x64 projections stay in shared memory (they are indexed per thread).
-constexpr int kMlpFloats = LL::WQ;
-__constant__ float c_mlp[kMlpFloats];
 constexpr int NMAX = 512;      // max points per frame supported by the rank select
 constexpr int LDP = 65;
+#ifdef MMEGO_FFMA_GEN   // fp32 FFMA generation: emulator suite and -DMMEGO_WITH_FFMA test builds only (not in the product library)
+constexpr int kMlpFloats = LL::WQ;
+__constant__ float c_mlp[kMlpFloats];
 
 template <int CINP, int COUT, bool RELU>
 __device__ __forceinline__ void dense(const float* __restrict__ W, const float* __restrict__ b, const float* x,
@@ -209,6 +210,8 @@ __global__ void __launch_bounds__(NT) lower_frame_kernel(float* __restrict__ x, 
     }
 }
 
+
+#endif  // MMEGO_FFMA_GEN
 
 // ================================================================================================================
 // Tensor-core version (default): the same per-frame work on mma.sync m16n8k16 fragments (mma_frag.cuh), fp16 hi/lo
@@ -473,9 +476,9 @@ __global__ void __launch_bounds__(NT, 4) lower_frame_mma_kernel(float* __restric
 
 }  // namespace
 
-size_t lower_frame_smem_bytes() { return sizeof(Smem); }
 int lower_frame_max_points() { return NMAX; }
 
+#ifdef MMEGO_FFMA_GEN   // fp32 FFMA generation: emulator suite and -DMMEGO_WITH_FFMA test builds only (not in the product library)
 void launch_lower_frame(float* x, const float* R, const float* t, const float* kfeat, const float* wblob, float* ak,
                         long long F, int N, int sm_count, cudaStream_t st) {
     if (F <= 0) return;
@@ -487,6 +490,8 @@ void launch_lower_frame(float* x, const float* R, const float* t, const float* k
     long long grid = F < (long long)sm_count * 2 ? F : (long long)sm_count * 2;
     MMEGO_LAUNCH(lower_frame_kernel, dim3((unsigned)grid), dim3(NT), sizeof(Smem), st, x, R, t, kfeat, wblob, ak, F, N);
 }
+
+#endif  // MMEGO_FFMA_GEN
 
 // wblob: LowerMmaLayout (pack_lower_frame_mma)
 void launch_lower_frame_mma(float* x, const float* R, const float* t, const float* kfeat, const float* wblob, float* ak,

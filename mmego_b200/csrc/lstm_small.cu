@@ -29,6 +29,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 // result of that warp was garbage.  __fdividef is MUFU.RCP + FMUL, 2 ulp, and returns 0 for denominators >= 2^126.
 __device__ __forceinline__ float sigmoid_nb(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
 
+#ifdef MMEGO_FFMA_GEN   // fp32 FFMA generation: emulator suite and -DMMEGO_WITH_FFMA test builds only (not in the product library)
 // gx   [S][T][2][256]   input projection incl. biases, column = thread order (w*32 + gate*8 + e)
 // whh  [2][256][64]     recurrent weights, row = thread order
 // h0/c0 [2][S][64] (this layer's slice of the [6,S,64] state) or nullptr for zeros
@@ -118,6 +119,8 @@ __global__ void __launch_bounds__(NTH) lstm_small_kernel(const float* __restrict
     }
 }
 
+
+#endif  // MMEGO_FFMA_GEN
 
 // ================================================================================================================
 // Tensor-core version (default): both GEMMs of the layer on mma.sync m16n8k16 fragments (mma_frag.cuh, fp16 hi/lo
@@ -311,12 +314,15 @@ __global__ void __launch_bounds__(TPC * 128) lstm_rec_mma_kernel(const float* __
 
 }  // namespace
 
+#ifdef MMEGO_FFMA_GEN   // fp32 FFMA generation: emulator suite and -DMMEGO_WITH_FFMA test builds only (not in the product library)
 void launch_lstm_small(const float* gx, const float* whh, const float* h0, const float* c0, float* y, float* hn,
                        float* cn, int S, int T, cudaStream_t st) {
     if (S <= 0 || T <= 0) return;
     dim3 grid((S + SEQ - 1) / SEQ, 2);
     MMEGO_LAUNCH(lstm_small_kernel, grid, dim3(NTH), 0, st, gx, whh, h0, c0, y, hn, cn, S, T);
 }
+
+#endif  // MMEGO_FFMA_GEN
 
 // One H=64 bidirectional layer on mma.sync: x [S*T, In] (row stride ldx) -> gx (workspace [S*T, 512]) -> y [S, T, 128]
 void launch_lstm_small_mma(const float* x, long long ldx, int In, const float* blob, float* gx, const float* h0,

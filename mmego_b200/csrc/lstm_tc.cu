@@ -146,6 +146,14 @@ __device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po
     }
 }
 
+// Experiment switches (skip the cell math / the TMEM drains, cycle counters) exist only in test builds: in the product
+// library they are compiled out, so no option can make the kernel produce wrong results.
+#ifdef MMEGO_DEBUG_SWITCHES
+#define TC_DBG(p) ((p).dbg)
+#else
+#define TC_DBG(p) 0
+#endif
+
 template <int NPASS, int NCTA, int BN, bool MUFU_CELL = (NPASS == 1)>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtensorMap mXlo,
@@ -273,24 +281,24 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
             uint32_t phase = 0;
             uint32_t cc = 0;      // running chunk counter (same sequence in the epilogue warps)
             long long ms_epi = 0, ms_tma = 0, ms_tiles = 0;
-            const long long ms_start = (p.dbg & 4) ? clock64() : 0;
+            const long long ms_start = (TC_DBG(p) & 4) ? clock64() : 0;
             for (int tile = first_item; tile < total_tiles; tile += item_stride) {
-                if (p.dbg & 4) ++ms_tiles;
+                if (TC_DBG(p) & 4) ++ms_tiles;
                 for (int c0 = 0, ci = 0; c0 < kb_total; ++cc, ++ci) {
                     const int clen = ci < 2 ? p.kb_chunk0 : p.kb_chunk;
                     const uint32_t buf = cc % NBUF, bph = (cc / NBUF) & 1;
                     long long tm0 = 0;
-                    if (p.dbg & 4) tm0 = clock64();
+                    if (TC_DBG(p) & 4) tm0 = clock64();
                     mbar_wait(&tempty[buf], bph ^ 1);
                     tc_fence_after();
-                    if (p.dbg & 4) ms_epi += clock64() - tm0;
+                    if (TC_DBG(p) & 4) ms_epi += clock64() - tm0;
                     const uint32_t d_tmem = tmem_base + buf * BN;
                     const int c1 = min(kb_total, c0 + clen);
                     for (int kb = c0; kb < c1; ++kb) {
-                        if (p.dbg & 4) tm0 = clock64();
+                        if (TC_DBG(p) & 4) tm0 = clock64();
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
-                        if (p.dbg & 4) ms_tma += clock64() - tm0;
+                        if (TC_DBG(p) & 4) ms_tma += clock64() - tm0;
                         const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
                         const uint32_t a_lo = a_hi + A_TILE;
                         const uint32_t w_hi = a_hi + C::PLANES * A_TILE;
@@ -325,7 +333,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
                     c0 = c1;
                 }
             }
-            if (p.dbg & 4) {
+            if (TC_DBG(p) & 4) {
                 atomicAdd(p.stats + 4, (unsigned long long)ms_epi);
                 atomicAdd(p.stats + 5, (unsigned long long)ms_tma);
                 atomicAdd(p.stats + 6, (unsigned long long)(clock64() - ms_start));
@@ -362,7 +370,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
                 mbar_wait(&tfull[buf], bph);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + u0);
-                if (!(p.dbg & 2))
+                if (!(TC_DBG(p) & 2))
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {        // one gate at a time keeps the temporaries small
                     uint32_t r0[kUnitsPerEpiWarp];
@@ -385,7 +393,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
                 }
                 c0 += clen;
             }
-            if (p.dbg & 1) continue;
+            if (TC_DBG(p) & 1) continue;
             // ---- LSTM cell on the register-resident pre-activations (bias from shared memory: warp-wide broadcast reads)
             // The epilogue warps run at 112 registers with 64 of them holding the accumulators, and shared memory leaves almost
             // no L1, so a spilled register costs an L2 round trip: the 16 units are processed in two halves of 8 whose
@@ -817,6 +825,12 @@ static bool pack_variant(mmego_handle* h, const StateDict& sd, const std::string
         h->owned.push_back(*dst);
         return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
     };
+    // a re-pack (load_state_dict, in-place weight edit) replaces the planes: release the previous ones first
+    handle_free(h, out.whi);
+    handle_free(h, out.wlo);
+    handle_free(h, out.bias);
+    out.whi = out.wlo = nullptr;
+    out.bias = nullptr;
     void *dhi = nullptr, *dlo = nullptr, *db = nullptr;
     if (!up(hi.data(), hi.size() * 2, &dhi) || !up(lo.data(), lo.size() * 2, &dlo) || !up(bias.data(), bias.size() * 4, &db))
         return false;
@@ -915,7 +929,7 @@ int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const
         p.tt1 = T - 1 - step;
         p.tp0 = step > 0 ? step - 1 : 0;
         p.tp1 = step > 0 ? p.tt1 + 1 : p.tt1;
-        ++g_launches;
+        ++t_launches;
 #define MMEGO_STEP(NP, NC, BNV) launch_step<NP, NC, BNV>(grid, st, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p)
         if (npass == 3) { if (pair) MMEGO_STEP(3, 2, 256); else MMEGO_STEP(3, 1, 256); }
         else { if (pair) MMEGO_STEP(1, 2, 256); else MMEGO_STEP(1, 1, 256); }
@@ -940,7 +954,7 @@ void tc_imu_fc1(const float* imu, const float* fc1_mma, void* uhi, void* ulo, lo
         cudaFuncSetAttribute(imu_fc1_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     long long blocks = (rows + 127) / 128;
     if (blocks > 4LL * sm_count) blocks = 4LL * sm_count;
-    ++g_launches;
+    ++t_launches;
     imu_fc1_mma_kernel<<<(unsigned)blocks, 256, smem, st>>>(imu, fc1_mma, static_cast<__half*>(uhi),
                                                             static_cast<__half*>(ulo), rows, lo_round_add(lo_drop),
                                                             lo_round_mask(lo_drop));
@@ -948,7 +962,7 @@ void tc_imu_fc1(const float* imu, const float* fc1_mma, void* uhi, void* ulo, lo
 void tc_imu_pool(const void* yhi, const void* ylo, const float* attn, void* shi, void* slo, long long F, int n,
                  int lo_drop, cudaStream_t st) {
     if (F <= 0) return;
-    ++g_launches;
+    ++t_launches;
     imu_pool_split_kernel<<<(unsigned)((F + POOL_WARPS - 1) / POOL_WARPS), POOL_WARPS * 32, 0, st>>>(
         static_cast<const __half*>(yhi), static_cast<const __half*>(ylo), attn, static_cast<__half*>(shi),
         static_cast<__half*>(slo), F, n, lo_round_add(lo_drop), lo_round_mask(lo_drop));
@@ -964,13 +978,13 @@ void tc_imu_decode(const void* ghi, const void* glo, const float* fc2, float* R,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long blocks = (F + 15) / 16;
     if (blocks > 2LL * sms) blocks = 2LL * sms;
-    ++g_launches;
+    ++t_launches;
     imu_decode_split_kernel<<<(unsigned)blocks, 256, smem, st>>>(static_cast<const __half*>(ghi),
                                                                  static_cast<const __half*>(glo), fc2, R, t, F);
 }
 void tc_unsplit(const void* hi, const void* lo, float* out, long long n, cudaStream_t st) {
     if (n <= 0) return;
-    ++g_launches;
+    ++t_launches;
     unsplit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<const __half*>(hi),
                                                                 static_cast<const __half*>(lo), out, n);
 }

@@ -15,6 +15,7 @@ namespace mmego {
 
 namespace {
 
+#ifdef MMEGO_FFMA_GEN   // fp32 FFMA generation: emulator suite and -DMMEGO_WITH_FFMA test builds only (not in the product library)
 using UL = UpperPointLayout;
 constexpr int PT = 128;          // threads per CTA = points per chunk
 
@@ -140,6 +141,8 @@ __global__ void __launch_bounds__(PT) upper_point_kernel(float* __restrict__ x, 
     }
 }
 
+
+#endif  // MMEGO_FFMA_GEN
 
 // ================================================================================================================
 // Tensor-core version (default): the same network on mma.sync m16n8k16 fragments (mma_frag.cuh), fp16 hi/lo split
@@ -325,6 +328,7 @@ __global__ void __launch_bounds__(MT, 2) upper_point_mma_kernel(float* __restric
 
 }  // namespace
 
+#ifdef MMEGO_FFMA_GEN   // fp32 FFMA generation: emulator suite and -DMMEGO_WITH_FFMA test builds only (not in the product library)
 size_t upper_point_smem_bytes() { return (size_t)(64 * RED_LD + 128 + 8 + 12 + 4) * sizeof(float); }
 
 void launch_upper_point(float* x, const float* R, const float* t, const float* wblob, float* g, float* gw,
@@ -340,6 +344,8 @@ void launch_upper_point(float* x, const float* R, const float* t, const float* w
     MMEGO_LAUNCH(upper_point_kernel, dim3((unsigned)grid), dim3(PT), upper_point_smem_bytes(), st, x, R, t, wblob, g,
                  gw, F, N);
 }
+
+#endif  // MMEGO_FFMA_GEN
 
 // wblob: UpperMmaLayout (pack_upper_point_mma)
 void launch_upper_point_mma(float* x, const float* R, const float* t, const float* wblob, float* g, float* gw,

@@ -63,6 +63,14 @@ __global__ void __launch_bounds__(ST) snippet_build_kernel(RawFrames raw, const 
     const long long r = blockIdx.x;                      // output frame b*L + l
     const long long f = starts[r / L] + (r % L);         // source frame
     const int tid = threadIdx.x;
+    if (f < 0 || f >= raw.n_frames) {                    // window outside the raw table: defined output, no stray reads
+        for (int s = tid; s < N * 6; s += ST) data[r * (long long)N * 6 + s] = 0.f;
+        for (int s = tid; s < 20 * 15; s += ST) imu[r * 300 + s] = 0.f;
+        for (int s = tid; s < 63; s += ST) key[r * 63 + s] = 0.f;
+        if (tid < 9) R[r * 9 + tid] = 0.f;
+        if (tid < 3) t[r * 3 + tid] = 0.f;
+        return;
+    }
     const long long p0 = raw.pt_start[f];
     const int n = (int)(raw.pt_start[f + 1] - p0);
     // ---- radar cloud ---------------------------------------------------------------------------------------

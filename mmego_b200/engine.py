@@ -34,18 +34,19 @@ class NativeNet(nn.Module):
 
     def __init__(self):
         super().__init__()
-        self._packed_key = None
-        self._packed_handle = None
 
     def _weights_key(self):
         return tuple((id(t), t._version, t.data_ptr()) for t in self.state_dict(keep_vars=True).values())
 
     def _sync(self, device) -> "_capi.Handle":
+        """A handle holds ONE packed weight set per net type and all modules on a GPU share the handle, so the handle
+        records which module (and which version of its tensors) each slot currently holds: two UpperNet instances used
+        alternately re-upload on every switch instead of silently running with each other's weights."""
         h = get_handle(device)
-        key = self._weights_key()
-        if self._packed_handle is not h or key != self._packed_key:
+        key = (id(self), self._weights_key())
+        if h.weights_owner.get(self._net_id) != key:
             h.set_weights(self._net_id, self.state_dict())
-            self._packed_key, self._packed_handle = key, h
+            h.weights_owner[self._net_id] = key
         return h
 
     @staticmethod

@@ -63,7 +63,12 @@ class MMEgoPipeline:
         self.lower_net.load_state_dict(lower_state if lower_state is not None else load_checkpoint(Config.model_lower_path))
         for m in (self.imu_net, self.upper_net, self.lower_net):
             m.to(self.device).eval()
+        if body_index_mode not in ("ref", "per_snippet"):
+            raise MMEgoError(f"body_index_mode must be 'ref' or 'per_snippet' (got {body_index_mode!r})")
         self.body_mode = _capi.BODY_REF if body_index_mode == "ref" else _capi.BODY_PER_SNIPPET
+        # the drop-in modules follow the pipeline's mode ("ref" = the reference's initial_body[r % B] of ONE call)
+        self.upper_net.body_index_mode = body_index_mode
+        self.lower_net.body_index_mode = body_index_mode
         self.handle = None
         self._sync()
 

@@ -12,8 +12,7 @@ import torch
 
 from .Net import _layout
 
-_SKELETON_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
-                              "skeleton.npy")
+_SKELETON_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "skeleton.npy")
 
 
 def default_skeleton() -> np.ndarray:

@@ -85,9 +85,36 @@ def run_reference_chain(up_net, lo_net, Config, data, skl, R, t, bs):
     return {k: torch.cat(v).numpy() for k, v in outs.items()}
 
 
+SWEEP_SHAPES = [(2, 40, 256), (1, 80, 128), (2, 20, 512)]       # (B, L, N): config 5 of BASELINE.json (N, L up to 4x)
+SWEEP_GCN_T = [(2, 40), (1, 80)]
+
+
+def sweep_pins(up_net, lo_net, Config, O):
+    """Pins F/G: the reference's classes accept any L and N (Net/GCN.py:103-117 pads by kernel size only; the point
+    encoders are 1x1 convolutions; Net/Lower_Net.py:216-227 keeps Config.lower_pc_no = 64 of N points), so the sweep
+    shapes get reference-generated vectors of their own.  One reference call per shape (B = 2: the initial_body[r % B]
+    quirk is visible); (R, t) are the synthetic generator's poses."""
+    skeleton = np.load(os.path.join(GOLD, "skeleton.npy"))
+    for B, L, N in SWEEP_SHAPES:
+        sb = O.synth_batch(B, L=L, N=N, n_imu=1, seed=500 + L + N, skeleton=skeleton, distinct_skeletons=True)
+        o = run_reference_chain(up_net, lo_net, Config, sb["data"], sb["skl"], sb["R"], sb["t"], B)
+        keep = {k: o[k] for k in ("upper_l", "q_upper", "gw", "hn", "cn", "lower_l", "q_lower", "pred")}
+        np.savez_compressed(os.path.join(GOLD, f"sweep_L{L}_N{N}.npz"), data=sb["data"].numpy(), skl=sb["skl"].numpy(),
+                            R=sb["R"].numpy(), t=sb["t"].numpy(), **keep)
+        print("sweep pin", (B, L, N), "upper_l", keep["upper_l"].shape)
+    for B, T in SWEEP_GCN_T:
+        g = torch.Generator().manual_seed(40 + T)
+        xg = torch.randn(B, 3, T, 15, 1, generator=g)
+        with torch.no_grad():
+            kf = lo_net.keyEncoder.gcn.extract_feature(xg)
+        np.savez_compressed(os.path.join(GOLD, f"gcn_T{T}.npz"), x=xg.numpy(), out=kf.numpy())
+        print("gcn pin T =", T, tuple(kf.shape))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full-sample", action="store_true", help="also freeze all 835 sample snippets (large)")
+    ap.add_argument("--sweep-only", action="store_true", help="only (re)generate the non-config-shape pins (F, G)")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -98,6 +125,10 @@ def main():
     up_net.load_state_dict(torch.load(Config.model_upper_path, map_location="cpu", weights_only=True))
     lo_net.load_state_dict(torch.load(Config.model_lower_path, map_location="cpu", weights_only=True))
     up_net.eval(), lo_net.eval()
+
+    if args.sweep_only:
+        sweep_pins(up_net, lo_net, Config, O)
+        return
 
     # ---- sample data (seeded; F9) --------------------------------------------------------------
     from Util.Universal_Util.Dataset_sample import PosePC
@@ -158,6 +189,8 @@ def main():
     with torch.no_grad():
         kf = lo_net.keyEncoder.gcn.extract_feature(xg)
     np.savez_compressed(os.path.join(GOLD, "gcn2.npz"), x=xg.numpy(), out=kf.numpy())
+
+    sweep_pins(up_net, lo_net, Config, O)
 
     if args.full_sample:
         np.savez_compressed(os.path.join(ROOT, "Resource", "Sample_data_frozen", "sample835_seed0.npz"),

@@ -14,7 +14,27 @@ from oracle import mmego_oracle as O
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 POS_TOL = 1e-5          # metres  (= 1e-3 cm)
-ROT_TOL = 2e-5          # rotation-matrix entries (1e-3 deg = 1.7e-5 rad)
+ANG_TOL = 1e-3          # degrees: geodesic angle between a computed rotation and its reference (BASELINE.json north_star)
+ROT_TOL = 2e-5          # rotation-matrix entries: a looser secondary bound kept for non-rotation uses (see rot_angle_deg)
+
+
+def rot_angle_deg(a, b):
+    """Largest geodesic angle (degrees) between corresponding 3x3 rotations of a and b [..., 3, 3], in float64.
+    theta = acos((tr(A^T B) - 1) / 2) cannot be evaluated as written at this scale: 1 - cos(theta) = theta^2 / 2 is
+    1.5e-10 for theta = 1e-3 deg, far below the ~1e-7 by which fp32 matrices miss orthonormality (the acos form returns
+    ~2e-2 deg for two fp32 roundings of the SAME rotation).  The same angle is therefore taken from the first-order
+    quantities: atan2(sin, cos) with sin = |vee(M - M^T)| / 2, cos = (tr M - 1) / 2, M = A^T B; and from the chord
+    2 asin(|A - B|_F / (2 sqrt 2)), which also sees non-rotational (symmetric) differences.  The LARGER is returned."""
+    A = torch.as_tensor(a).detach().cpu().double().reshape(-1, 3, 3)
+    B = torch.as_tensor(b).detach().cpu().double().reshape(-1, 3, 3)
+    M = A.transpose(1, 2) @ B
+    sk = M - M.transpose(1, 2)
+    sin = 0.5 * torch.stack((sk[:, 2, 1], sk[:, 0, 2], sk[:, 1, 0]), dim=1).norm(dim=1)
+    cos = 0.5 * (M.diagonal(dim1=1, dim2=2).sum(dim=1) - 1.0)
+    ang_geo = torch.atan2(sin, cos)
+    chord = (A - B).pow(2).sum(dim=(1, 2)).sqrt()
+    ang_chord = 2.0 * torch.asin(torch.clamp(chord / (2.0 * 2.0 ** 0.5), max=1.0))
+    return float(torch.rad2deg(torch.maximum(ang_geo, ang_chord)).max())
 
 
 def golden(name):
@@ -61,7 +81,7 @@ def check_upper_lower_golden(h, name, sl=None):
         skl, R, t = dev(h, g["skl"][s]), dev(h, g["R"][s]), dev(h, g["t"][s])
         l, q, gw, hn, cn = h.upper_forward(x, h0, h0.clone(), skl, R, t)
         assert maxerr(l, g["upper_l"][s]) < POS_TOL
-        assert maxerr(q, g["q_upper"][s]) < ROT_TOL
+        assert rot_angle_deg(q, g["q_upper"][s]) < ANG_TOL
         assert maxerr(gw.reshape(b, 20, -1), g["gw"][s]) < 1e-5
         assert maxerr(hn.permute(1, 0, 2), g["hn"][s]) < 2e-5
         assert maxerr(cn.permute(1, 0, 2), g["cn"][s]) < 5e-5
@@ -78,14 +98,38 @@ def check_upper_lower_golden(h, name, sl=None):
         # sort picks arbitrarily; the library's rule (lowest slot wins) is checked exactly against the oracle
         lo_o, ql_o, _ = O.lower_forward(lo_sd, g["upper_l"][s], g["x1"][s], g["skl"][s], g["R"][s], g["t"][s])
         assert maxerr(ll, lo_o) < POS_TOL
-        assert maxerr(ql, ql_o) < ROT_TOL * 2
+        assert rot_angle_deg(ql, ql_o) < ANG_TOL
         assert maxerr(ll, g["lower_l"][s]) < (POS_TOL if one_call else 5e-3)
         pred = h.assemble_metrics(l, ll)
         assert maxerr(pred, O.assemble(l.cpu(), ll.cpu())) == 0.0
 
 
-def check_gcn_golden(h, gcn_gemm=None):
-    g = golden("gcn2.npz")
+SWEEP_GOLDENS = ("sweep_L40_N256.npz", "sweep_L80_N128.npz", "sweep_L20_N512.npz")
+GCN_GOLDENS = ("gcn2.npz", "gcn_T40.npz", "gcn_T80.npz")
+
+
+def check_sweep_golden(h, name):
+    """Upper_Net -> Lower_Net at a non-config (L, N) against vectors produced by ONE call of the reference's own classes
+    (oracle/make_golden.py sweep_pins; B = 2 snippets with distinct skeletons where B > 1)."""
+    g = golden(name)
+    B, L, N, _ = g["data"].shape
+    x = dev(h, g["data"].clone())
+    h0 = torch.zeros(6, B, 64, device=h.device)
+    skl, R, t = dev(h, g["skl"]), dev(h, g["R"]), dev(h, g["t"])
+    l, q, gw, hn, cn = h.upper_forward(x, h0, h0.clone(), skl, R, t)
+    errs = dict(upper=maxerr(l, g["upper_l"]), q_upper_deg=rot_angle_deg(q, g["q_upper"]),
+                gw=maxerr(gw.reshape(B, L, -1), g["gw"]), hn=maxerr(hn.permute(1, 0, 2), g["hn"]))
+    ll, ql = h.lower_forward(dev(h, g["upper_l"]), x, skl, R, t)          # x: the once-transformed cloud (in place)
+    errs.update(lower=maxerr(ll, g["lower_l"]), q_lower_deg=rot_angle_deg(ql, g["q_lower"]))
+    assert errs["upper"] < POS_TOL and errs["lower"] < POS_TOL, errs
+    assert errs["q_upper_deg"] < ANG_TOL and errs["q_lower_deg"] < ANG_TOL, errs
+    assert errs["gw"] < 1e-5 and errs["hn"] < 2e-5, errs
+    assert maxerr(h.assemble_metrics(l, ll), O.assemble(l.cpu(), ll.cpu())) == 0.0
+    return errs
+
+
+def check_gcn_golden(h, gcn_gemm=None, name="gcn2.npz"):
+    g = golden(name)
     if gcn_gemm is not None:
         h.set_option("gcn_gemm", gcn_gemm)
     try:
@@ -99,11 +143,12 @@ def check_gcn_golden(h, gcn_gemm=None):
     return err
 
 
-# IMU_Net precision modes of the library ("imu_gemm" option) and their tolerances on (R entries, t metres, joint metres).
+# IMU_Net precision modes of the library ("imu_gemm" option) and their tolerances on (R geodesic angle in degrees,
+# t metres, joint metres).
 # 0 = fp32 FFMA, 1 = tcgen05 fp16x3 (default; fp32-grade), 2 = tcgen05 single-pass fp16 (the "reduced precision" mode that
 # BASELINE.json asks to be reported separately).  The seeded stand-in IMU weights produce 6D vectors of norm ~0.05, so the
 # Gram-Schmidt normalisation amplifies upstream error ~20x; a trained checkpoint (norm ~1) would sit far below these.
-IMU_MODE_TOL = {0: (ROT_TOL, POS_TOL, POS_TOL), 1: (ROT_TOL, POS_TOL, POS_TOL), 2: (2e-3, 1e-4, 3e-3)}
+IMU_MODE_TOL = {0: (ANG_TOL, POS_TOL, POS_TOL), 1: (ANG_TOL, POS_TOL, POS_TOL), 2: (0.15, 1e-4, 3e-3)}
 
 
 def check_imu_golden(h, tag="synth", nb=1, mode=None):
@@ -116,7 +161,7 @@ def check_imu_golden(h, tag="synth", nb=1, mode=None):
     finally:
         if mode is not None:
             h.set_option("imu_gemm", 1 if h.require_cuda else 0)
-    er, et = maxerr(R, g["R_" + tag][:nb]), maxerr(t, g["t_" + tag][:nb])
+    er, et = rot_angle_deg(R, g["R_" + tag][:nb]), maxerr(t, g["t_" + tag][:nb])
     assert er < rt and et < tt, (er, et)
     return er, et
 
@@ -155,8 +200,14 @@ def check_metrics(h):
     assert np.allclose(sums.cpu().numpy(), 2 * got, rtol=1e-12)
 
 
-def check_pipeline_vs_oracle(h, B=2, L=20, N=128, n_imu=20, seed=11, distinct=True, imu_seed=0, mode=None, pos_tol=None):
-    """Whole chain on synthetic snippets vs the oracle pipeline (IMU_Net with the seeded stand-in weights)."""
+def check_pipeline_vs_oracle(h, B=2, L=20, N=128, n_imu=20, seed=11, distinct=True, imu_seed=0, mode=None, pos_tol=None,
+                             truth64=False):
+    """Whole chain on synthetic snippets vs the oracle pipeline (IMU_Net with the seeded stand-in weights).
+
+    truth64: additionally evaluate the oracle in float64 and judge the library against THAT: the fp32 oracle is itself
+    only one fp32 evaluation order, and on shapes where the stand-in IMU_Net's 6D outputs are tiny its own distance to
+    the float64 result (`noise32_*`) reaches several 1e-6 m.  The bounds then read: library-vs-float64 error below the
+    contract tolerance, or -- where the fp32 oracle itself is that far out -- within 3x the fp32 oracle's own error."""
     sb = O.synth_batch(B, L=L, N=N, n_imu=n_imu, seed=seed, distinct_skeletons=distinct)
     up_sd, lo_sd = checkpoints()
     ref = O.pipeline(O.synth_imu_state_dict(imu_seed), up_sd, lo_sd, sb["imu"], sb["data"], sb["skl"])
@@ -175,14 +226,27 @@ def check_pipeline_vs_oracle(h, B=2, L=20, N=128, n_imu=20, seed=11, distinct=Tr
     finally:
         if mode is not None:
             h.set_option("imu_gemm", 1 if h.require_cuda else 0)
-    errs = dict(R=maxerr(outs["R"], ref["R"]), t=maxerr(outs["t"], ref["t"]), upper=maxerr(outs["upper_l"], ref["upper_l"]),
+    errs = dict(R_deg=rot_angle_deg(outs["R"], ref["R"]), R=maxerr(outs["R"], ref["R"]), t=maxerr(outs["t"], ref["t"]),
+                upper=maxerr(outs["upper_l"], ref["upper_l"]),
                 lower=maxerr(outs["lower_l"], ref["lower_l"]), pred=maxerr(pred, ref["pred"]),
                 x=maxerr(x, ref["x_after_lower"]))
-    assert errs["R"] < rt and errs["t"] < tt, errs
+    if truth64:
+        ref64 = O.pipeline(O.synth_imu_state_dict(imu_seed), up_sd, lo_sd, sb["imu"], sb["data"], sb["skl"], dtype=torch.float64)
+        errs.update(R_deg64=rot_angle_deg(outs["R"], ref64["R"]), upper64=maxerr(outs["upper_l"], ref64["upper_l"]),
+                    lower64=maxerr(outs["lower_l"], ref64["lower_l"]),
+                    noise32_R_deg=rot_angle_deg(ref["R"], ref64["R"]), noise32_upper=maxerr(ref["upper_l"], ref64["upper_l"]),
+                    noise32_lower=maxerr(ref["lower_l"], ref64["lower_l"]))
+        assert errs["R_deg64"] < max(rt, 3 * errs["noise32_R_deg"]) and errs["t"] < tt, errs
+        assert errs["upper64"] < max(POS_TOL, 3 * errs["noise32_upper"]), errs
+        assert errs["lower64"] < max(POS_TOL, 3 * errs["noise32_lower"]), errs
+        assert errs["x"] < 8 * max(float(np.deg2rad(rt)), errs["R"]), errs
+        assert sums.cpu().numpy()[43] == B * L
+        return pred, errs
+    assert errs["R_deg"] < rt and errs["t"] < tt, errs
     assert errs["upper"] < pt and errs["pred"] < pt, errs
     # the cloud left behind in x went through R(R(p - t) - t) with |p| up to ~3 m, so it carries up to ~2 |p| times the
     # error of R; it is a side effect, not a joint position, and gets the correspondingly scaled bound
-    assert errs["x"] < 6 * max(rt, errs["R"]), errs
+    assert errs["x"] < 8 * max(float(np.deg2rad(rt)), errs["R"]), errs
     # a point whose x-key sits within the mode's error of the 64th/65th boundary may swap in the top-64 set; in the
     # fp32-grade modes that must not happen on these seeds
     assert errs["lower"] < (pt if (mode is None or mode < 2) else 10 * pt), errs

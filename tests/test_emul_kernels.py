@@ -36,8 +36,14 @@ def test_upper_lower_real_sample(handle):
     P.check_upper_lower_golden(handle, "sample16.npz", sl=[slice(0, 1), slice(7, 8)])
 
 
-def test_gcn(handle):
-    P.check_gcn_golden(handle)
+@pytest.mark.parametrize("name", P.GCN_GOLDENS)
+def test_gcn(handle, name):
+    P.check_gcn_golden(handle, name=name)
+
+
+def test_upper_lower_sweep_shape(handle):
+    # (L, N) = (20, 512): 4x the config's point count, against the reference's own classes
+    P.check_sweep_golden(handle, "sweep_L20_N512.npz")
 
 
 def test_nan_inputs_stay_in_their_snippet(handle):
@@ -59,6 +65,7 @@ def test_imu_golden(handle):
 def test_pipeline_ragged_shapes(handle):
     # L, N, n_imu away from the config values; B*L not a multiple of any tile; distinct skeletons (F8)
     P.check_pipeline_vs_oracle(handle, B=3, L=5, N=70, n_imu=3, seed=21)
+    P.check_pipeline_vs_oracle(handle, B=3, L=5, N=70, n_imu=3, seed=21, truth64=True)      # judged against float64
 
 
 def test_pipeline_many_snippets(handle):
@@ -139,3 +146,23 @@ def test_infer_host_chunk_pipeline_matches_device_path(handle):
         handle.set_option("host_chunk", 2048)
     assert torch.equal(pred_h, pred_d)
     assert sums[43].item() == 22
+
+
+def test_boundary_validates_sizes_before_the_library_reads_them(handle):
+    """The C entry points trust their sizes; the ctypes layer checks everything they will read."""
+    from oracle import mmego_oracle as O
+    sb = O.synth_batch(2, L=3, N=64, n_imu=2, seed=1)
+    with pytest.raises(_capi.MMEgoError, match="initial_body"):        # a shard passing its LOCAL skeletons with the global B
+        handle.pipeline_forward(sb["imu"], sb["data"].clone(), sb["skl"], b_offset=2, B_global=4)
+    with pytest.raises(_capi.MMEgoError, match="imu must be"):
+        handle.pipeline_forward(sb["imu"][:1].contiguous(), sb["data"].clone(), sb["skl"])
+    with pytest.raises(_capi.MMEgoError, match="target must be"):
+        handle.pipeline_forward(sb["imu"], sb["data"].clone(), sb["skl"], torch.zeros(2, 3, 20, 3), torch.zeros(46, dtype=torch.float64))
+    with pytest.raises(_capi.MMEgoError, match="initial_body"):
+        handle.infer_host(sb["imu"], sb["data"], sb["skl"][:1].contiguous())
+    import numpy as np
+    z = dict(np.load(os.path.join(P.GOLDEN, "raw_subset.npz")))
+    raw = {k: torch.from_numpy(np.ascontiguousarray(z[k])) for k in _capi.RawFramesStruct.DTYPES}
+    n_frames = raw["pt_start"].numel() - 1
+    with pytest.raises(_capi.MMEgoError, match="raw frames"):
+        handle.build_snippets(raw, torch.tensor([n_frames - 5], dtype=torch.int64))

@@ -23,9 +23,11 @@ def test_graph_adjacency_matches_checkpoint_buffer(checkpoints):
     assert _maxerr(torch.from_numpy(O.graph_adjacency()).float(), lo["keyEncoder.gcn.A"]) < 1e-7
 
 
-def test_gcn_extract_feature(golden_dir, checkpoints):
+@pytest.mark.parametrize("name", ["gcn2.npz", "gcn_T40.npz", "gcn_T80.npz"])
+def test_gcn_extract_feature(golden_dir, checkpoints, name):
+    """T = 20 (config) and T = 40 / 80 (sweep): the reference's GCN.Model accepts any T (Net/GCN.py:103-117)."""
     _, lo = checkpoints
-    g = _load(golden_dir, "gcn2.npz")
+    g = _load(golden_dir, name)
     sd = {k[len("keyEncoder.gcn."):]: v for k, v in lo.items() if k.startswith("keyEncoder.gcn.")}
     out = O.gcn_extract_feature(sd, g["x"])
     assert out.shape == g["out"].shape
@@ -62,6 +64,24 @@ def test_upper_lower_against_reference(golden_dir, checkpoints, name):
         assert _maxerr(lo_s, g["lower_l"][sl]) < (1e-5 if one_call else 5e-3)
         pred = O.assemble(l, lo)
         assert _maxerr(pred, g["pred"][sl]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["sweep_L40_N256.npz", "sweep_L80_N128.npz", "sweep_L20_N512.npz"])
+def test_upper_lower_sweep_shapes_against_reference(golden_dir, checkpoints, name):
+    """Non-config (L, N): the oracle is pinned to the reference's own classes there too (one reference call per shape)."""
+    up_sd, lo_sd = checkpoints
+    g = _load(golden_dir, name)
+    B = g["data"].shape[0]
+    h0 = torch.zeros(6, B, 64)
+    l, q, w, hn, cn, x1 = O.upper_forward(up_sd, g["data"], h0, h0, g["skl"], g["R"], g["t"])
+    assert _maxerr(l, g["upper_l"]) < 5e-6
+    assert _maxerr(q, g["q_upper"]) < 2e-5
+    assert _maxerr(w.reshape(B, g["data"].shape[1], -1), g["gw"]) < 1e-5
+    assert _maxerr(hn.permute(1, 0, 2), g["hn"]) < 1e-5
+    lo, ql, _ = O.lower_forward(lo_sd, g["upper_l"], x1, g["skl"], g["R"], g["t"], tie_rule="torch_cpu")
+    assert _maxerr(lo, g["lower_l"]) < 1e-5
+    assert _maxerr(ql, g["q_lower"]) < 5e-5
+    assert _maxerr(O.assemble(l, lo), g["pred"]) < 1e-5
 
 
 def test_body_index_quirk_is_visible(golden_dir, checkpoints):
