@@ -326,6 +326,9 @@ def main():
     ap.add_argument("--cpu-snippets", type=int, default=128, help="snippets per CPU-baseline step (bounded sample; 128 = best CPU batch)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-config1", action="store_true", help="skip the 835-sample-snippet record (config 1)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = --batch snippets PER GPU (default, config 3 per GPU); strong = --batch snippets in total, "
+                         "split contiguously over the GPUs (config 4 of BASELINE.json)")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (repeatable)")
     ap.add_argument("--no-half", action="store_true", help="skip the extra pass in single-pass fp16 mode")
     ap.add_argument("--imu-gemm", type=int, default=None, help="0 fp32 FFMA, 1 tcgen05 fp16x3, 2 tcgen05 fp16 (default: library default)")
@@ -358,8 +361,16 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.batch
-    Bg = B * world                                   # weak scaling: every rank owns B snippets
+    strong = args.scaling == "strong" and world > 1
+    if strong:
+        from mmego_b200.pipeline import shard_bounds
+        Bg = args.batch                              # strong scaling: the SAME global batch, split contiguously on dim 0
+        lo_, hi_ = shard_bounds(Bg, world, rank)
+        B = hi_ - lo_
+    else:
+        B = args.batch
+        Bg = B * world                               # weak scaling: every rank owns B snippets
+        lo_ = 0
     pipe = MMEgoPipeline(dev, imu_state=None)
     if args.imu_gemm is not None:
         pipe.handle.set_option("imu_gemm", args.imu_gemm)
@@ -367,14 +378,19 @@ def main():
         k, v = kv.split("=")
         pipe.handle.set_option(k, int(v))
     # this rank's shard of the global synthetic batch (seed depends on the rank; same distribution)
-    sb = synth.batch(B, L=L, N=N_PTS, n_imu=N_IMU, seed=1234 + rank)
+    if strong:      # every rank generates the global batch and keeps its slice; skeletons stay global (initial_body[r % B_global])
+        sb = synth.batch(Bg, L=L, N=N_PTS, n_imu=N_IMU, seed=1234)
+        sb = dict(imu=sb["imu"][lo_:hi_].contiguous(), data=sb["data"][lo_:hi_].contiguous(), skl=sb["skl"])
+    else:
+        sb = synth.batch(B, L=L, N=N_PTS, n_imu=N_IMU, seed=1234 + rank)
+    fwd_kw = dict(b_offset=lo_, B_global=Bg) if strong else {}
     imu_h, data_h, skl_h = sb["imu"].pin_memory(), sb["data"].pin_memory(), sb["skl"].pin_memory()
     imu_d, data0_d, skl_d = imu_h.to(dev), data_h.to(dev), skl_h.to(dev)
     data_d = torch.empty_like(data0_d)
     sums_d = torch.zeros(SUMS_LEN, dtype=torch.float64, device=dev)
     # synthetic ground truth: first prediction + 3 cm noise
     data_d.copy_(data0_d)
-    pred0 = pipe.forward(imu_d, data_d, skl_d)
+    pred0 = pipe.forward(imu_d, data_d, skl_d, **fwd_kw)
     target_h = synth.target_like(pred0, seed=99 + rank).contiguous().pin_memory()
     target_d = target_h.to(dev)
     torch.cuda.synchronize()
@@ -383,13 +399,13 @@ def main():
         # the in-place Transform2H mutates the cloud: every step starts from a fresh copy of the resident input
         data_d.copy_(data0_d)
         sums_d.zero_()
-        pred = pipe.forward(imu_d, data_d, skl_d, target_d, sums_d)
+        pred = pipe.forward(imu_d, data_d, skl_d, target_d, sums_d, **fwd_kw)
         return pred, sums_d
 
     runner = ShardedRunner(lambda lo, hi, Bglobal: step_fn(lo, hi, Bglobal), world, rank)
 
     def one_step():
-        # every rank holds exactly its own B snippets, so the shard bounds are (rank*B, (rank+1)*B)
+        # every rank holds exactly its own shard of the Bg snippets (weak: B each; strong: shard_bounds of --batch)
         return runner.run(Bg)
 
     def barrier():
@@ -410,22 +426,34 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for _ in range(steps):
-            pred, sums = one_step()
+        if world > 1:
+            # the gather / all-reduce of step i runs on a side stream while step i+1 computes (two result slots):
+            # no rank waits inside a step for the slowest GPU of the box; every step's result is collected
+            for i in range(steps):
+                runner.submit(Bg)
+                if i >= 1:
+                    pred, sums = runner.collect()
+            pred, sums = runner.collect()
+        else:
+            for _ in range(steps):
+                pred, sums = one_step()
         e1.record()
         barrier()
         ms_ = e0.elapsed_time(e1)
         launches_ = pipe.launch_count() - n0
+        coll_ms_ = runner.collective_ms() / steps if world > 1 else 0.0
         prof_ = pipe.handle.profile_read()
         pipe.handle.profile_end()
         clocks_ = sampler.stop() if rank == 0 else None
         t_ms = torch.tensor([ms_], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        timed_pass.collective_ms = coll_ms_
         return float(t_ms.item()), launches_, prof_, clocks_, sums
 
     mode = args.imu_gemm if args.imu_gemm is not None else 1
     ms, launches, prof, clocks, sums = timed_pass(args.steps, args.warmup)
+    collective_ms = timed_pass.collective_ms
     ms_per_step = ms / args.steps
     frames = Bg * L
     value = frames / (ms_per_step * 1e-3)
@@ -439,14 +467,14 @@ def main():
         out_pred = torch.empty(B, L, 21, 3, dtype=torch.float32).pin_memory()
         out_sums = torch.zeros(SUMS_LEN, dtype=torch.float64).pin_memory()
         for _ in range(2):
-            pipe.infer_host(imu_h, data_h, skl_h, target_h, out_pred=out_pred, out_sums=out_sums)
+            pipe.infer_host(imu_h, data_h, skl_h, target_h, out_pred=out_pred, out_sums=out_sums, **fwd_kw)
         barrier()
         k2 = max(3, min(args.steps, 8))
         step_s = []
         t0 = time.perf_counter()
         for _ in range(k2):
             ts = time.perf_counter()
-            pred_h, sums_h = pipe.infer_host(imu_h, data_h, skl_h, target_h, out_pred=out_pred, out_sums=out_sums)   # synchronous on return
+            pred_h, sums_h = pipe.infer_host(imu_h, data_h, skl_h, target_h, out_pred=out_pred, out_sums=out_sums, **fwd_kw)   # synchronous on return
             step_s.append(time.perf_counter() - ts)
         barrier()
         dt = torch.tensor([(time.perf_counter() - t0) / k2], dtype=torch.float64, device=dev)
@@ -523,7 +551,9 @@ def main():
                 "imu.pool": F_ * (N_IMU * 1024 * act + 1024 * act),
                 "imu.decode": F_ * (1024 * act + 48),
                 "upper.point": F_ * (N_PTS * 6 * 4 + N_PTS * 3 * 4 + 64 * 4 + 48),
-                "assemble_metrics": F_ * ((45 + 24 + 63) * 4 + 63 * 4),
+                # fused tails (heads_mma.cu): head input in; joints (+ pred) out; R, t; lower also reads upper_l and target
+                "upper.head_decode": F_ * (128 * 4 + 48 + 45 * 4),
+                "lower.head_decode": F_ * ((128 + 45) * 4 + 48 + 24 * 4 + 45 * 4 + 63 * 4 + 63 * 4),
             }
             flops = {"upper.point": F_ * 1.57e6, "lower.frame": F_ * 1.40e6, "small_lstm": F_ * (0.524e6 + 0.655e6),
                      "lower.gcn": F_ * 7.18e6}
@@ -543,14 +573,19 @@ def main():
             return out
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": {0: "f32", 1: "f32 (fp16x3 split products, fp32 accumulate)", 2: "f16 (fp32 accumulate)"}[mode],
             "data": "synthetic",
-            "config": {"workload": f"full pipeline, B={B} snippets per GPU, L={L}, N={N_PTS}, n_imu={N_IMU} "
-                                   "(config 3 of BASELINE.json); IMU_Net weights: " + pipe.imu_weights,
+            "config": {"workload": (f"full pipeline, B={Bg} snippets split over {world} GPUs, L={L}, N={N_PTS}, n_imu={N_IMU} "
+                                    "(config 4 of BASELINE.json)" if strong else
+                                    f"full pipeline, B={B} snippets per GPU, L={L}, N={N_PTS}, n_imu={N_IMU} "
+                                    "(config 3 of BASELINE.json)") + "; IMU_Net weights: " + pipe.imu_weights,
                        "global_batch": Bg, "frames_per_step": frames, "parallelism": f"dp{world}",
                        "l2": "inputs per step (350 MB per GPU) exceed the 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": launches,
+            "collective_ms_per_step": round(collective_ms, 4) if world > 1 else None,
+            "collective_note": ("all-gather of pred + all-reduce of 46 float64 sums, device time on the side stream they "
+                                "overlap the next step on (rank 0)") if world > 1 else None,
             "algorithmic_tflops": FLOPS_PER_FRAME["total"] * frames / (ms_per_step * 1e-3) / 1e12,
             "stage_ms_per_step": stage_ms,
             "mpjpe_vs_synthetic_target_cm": rep["mpjpe_cm"],

@@ -10,6 +10,10 @@
  *  - Calls are asynchronous on `stream` (a cudaStream_t passed as void*); nothing is retained past the call
  *    except packed weights.  A handle is not thread-safe; use one per GPU / per thread.
  *  - Return 0 on success, a negative MMEGO_E* code otherwise; text via mmego_last_error().
+ *  - Numeric range of the default ("fp32-grade") mode: the tensor-core stages carry activations as two fp16 planes of
+ *    2^s * value and SATURATE outside |value| <= 65000 / 2^s: 253 for IMU_Net's fc1 / LSTM / pooled features (s = 8; LSTM
+ *    outputs are bounded by 1), 4062 for the ST-GCN activations (s = 4).  The shipped Upper/Lower checkpoints stay three
+ *    orders of magnitude inside; a model whose activations leave the range is clipped, not turned into inf/NaN.
  */
 #ifndef MMEGO_B200_H
 #define MMEGO_B200_H

@@ -314,28 +314,34 @@ struct ImuTcWs {
     float* cst;
     long long Spad;
 };
-void plan_imu_tc(Carver& c, long long Bc, int L, int n, ImuTcWs& w) {
-    const size_t S = (size_t)Bc * L;
+// rnn_fast works on chunks of Bc snippets (u, y0, y1: 4.3 GB per 2048 snippets); the pooled features s of ALL B snippets
+// are kept (80 KB per snippet) so that rnn_slow and the decode run ONCE over the whole batch after the chunk loop: half
+// the rnn_slow launches at B = 4096, each with twice the work items for the 74 CTA pairs.
+void plan_imu_tc(Carver& c, long long B, long long Bc, int L, int n, ImuTcWs& w) {
+    const size_t S = (size_t)Bc * L, Sall = (size_t)B * L;
     auto plane = [&](size_t elems) { return static_cast<void*>(c.f((elems + 1) / 2)); };
     for (int k = 0; k < 2; ++k) {
         w.u[k] = plane(S * n * kImuH);
         w.y0[k] = plane(S * n * 2 * kImuH);
         w.y1[k] = plane(S * n * 2 * kImuH);
-        w.s[k] = plane(S * 2 * kImuH);
-        w.z0[k] = plane(S * 2 * kImuH);
-        w.z1[k] = plane(S * 2 * kImuH);
+        w.s[k] = plane(Sall * 2 * kImuH);
+        w.z0[k] = plane(Sall * 2 * kImuH);
+        w.z1[k] = plane(Sall * 2 * kImuH);
     }
-    w.Spad = (long long)((S + 127) / 128 * 128);
+    const size_t seqs = S > (size_t)B ? S : (size_t)B;      // rnn_fast: Bc*L sequences per chunk; rnn_slow: B sequences
+    w.Spad = (long long)((seqs + 127) / 128 * 128);
     w.cst = c.f((size_t)2 * kImuH * w.Spad);
 }
 
-int imu_chunk_forward_tc(mmego_handle* h, const float* imu, float* R, float* t, long long Bc, int L, int n,
-                         const ImuTcWs& w, cudaStream_t st) {
+// rnn_fast part of one chunk: imu [Bc,L,n,15] -> pooled features s (planes of the WHOLE batch, this chunk's rows at f0)
+int imu_chunk_fast_tc(mmego_handle* h, const float* imu, long long f0, long long Bc, int L, int n, const ImuTcWs& w,
+                      cudaStream_t st) {
     const long long S = Bc * L;
     const ImuWeights& W = h->imu;
     const int npass = h->imu_gemm == 1 ? 3 : 1;
     void* const nolo = nullptr;
     auto lo = [&](void* const* planes) { return npass == 3 ? planes[1] : nolo; };
+    auto at = [&](void* plane, long long elems) { return plane ? static_cast<void*>(static_cast<char*>(plane) + elems * 2) : nolo; };
     {
         Prof p(h, "imu.fc1", st);
         tc_imu_fc1(imu, W.fc1_mma.p, w.u[0], lo(w.u), S * n, h->sm_count, h->tc_lo_drop, st);                               // Net/IMU_Net.py:79
@@ -358,13 +364,32 @@ int imu_chunk_forward_tc(mmego_handle* h, const float* imu, float* R, float* t, 
     tap_split("imu.f", w.y1, S * n * 2 * kImuH);
     {
         Prof p(h, "imu.pool", st);
-        tc_imu_pool(w.y1[0], lo(w.y1), W.attn.p, w.s[0], lo(w.s), S, n, h->tc_lo_drop, st);              // :82-83
+        tc_imu_pool(w.y1[0], lo(w.y1), W.attn.p, at(w.s[0], f0 * 2 * kImuH), at(lo(w.s), f0 * 2 * kImuH), S, n, h->tc_lo_drop, st);   // :82-83
     }
+    if (rc) return fail(h, MMEGO_ECUDA, "imu_forward: cuTensorMapEncodeTiled failed");
+    return MMEGO_OK;
+}
+
+// rnn_slow + fc2 + 6D decode over the whole batch: s planes [B*L,1024] -> R [B,L,3,3], t [B,L,3]
+int imu_slow_decode_tc(mmego_handle* h, float* R, float* t, long long B, int L, const ImuTcWs& w, cudaStream_t st) {
+    const long long S = B * L;
+    const ImuWeights& W = h->imu;
+    const int npass = h->imu_gemm == 1 ? 3 : 1;
+    void* const nolo = nullptr;
+    auto lo = [&](void* const* planes) { return npass == 3 ? planes[1] : nolo; };
+    auto tap_split = [&](const char* name, void* const* planes, long long elems) {
+        auto it = h->taps.find(name);
+        if (it == h->taps.end()) return;
+        tc_unsplit(planes[0], lo(planes), static_cast<float*>(it->second.first),
+                   std::min<long long>(elems, (long long)(it->second.second / 4)), st);
+        h->taps.erase(it);
+    };
     tap_split("imu.s", w.s, S * 2 * kImuH);
+    int rc = 0;
     {
         Prof p(h, "imu.lstm_slow", st);
-        rc |= tc_lstm_layer(h, W.tc_slow[0], w.s[0], lo(w.s), w.z0[0], lo(w.z0), w.cst, Bc, w.Spad, L, npass, st);  // :85
-        rc |= tc_lstm_layer(h, W.tc_slow[1], w.z0[0], lo(w.z0), w.z1[0], lo(w.z1), w.cst, Bc, w.Spad, L, npass, st);
+        rc |= tc_lstm_layer(h, W.tc_slow[0], w.s[0], lo(w.s), w.z0[0], lo(w.z0), w.cst, B, w.Spad, L, npass, st);  // :85
+        rc |= tc_lstm_layer(h, W.tc_slow[1], w.z0[0], lo(w.z0), w.z1[0], lo(w.z1), w.cst, B, w.Spad, L, npass, st);
     }
     tap_split("imu.g", w.z1, S * 2 * kImuH);
     {
@@ -494,12 +519,12 @@ bool use_gcn_tc(const mmego_handle* h) {
 #endif
 }
 
-size_t imu_ws_bytes(const mmego_handle* h, long long Bc, int L, int n) {
+size_t imu_ws_bytes(const mmego_handle* h, long long B, long long Bc, int L, int n) {
     Carver s(nullptr);
 #ifndef MMEGO_EMUL
     if (h->imu_gemm != 0) {
         ImuTcWs w;
-        plan_imu_tc(s, Bc, L, n, w);
+        plan_imu_tc(s, B, Bc, L, n, w);
         return s.off;
     }
 #endif
@@ -840,7 +865,7 @@ size_t mmego_workspace_bytes(const mmego_handle* h, int stage, int B, int L, int
     Carver c(nullptr);
     const long long Bc = B < h->imu_chunk ? B : h->imu_chunk;
     if (stage == MMEGO_STAGE_IMU) {
-        c.off = imu_ws_bytes(h, Bc, L, n_imu);
+        c.off = imu_ws_bytes(h, B, Bc, L, n_imu);
     } else if (stage == MMEGO_STAGE_UPPER) {
         UpperWs w;
         plan_upper(c, B, L, w);
@@ -852,7 +877,7 @@ size_t mmego_workspace_bytes(const mmego_handle* h, int stage, int B, int L, int
         const size_t F = (size_t)B * L;
         c.f(F * 9); c.f(F * 3); c.f(F * 45); c.f(F * 24);
         size_t best = 0;
-        best = std::max(best, imu_ws_bytes(h, Bc, L, n_imu));
+        best = std::max(best, imu_ws_bytes(h, B, Bc, L, n_imu));
         {
             Carver s(nullptr); UpperWs w; plan_upper(s, B, L, w); best = std::max(best, s.off);
         }
@@ -882,13 +907,12 @@ int mmego_imu_forward(mmego_handle* h, const float* imu, float* R, float* t, int
     if (h->imu_gemm != 0) {
         if (!h->imu.tc_ready) return fail(h, MMEGO_ESTATE, "imu_forward: tensor-core weights are not packed");
         ImuTcWs w;
-        plan_imu_tc(c, Bc, L, n_imu, w);
+        plan_imu_tc(c, B, Bc, L, n_imu, w);
         for (long long b0 = 0; b0 < B; b0 += Bc) {
             const long long nb = (B - b0) < Bc ? (B - b0) : Bc;
-            if (int rc = imu_chunk_forward_tc(h, imu + (size_t)b0 * L * n_imu * kImuFeat, R + (size_t)b0 * L * 9,
-                                              t + (size_t)b0 * L * 3, nb, L, n_imu, w, st))
-                return rc;
+            if (int rc = imu_chunk_fast_tc(h, imu + (size_t)b0 * L * n_imu * kImuFeat, b0 * L, nb, L, n_imu, w, st)) return rc;
         }
+        if (int rc = imu_slow_decode_tc(h, R, t, B, L, w, st)) return rc;
         CUDA_TRY(h, cudaGetLastError());
             return MMEGO_OK;
     }
@@ -945,19 +969,34 @@ int mmego_upper_forward(mmego_handle* h, float* x, const float* h0, const float*
     if (!h->head_gemm) {
         linear(h, W.fc1, hs, 128, w.h1, 128, F, 1, st);
         linear(h, W.fc2, w.h1, 128, w.o, 87, F, 0, st);
+        tap(h, "upper.o", w.o, (size_t)F * 87 * 4, st);
+        launch_upper_decode(w.o, initial_body, R, t, l, q, F, L, body_index_mode, (long long)b_offset * L, B_global, st);
     } else
 #endif
-        launch_upper_head_mma(hs, W.head_mma.p, w.o, F, h->sm_count, st);                // :351-353
-    tap(h, "upper.o", w.o, (size_t)F * 87 * 4, st);
-    launch_upper_decode(w.o, initial_body, R, t, l, q, F, L, body_index_mode, (long long)b_offset * L, B_global, st);   // :355-387
+    {
+        // MLPHead + 6D -> rotations + forward kinematics + Transform2R in ONE kernel (:351-353, 355-387): the 87 head
+        // outputs stay in shared memory (written out only for a debug tap)
+        HeadTail tl{};
+        tl.body = initial_body; tl.R = R; tl.t = t; tl.l = l; tl.q = q;
+        tl.L = L; tl.mode = body_index_mode; tl.B_global = B_global; tl.row_offset = (long long)b_offset * L;
+        const bool want_o = h->taps.count("upper.o") != 0;
+        launch_upper_tail_mma(hs, W.head_mma.p, want_o ? w.o : nullptr, F, tl, h->sm_count, st);
+        tap(h, "upper.o", w.o, (size_t)F * 87 * 4, st);
+    }
     CUDA_TRY(h, cudaGetLastError());
     return MMEGO_OK;
 }
 
-int mmego_lower_forward(mmego_handle* h, const float* upper_l, float* x, const float* initial_body, const float* R,
-                        const float* t, float* l, float* q, int B, int L, int N, int body_index_mode, int b_offset,
-                        int B_global, void* ws, size_t ws_bytes, void* stream) {
-    Entry entry(h);
+}  // extern "C"
+
+namespace {
+// LowerNet.forward; with `assemble` the fused tail kernel also scatters upper_l / lower_l into pred [F,21,3] and ADDS the
+// batch's error sums (target / pred / sums may each be null) -- Processor/Test/Demo_test.py:121-123, 64-69.
+int lower_forward_impl(mmego_handle* h, const float* upper_l, float* x, const float* initial_body, const float* R,
+                       const float* t, float* l, float* q, int B, int L, int N, int body_index_mode, int b_offset,
+                       int B_global, void* ws, size_t ws_bytes, void* stream, int assemble, const float* target,
+                       float* pred, double* sums, bool* assembled) {
+    if (assembled) *assembled = false;
     if (int rc = check_dims(h, B, L, N)) return rc;
     if (!upper_l || !x || !initial_body || !R || !t || !l || !ws) return fail(h, MMEGO_EINVAL, "lower_forward: NULL argument");
     if (!h->lower.ready) return fail(h, MMEGO_ESTATE, "lower_forward: Lower_Net weights were never set");
@@ -1015,13 +1054,35 @@ int mmego_lower_forward(mmego_handle* h, const float* upper_l, float* x, const f
         run_gemm(h, a, EPI_STORE, st);
         linear(h, W.fc1, w.f0, 128, w.f1, 64, F, 1, st);                                  // :122-123
         linear(h, W.fc2, w.f1, 64, w.o, 42, F, 0, st);                                    // :124
+        tap(h, "lower.o", w.o, (size_t)F * 42 * 4, st);
+        launch_lower_decode(w.o, initial_body, R, t, l, q, F, L, body_index_mode, (long long)b_offset * L, B_global, st);
     } else
 #endif
-        launch_lower_head_mma(hs, w.uh, W.head_mma.p, w.o, F, h->sm_count, st);           // :119-124
-    tap(h, "lower.o", w.o, (size_t)F * 42 * 4, st);
-    launch_lower_decode(w.o, initial_body, R, t, l, q, F, L, body_index_mode, (long long)b_offset * L, B_global, st);   // :126-135, 235-238
+    {
+        // fc0-fc2 + 6D -> rotations + forward kinematics + Transform2R (+ 21-joint assembly + error sums) in ONE kernel
+        // (:119-135, 235-238; Demo_test.py:121-123, 64-69)
+        HeadTail tl{};
+        tl.body = initial_body; tl.R = R; tl.t = t; tl.l = l; tl.q = q;
+        tl.L = L; tl.mode = body_index_mode; tl.B_global = B_global; tl.row_offset = (long long)b_offset * L;
+        tl.assemble = assemble; tl.upper_l = upper_l; tl.target = target; tl.pred = pred; tl.sums = sums;
+        const bool want_o = h->taps.count("lower.o") != 0;
+        launch_lower_tail_mma(hs, w.uh, W.head_mma.p, want_o ? w.o : nullptr, F, tl, h->sm_count, st);
+        tap(h, "lower.o", w.o, (size_t)F * 42 * 4, st);
+        if (assembled) *assembled = assemble != 0;
+    }
     CUDA_TRY(h, cudaGetLastError());
     return MMEGO_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mmego_lower_forward(mmego_handle* h, const float* upper_l, float* x, const float* initial_body, const float* R,
+                        const float* t, float* l, float* q, int B, int L, int N, int body_index_mode, int b_offset,
+                        int B_global, void* ws, size_t ws_bytes, void* stream) {
+    Entry entry(h);
+    return lower_forward_impl(h, upper_l, x, initial_body, R, t, l, q, B, L, N, body_index_mode, b_offset, B_global, ws,
+                              ws_bytes, stream, 0, nullptr, nullptr, nullptr, nullptr);
 }
 
 int mmego_gcn_extract_feature(mmego_handle* h, const float* x, float* out, int B, int T, void* ws, size_t ws_bytes,
@@ -1115,9 +1176,11 @@ int mmego_pipeline_forward(mmego_handle* h, const float* imu, float* x, const fl
     rc = mmego_upper_forward(h, x, nullptr, nullptr, initial_body, R, t, up, nullptr, nullptr, nullptr, nullptr, B, L, N,
                              body_index_mode, b_offset, B_global, sub, sub_bytes, stream);
     if (rc) return rc;
-    rc = mmego_lower_forward(h, up, x, initial_body, R, t, lo, nullptr, B, L, N, body_index_mode, b_offset, B_global, sub,
-                             sub_bytes, stream);
+    bool assembled = false;
+    rc = lower_forward_impl(h, up, x, initial_body, R, t, lo, nullptr, B, L, N, body_index_mode, b_offset, B_global, sub,
+                            sub_bytes, stream, 1, target, pred, sums, &assembled);
     if (rc) return rc;
+    if (assembled) return MMEGO_OK;          // the 21-joint assembly and the error sums ran inside the fused lower tail
     return mmego_assemble_metrics(h, up, lo, target, pred, sums, B, L, stream);
 }
 

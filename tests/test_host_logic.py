@@ -106,8 +106,15 @@ def _worker(rank, world, port, B, out):
         sums[0] = float(full[lo:hi].sum())
         return full[lo:hi].clone(), sums
 
-    pred, sums = ShardedRunner(step, world, rank).run(B)
+    runner = ShardedRunner(step, world, rank)
+    pred, sums = runner.run(B)
     ok = torch.equal(pred, full) and sums[43].item() == B * 2 and abs(sums[0].item() - float(full.sum())) < 1e-3
+    # pipelined form: two steps outstanding, collected in order, results identical to the synchronous form
+    runner.submit(B)
+    runner.submit(B)
+    for _ in range(2):
+        p2, s2 = runner.collect()
+        ok = ok and torch.equal(p2, full) and s2[43].item() == B * 2
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
