@@ -27,7 +27,7 @@ OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libmmego_b200.so")
 
 SOURCES = ["api.cu", "gemm_ffma.cu", "point_upper.cu", "lower_frame.cu", "lstm_small.cu", "gcn.cu", "decode.cu", "snippet.cu", "heads_mma.cu",
-           "lstm_tc.cu", "gemm_tc.cu", "pack.cpp"]
+           "lstm_tc.cu", "gemm_tc.cu", "lstm_resident.cu", "pack.cpp"]
 HEADERS = ["internal.h", "pack.h", "point_layout.h", "cuda_compat.h", "tc_common.cuh", "mma_frag.cuh",
            os.path.join("..", "..", "include", "mmego_b200.h")]
 

@@ -306,6 +306,46 @@ int imu_chunk_forward(mmego_handle* h, const float* imu, float* R, float* t, lon
 
 #endif  // MMEGO_FFMA_GEN
 
+// ---------------------------------------------------------------------------------------------- IMU_Net latency path
+// Small batches (B*L <= kResMaxSeq): fp32 throughout, persistent LSTM kernels with the gate weights resident in shared
+// memory (lstm_resident.cu).  7 launches per call instead of 83.
+struct ImuResWs {
+    float *u, *y0, *y1, *s, *z0, *z1, *cst;
+    unsigned* flags;
+};
+void plan_imu_res(Carver& c, long long B, int L, int n, ImuResWs& w) {
+    const size_t S = (size_t)B * L;
+    w.u = c.f(S * n * kImuH);
+    w.y0 = c.f(S * n * 2 * kImuH);
+    w.y1 = c.f(S * n * 2 * kImuH);
+    w.s = c.f(S * 2 * kImuH);
+    w.z0 = c.f(S * 2 * kImuH);
+    w.z1 = c.f(S * 2 * kImuH);
+    w.cst = c.f(2 * S * kImuH);
+    w.flags = reinterpret_cast<unsigned*>(c.f(2 * (size_t)(n > L ? n : L) + 8));
+}
+bool use_resident(const mmego_handle* h, long long B, int L) {
+    return h->imu_resident && h->imu.res_ready && B * L <= kResMaxSeq && resident_supported(h->sm_count);
+}
+int imu_res_forward(mmego_handle* h, const float* imu, float* R, float* t, long long B, int L, int n, const ImuResWs& w,
+                    cudaStream_t st) {
+    const long long S = B * L;
+    const ImuWeights& W = h->imu;
+    Prof p(h, "imu.resident", st);
+    launch_res_fc1(imu, W.res_fc1.p, w.u, S * n, st);                                                            // Net/IMU_Net.py:79
+    int rc = 0;
+    rc |= launch_lstm_resident(w.u, kImuH, w.y0, W.res_w[0].p, W.res_b[0].p, w.cst, w.flags, (int)S, n, st);      // :80
+    rc |= launch_lstm_resident(w.y0, 2 * kImuH, w.y1, W.res_w[1].p, W.res_b[1].p, w.cst, w.flags, (int)S, n, st);
+    tap(h, "imu.f", w.y1, (size_t)S * n * 2 * kImuH * 4, st);
+    launch_imu_pool(w.y1, W.attn.p, w.s, S, n, st);                                                              // :82-83
+    rc |= launch_lstm_resident(w.s, 2 * kImuH, w.z0, W.res_w[2].p, W.res_b[2].p, w.cst, w.flags, (int)B, L, st);  // :85
+    rc |= launch_lstm_resident(w.z0, 2 * kImuH, w.z1, W.res_w[3].p, W.res_b[3].p, w.cst, w.flags, (int)B, L, st);
+    launch_imu_decode(w.z1, W.fc2.p, R, t, S, st);                                                               // :87-93
+    if (rc) return fail(h, MMEGO_ECUDA, "imu_forward: launching the resident-weights LSTM kernel failed (%s)",
+                        cudaGetErrorString(cudaGetLastError()));
+    return MMEGO_OK;
+}
+
 #ifndef MMEGO_EMUL
 // ---------------------------------------------------------------------------------------------- IMU_Net on tensor cores
 // Activations are fp16 hi/lo planes (see lstm_tc.cu); one plane of n elements takes n/2 floats of workspace.
@@ -521,6 +561,11 @@ bool use_gcn_tc(const mmego_handle* h) {
 
 size_t imu_ws_bytes(const mmego_handle* h, long long B, long long Bc, int L, int n) {
     Carver s(nullptr);
+    if (use_resident(h, B, L)) {
+        ImuResWs w;
+        plan_imu_res(s, B, L, n, w);
+        return s.off;
+    }
 #ifndef MMEGO_EMUL
     if (h->imu_gemm != 0) {
         ImuTcWs w;
@@ -702,6 +747,10 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
 #endif
         return MMEGO_OK;
     }
+    if (!strcmp(key, "imu_resident")) {
+        h->imu_resident = value != 0;
+        return MMEGO_OK;
+    }
     if (!strcmp(key, "tc_pdl")) {
         h->tc_pdl = value != 0;
         return MMEGO_OK;
@@ -760,6 +809,19 @@ int mmego_set_weights(mmego_handle* h, int net, const char* const* names, const 
             memcpy(fc2.data(), sd.get("fc2.weight", 9 * 2 * H), sizeof(float) * 9 * 2 * H);
             memcpy(fc2.data() + 9 * 2 * H, sd.get("fc2.bias", 9), sizeof(float) * 9);
             ok &= upload(h, fc2, W.fc2);
+            {   // latency path: fp32 slices per (direction, 8-unit group), k-major (lstm_resident.cu)
+                std::vector<float> rw, rb;
+                const char* pre[4] = {"rnn_fast.", "rnn_fast.", "rnn_slow.", "rnn_slow."};
+                for (int i = 0; i < 4; ++i) {
+                    pack_resident_layer(sd, pre[i], i & 1, i == 0 ? H : 2 * H, rw, rb);
+                    ok &= upload(h, rw, W.res_w[i]) && upload(h, rb, W.res_b[i]);
+                }
+                std::vector<float> f1((size_t)H * kImuFeat + H);
+                memcpy(f1.data(), sd.get("fc1.weight", H * kImuFeat), sizeof(float) * H * kImuFeat);
+                memcpy(f1.data() + (size_t)H * kImuFeat, sd.get("fc1.bias", H), sizeof(float) * H);
+                ok &= upload(h, f1, W.res_fc1);
+                W.res_ready = ok;
+            }
             W.ready = ok;
             W.tc_ready = false;
 #ifndef MMEGO_EMUL
@@ -903,6 +965,13 @@ int mmego_imu_forward(mmego_handle* h, const float* imu, float* R, float* t, int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long Bc = B < h->imu_chunk ? B : h->imu_chunk;
     Carver c(ws);
+    if (use_resident(h, B, L)) {
+        ImuResWs w;
+        plan_imu_res(c, B, L, n_imu, w);
+        if (int rc = imu_res_forward(h, imu, R, t, B, L, n_imu, w, st)) return rc;
+        CUDA_TRY(h, cudaGetLastError());
+        return MMEGO_OK;
+    }
 #ifndef MMEGO_EMUL
     if (h->imu_gemm != 0) {
         if (!h->imu.tc_ready) return fail(h, MMEGO_ESTATE, "imu_forward: tensor-core weights are not packed");

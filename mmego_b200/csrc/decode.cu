@@ -160,9 +160,8 @@ __global__ void __launch_bounds__(DT) assemble_metrics_kernel(const float* __res
     if (tid < kSumsLen && s.acc[tid] != 0.0) atomicAdd(&sums[tid], s.acc[tid]);
 }
 
-#ifdef MMEGO_FFMA_GEN   // fp32 FFMA generation: emulator suite and -DMMEGO_WITH_FFMA test builds only (not in the product library)
 // ------------------------------------------------------------------------------------------------
-// IMU_Net tail
+// IMU_Net tail in fp32: used by the small-batch latency path (lstm_resident.cu) and by the fp32 FFMA test generation
 // ------------------------------------------------------------------------------------------------
 // attention pooling over the n samples of a frame (Net/IMU_Net.py:82-83): y [F,n,1024] -> s [F,1024]
 constexpr int PW = 256;
@@ -235,8 +234,6 @@ __global__ void __launch_bounds__(256) imu_decode_kernel(const float* __restrict
     }
 }
 
-#endif  // MMEGO_FFMA_GEN
-
 // ------------------------------------------------------------------------------------------------
 // rigid transforms (Utils.py:274-292) as standalone ops for the drop-in Util module
 // ------------------------------------------------------------------------------------------------
@@ -294,7 +291,6 @@ void launch_assemble_metrics(const float* up, const float* lo, const float* tg, 
     MMEGO_LAUNCH(assemble_metrics_kernel, dim3((unsigned)((F + FPB - 1) / FPB)), dim3(DT), sizeof(MetricsSmem), st, up,
                  lo, tg, pred, sums, F);
 }
-#ifdef MMEGO_FFMA_GEN   // fp32 FFMA generation: emulator suite and -DMMEGO_WITH_FFMA test builds only (not in the product library)
 void launch_imu_pool(const float* y, const float* attn, float* out, long long F, int n, cudaStream_t st) {
     if (F <= 0) return;
     MMEGO_LAUNCH(imu_pool_kernel, dim3((unsigned)F), dim3(PW), 0, st, y, attn, out, F, n);
@@ -303,8 +299,6 @@ void launch_imu_decode(const float* g, const float* fc2, float* R, float* t, lon
     if (F <= 0) return;
     MMEGO_LAUNCH(imu_decode_kernel, dim3((unsigned)((F + 7) / 8)), dim3(256), 0, st, g, fc2, R, t, F);
 }
-#endif  // MMEGO_FFMA_GEN
-
 void launch_transform2h(float* pts, const float* R, const float* t, long long F, int n, int D, cudaStream_t st) {
     const long long total = F * n;
     if (total <= 0) return;

@@ -135,6 +135,17 @@ void launch_transform2h(float* pts, const float* R, const float* t, long long F,
 void launch_transform2r(const float* pts, const float* R, const float* t, float* out, long long F, int n,
                         cudaStream_t st);
 
+// small-batch latency path of IMU_Net (lstm_resident.cu): fp32, gate weights resident in shared memory across timesteps
+constexpr int kResMaxSeq = 64;       // B*L up to which the resident path is taken (B <= 3 at L = 20; measured break-even with the
+                                     // tcgen05 path: B = 4, profiles/r02_latency_path.txt)
+struct StateDict;
+void pack_resident_layer(const StateDict& sd, const std::string& prefix, int layer, int In, std::vector<float>& w,
+                         std::vector<float>& bias);
+bool resident_supported(int sm_count);
+int launch_lstm_resident(const float* x, int In, float* y, const float* w, const float* bias, float* cstate,
+                         unsigned* flags, int S, int T, cudaStream_t st);
+void launch_res_fc1(const float* imu, const float* w, float* u, long long rows, cudaStream_t st);
+
 // snippet builder (snippet.cu): device views of the packed raw cache (scripts/pack_sample_data.py)
 struct RawFrames {
     const float* points;            // [P][5]  x, y, z, intensity, velocity
@@ -210,6 +221,10 @@ struct ImuWeights {
     PackedBigLstmLayer fast[2], slow[2];
     DevBuf attn;       // [1024] + [1] bias at the end
     DevBuf fc2;        // [9][1024] + [9]
+    // latency path (lstm_resident.cu): fp32 k-major slices per (direction, 8-unit group); order fast l0, l1, slow l0, l1
+    bool res_ready = false;
+    DevBuf res_w[4], res_b[4];
+    DevBuf res_fc1;    // [512][15] + [512]
 };
 struct UpperWeights {
     bool ready = false;
@@ -306,6 +321,7 @@ struct mmego_handle {
     int small_lstm_gemm = 1;  // H=64 LSTMs: 0 = fp32 FFMA, 1 = mma.sync fp16x3 (default)
     int tc_kb_chunk0 = 8;     // ... of the first two chunks of every tile
     int tc_kb_chunk = 4;      // fp16x3 mode: K blocks (of 64) per TMEM partial accumulation (see lstm_tc.cu)
+    int imu_resident = 1;     // small batches (B*L <= kResMaxSeq): persistent fp32 LSTM with weights resident in shared memory
     mmego::ImuWeights imu;
     mmego::UpperWeights upper;
     mmego::LowerWeights lower;

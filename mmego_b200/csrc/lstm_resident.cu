@@ -1,0 +1,330 @@
+// lstm_resident.cu -- the LATENCY path of IMU_Net (Net/IMU_Net.py:67-94) for small batches: the reference's own operating
+// point is ONE snippet per call (Processor/Test/Demo_test.py:61), i.e. 20 sequences for rnn_fast and a single sequence
+// for rnn_slow.  The tcgen05 kernel of lstm_tc.cu is built for 40,960 sequences per launch; at 20 it spends 80 timestep
+// launches streaming the 92 MB of weights through 16 CTA pairs (2.1 ms per snippet).
+//
+// Here one PERSISTENT kernel per bidirectional layer keeps the gate weights resident in shared memory for all
+// timesteps -- in exact fp32:
+//   * 128 CTAs = 2 directions x 64 groups of 8 hidden units; a CTA owns the 32 gate rows (i,f,g,o of its 8 units) over
+//     the full K = In + 512: 128 / 192 KB of shared memory, loaded once per launch.
+//   * per timestep a warp's lanes are the 32 gate rows, warps split the (sequence group, K slice) items; partial sums
+//     meet in shared memory, then one thread per (sequence, unit) applies the cell update (c in a small global scratch).
+//   * the 64 CTAs of a direction exchange h through the layer's own output tensor in global memory (L2): a CTA publishes
+//     its 8 units with a device-scope fence + one arrival on a per-(direction, step) counter and waits for 64 arrivals
+//     before the recurrent half of the next step.  The INPUT half of a step (x_t W_ih^T, K = In) does not depend on the
+//     other CTAs and runs before the wait, hiding the exchange latency.
+//   * launched with cudaLaunchCooperativeKernel (all CTAs co-resident, or the launch fails); the wait gives up after a
+//     bounded number of polls and raises a flag instead of hanging the GPU.
+// Everything around it (fc1, attention pooling, fc2 + 6D decode) is fp32 as well, so this path is the exact-fp32
+// evaluation of IMU_Net; the host picks it when B*L <= kResMaxSeq.
+#include "internal.h"
+#include "pack.h"
+#ifndef MMEGO_EMUL
+#include <cuda_pipeline.h>
+#endif
+
+namespace mmego {
+
+namespace {
+
+constexpr int RU = 8;                    // hidden units per CTA
+constexpr int RR = 4 * RU;               // gate rows per CTA = lanes of a warp
+constexpr int RGROUPS = kImuH / RU;      // 64 CTAs per direction
+constexpr int RT = 256, RW = RT / 32;    // threads / warps per CTA
+constexpr int SBLK = 20;                 // sequences per block of the K loop (4 sequence groups x 5)
+
+#ifdef MMEGO_EMUL
+#define RES_LDCG(p) (*(p))
+#else
+#define RES_LDCG(p) __ldcg(p)
+#endif
+
+struct ResParams {
+    const float* x;        // [S][T][In]
+    float* y;              // [S][T][1024]  (fwd -> 0..511, bwd -> 512..1023); also the recurrent operand
+    const float* w;        // [2][64][K][32]  k-major slices, col = gate*8 + unit
+    const float* bias;     // [2][64][32]     b_ih + b_hh
+    float* cstate;         // [2][S][512]
+    unsigned* flags;       // [2][T] arrival counters, zero at launch (null: no inter-CTA waiting, one step per launch)
+    unsigned* error;       // set to 1 when a wait gave up
+    int S, T, In, K;
+    int t_begin, t_end;
+};
+
+__device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// One K segment (the input half x_t or the recurrent half h_{t-1}) of one block of <= 4 SQ sequences:
+//   acc[r][j] += sum_k W[kw0 + k][4 rg + r] * a_{sg SQ + j}[k],  k in [0, len),  a_s = src + s * stride.
+// The activations are streamed through shared memory in chunks of KC = 128 k with cp.async (16 bytes per copy, rows kept
+// as they are in global memory: [sequence][k], row stride KC + 4 floats so that the four sequence groups of a warp hit
+// different banks), three buffers, two chunks in flight while one is consumed -- h comes from L2 (other CTAs wrote it)
+// and that latency must not sit inside the FMA loop.  Within a chunk warp w owns k-quads w, w + 8, ...; a lane is (row
+// group rg = lane / 4, sequence group sg = lane % 4) with a 4 x SQ register tile: per k-quad 4 weight reads + SQ
+// activation reads (all 16-byte, conflict-free) for 16 SQ FMAs.
+// (Measured dead ends, B200: one gate row per lane with broadcast activation reads -- 21 shared-memory wavefronts per
+// k, 30 FMA/clk/SM; activations straight from global memory into a register pipeline -- 4 sectors per load instruction,
+// L1/TEX-bound; register-staged chunks with one chunk in flight -- the loop waited on L2.)
+constexpr int KC = 128, KROW = KC + 4, NBUF = 3;
+constexpr int ABUF = NBUF * SBLK * KROW;     // floats (31.7 KB); afterwards the cross-warp partial sums [warp][sequence][row] (20 KB)
+
+__device__ __forceinline__ void copy16_async(float* dst, const float* src) {
+#ifdef MMEGO_EMUL
+    *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
+#else
+    __pipeline_memcpy_async(dst, src, 16);       // cp.async.cg: global -> shared without a register round trip, L2 only
+#endif
+}
+__device__ __forceinline__ void copy_commit() {
+#ifndef MMEGO_EMUL
+    __pipeline_commit();
+#endif
+}
+template <int N>
+__device__ __forceinline__ void copy_wait_prior() {
+#ifndef MMEGO_EMUL
+    __pipeline_wait_prior(N);
+#endif
+}
+
+template <int SQ>
+__device__ __forceinline__ void segment(const float* __restrict__ sw, float* __restrict__ abuf, const float* __restrict__ src,
+                                        size_t stride, int nseq, int kw0, int len, int tid, float (&acc)[4][SQ]) {
+    constexpr int SP = 4 * SQ;                         // sequence slots per block
+    const int lane = tid & 31, warp = tid >> 5, rg = lane >> 2, sg = lane & 3;
+    const int nchunk = len / KC;                       // len is a multiple of 128
+    auto issue = [&](int c) {
+        if (c < nchunk) {
+            float* buf = abuf + (c % NBUF) * (SBLK * KROW);
+            for (int i = tid; i < SP * (KC / 4); i += RT) {
+                const int sq = i / (KC / 4), kq = i % (KC / 4);
+                copy16_async(buf + sq * KROW + 4 * kq, src + (size_t)(sq < nseq ? sq : 0) * stride + c * KC + 4 * kq);
+            }
+        }
+        copy_commit();                                 // (an empty group keeps the wait counts uniform)
+    };
+    issue(0);
+    issue(1);
+    for (int c = 0; c < nchunk; ++c) {
+        issue(c + 2);
+        copy_wait_prior<2>();                          // chunk c has landed (this thread's copies) ...
+        __syncthreads();                               // ... and everybody else's
+        const float* buf = abuf + (c % NBUF) * (SBLK * KROW) + (sg * SQ) * KROW;
+        const float* wc = sw + (size_t)(kw0 + c * KC) * RR + 4 * rg;
+#pragma unroll
+        for (int q = warp; q < KC / 4; q += RW) {
+            const float* wq = wc + (size_t)q * 4 * RR;
+            const float4 w0 = *reinterpret_cast<const float4*>(wq), w1 = *reinterpret_cast<const float4*>(wq + RR);
+            const float4 w2 = *reinterpret_cast<const float4*>(wq + 2 * RR), w3 = *reinterpret_cast<const float4*>(wq + 3 * RR);
+#pragma unroll
+            for (int j = 0; j < SQ; ++j) {
+                const float4 v = *reinterpret_cast<const float4*>(buf + j * KROW + 4 * q);
+                acc[0][j] = fmaf(w0.x, v.x, acc[0][j]); acc[1][j] = fmaf(w0.y, v.x, acc[1][j]);
+                acc[2][j] = fmaf(w0.z, v.x, acc[2][j]); acc[3][j] = fmaf(w0.w, v.x, acc[3][j]);
+                acc[0][j] = fmaf(w1.x, v.y, acc[0][j]); acc[1][j] = fmaf(w1.y, v.y, acc[1][j]);
+                acc[2][j] = fmaf(w1.z, v.y, acc[2][j]); acc[3][j] = fmaf(w1.w, v.y, acc[3][j]);
+                acc[0][j] = fmaf(w2.x, v.z, acc[0][j]); acc[1][j] = fmaf(w2.y, v.z, acc[1][j]);
+                acc[2][j] = fmaf(w2.z, v.z, acc[2][j]); acc[3][j] = fmaf(w2.w, v.z, acc[3][j]);
+                acc[0][j] = fmaf(w3.x, v.w, acc[0][j]); acc[1][j] = fmaf(w3.y, v.w, acc[1][j]);
+                acc[2][j] = fmaf(w3.z, v.w, acc[2][j]); acc[3][j] = fmaf(w3.w, v.w, acc[3][j]);
+            }
+        }
+        __syncthreads();                               // buffer c % 3 is refilled by the issue of the next iteration
+    }
+    copy_wait_prior<0>();
+}
+
+template <int SQ>
+__device__ __forceinline__ void run_steps(const ResParams& p, float* sw, float* abuf, int dir, int ug) {
+    constexpr int SP = 4 * SQ;
+    static_assert(SQ == 1 || SQ == 2 || SQ == 3 || SQ == 5, "sequence groups of 1, 2, 3 or 5");
+    static_assert(RW * SP * RR <= ABUF, "partial-sum buffer");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, rg = lane >> 2, sg = lane & 3;
+    const int H2 = 2 * kImuH;
+    const float* bsrc = p.bias + (dir * RGROUPS + ug) * RR;      // 32 floats, L1-resident
+    for (int t = p.t_begin; t < p.t_end; ++t) {
+        const int tt = dir ? p.T - 1 - t : t, tp = dir ? tt + 1 : tt - 1;
+        const int nblocks = (p.S + SP - 1) / SP;
+        bool waited = t == 0;
+        for (int blk = 0; blk < nblocks; ++blk) {
+            const int s0 = blk * SP, nseq = (p.S - s0) < SP ? (p.S - s0) : SP;
+            float acc[4][SQ];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int j = 0; j < SQ; ++j) acc[r][j] = 0.f;
+            // ---- input half: x_t W_ih^T (independent of the other CTAs; runs before the wait for h_{t-1}) ------------
+            segment<SQ>(sw, abuf, p.x + ((size_t)s0 * p.T + tt) * p.In, (size_t)p.T * p.In, nseq, 0, p.In, tid, acc);
+            if (t > 0) {
+                if (!waited) {
+                    // ---- wait for h_{t-1} of all 64 unit groups of this direction ------------------------------------
+                    if (p.flags && tid == 0) {
+                        volatile unsigned* f = p.flags + dir * p.T + (t - 1);
+                        unsigned polls = 0;
+                        while (*f < (unsigned)RGROUPS) {
+#ifndef MMEGO_EMUL
+                            __nanosleep(20);
+#endif
+                            if (++polls > (1u << 22)) {        // ~0.1 s: something is badly wrong -- do not hang the GPU
+                                *p.error = 1u;
+                                break;
+                            }
+                        }
+                        __threadfence();
+                    }
+                    __syncthreads();
+                    waited = true;
+                }
+                // ---- recurrent half: h_{t-1} W_hh^T (h is read through L2: other CTAs wrote it) ----------------------
+                segment<SQ>(sw, abuf, p.y + ((size_t)s0 * p.T + tp) * H2 + dir * kImuH, (size_t)p.T * H2, nseq, p.In, kImuH,
+                            tid, acc);
+            }
+            // ---- cross-warp sum of the K slices (the chunk buffers are free now), then the cell update ------------------
+            float* red = abuf;                                   // [RW][SP][32]
+#pragma unroll
+            for (int j = 0; j < SQ; ++j)
+                *reinterpret_cast<float4*>(red + ((size_t)(warp * SP + sg * SQ + j)) * RR + 4 * rg) =
+                    make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+            __syncthreads();
+            for (int i = tid; i < nseq * RU; i += RT) {
+                const int sl = i / RU, u = i % RU, s = s0 + sl;
+                float pre[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float v = bsrc[g * RU + u];
+#pragma unroll
+                    for (int w = 0; w < RW; ++w) v += red[(w * SP + sl) * RR + g * RU + u];
+                    pre[g] = v;
+                }
+                const float gi = sigm(pre[0]), gf = sigm(pre[1]), gg = tanhf(pre[2]), go = sigm(pre[3]);
+                float* cp = p.cstate + ((size_t)dir * p.S + s) * kImuH + ug * RU + u;
+                const float cprev = t > 0 ? *cp : 0.f;
+                const float cn = gf * cprev + gi * gg;
+                *cp = cn;
+                p.y[((size_t)s * p.T + tt) * H2 + dir * kImuH + ug * RU + u] = go * tanhf(cn);
+            }
+            __syncthreads();                                     // red is rewritten by the next block / step
+        }
+        __threadfence();
+        __syncthreads();
+        if (p.flags && tid == 0) atomicAdd(p.flags + dir * p.T + t, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(RT, 1) lstm_resident_kernel(const ResParams p) {
+    MMEGO_DYN_SMEM(float, sm);
+    float* sw = sm;                                    // [K][32]
+    float* abuf = sm + (size_t)p.K * RR;               // activation chunks [3][20][132], later [RW][SP][32] partial sums
+    const int tid = threadIdx.x;
+    const int dir = blockIdx.x / RGROUPS, ug = blockIdx.x % RGROUPS;
+    {
+        const float4* src = reinterpret_cast<const float4*>(p.w + ((size_t)(dir * RGROUPS + ug)) * p.K * RR);
+        float4* dst = reinterpret_cast<float4*>(sw);
+        for (int i = tid; i < p.K * RR / 4; i += RT) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    // register tile = 4 gate rows x SQ sequences per lane; a block of the K loop covers 4 SQ sequences
+    if (p.S <= 4) run_steps<1>(p, sw, abuf, dir, ug);
+    else if (p.S <= 8) run_steps<2>(p, sw, abuf, dir, ug);
+    else if (p.S <= 12) run_steps<3>(p, sw, abuf, dir, ug);
+    else run_steps<5>(p, sw, abuf, dir, ug);
+}
+
+// fc1 + ReLU in fp32 (Net/IMU_Net.py:79): imu [rows,15] -> u [rows,512]; w = [512][15] | bias [512]
+__global__ void __launch_bounds__(256) res_fc1_kernel(const float* __restrict__ imu, const float* __restrict__ w,
+                                                      float* __restrict__ u, long long rows) {
+    __shared__ float sw[kImuH * kImuFeat + kImuH];
+    for (int i = threadIdx.x; i < kImuH * kImuFeat + kImuH; i += 256) sw[i] = w[i];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < rows * kImuH; i += (long long)gridDim.x * 256) {
+        const long long r = i / kImuH;
+        const int c = (int)(i % kImuH);
+        const float* x = imu + r * kImuFeat;
+        float a = sw[kImuH * kImuFeat + c];
+#pragma unroll
+        for (int k = 0; k < kImuFeat; ++k) a = fmaf(sw[c * kImuFeat + k], x[k], a);
+        u[i] = fmaxf(a, 0.f);
+    }
+}
+
+}  // namespace
+
+// [2 dirs][64 groups][K][32]: col = gate*8 + u  <->  torch row gate*512 + group*8 + u;  k < In: W_ih, else W_hh
+void pack_resident_layer(const StateDict& sd, const std::string& prefix, int layer, int In, std::vector<float>& w,
+                         std::vector<float>& bias) {
+    const int H = kImuH, K = In + H;
+    w.assign((size_t)2 * RGROUPS * K * RR, 0.f);
+    bias.assign((size_t)2 * RGROUPS * RR, 0.f);
+    const char* sfx[2] = {"", "_reverse"};
+    for (int d = 0; d < 2; ++d) {
+        const std::string k = "l" + std::to_string(layer) + sfx[d];
+        const float* wih = sd.get(prefix + "weight_ih_" + k, (long long)4 * H * In);
+        const float* whh = sd.get(prefix + "weight_hh_" + k, (long long)4 * H * H);
+        const float* bih = sd.get(prefix + "bias_ih_" + k, 4 * H);
+        const float* bhh = sd.get(prefix + "bias_hh_" + k, 4 * H);
+        for (int ug = 0; ug < RGROUPS; ++ug) {
+            float* dst = &w[((size_t)d * RGROUPS + ug) * K * RR];
+            for (int col = 0; col < RR; ++col) {
+                const int r = (col / RU) * H + ug * RU + col % RU;
+                for (int kk = 0; kk < In; ++kk) dst[(size_t)kk * RR + col] = wih[(size_t)r * In + kk];
+                for (int kk = 0; kk < H; ++kk) dst[(size_t)(In + kk) * RR + col] = whh[(size_t)r * H + kk];
+                bias[((size_t)d * RGROUPS + ug) * RR + col] = bih[r] + bhh[r];
+            }
+        }
+    }
+}
+
+size_t resident_smem_bytes(int K) { return ((size_t)K * RR + ABUF) * sizeof(float); }
+
+#ifdef MMEGO_EMUL
+bool resident_supported(int) { return true; }          // the emulator runs one timestep per launch: no co-residency needed
+#else
+bool resident_supported(int sm_count) { return sm_count >= 2 * RGROUPS; }   // all 128 CTAs must be co-resident (1 per SM)
+#endif
+
+// One bidirectional H=512 layer over T steps for S <= kResMaxSeq sequences, fp32: x [S][T][In] -> y [S][T][1024].
+// cstate: [2][S][512] floats, flags: [2][T] unsigned + 1 error word (all scratch).  Returns 0, or -1 on a launch error.
+int launch_lstm_resident(const float* x, int In, float* y, const float* w, const float* bias, float* cstate,
+                         unsigned* flags, int S, int T, cudaStream_t st) {
+    ResParams p{};
+    p.x = x; p.y = y; p.w = w; p.bias = bias; p.cstate = cstate;
+    p.S = S; p.T = T; p.In = In; p.K = In + kImuH;
+    const size_t smem = resident_smem_bytes(p.K);
+    static int attr_bytes[64] = {0};
+    int d = 0;
+    cudaGetDevice(&d);
+    if (attr_bytes[d & 63] < (int)smem) {
+        if (cudaFuncSetAttribute(lstm_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return -1;
+        attr_bytes[d & 63] = (int)smem;
+    }
+#ifdef MMEGO_EMUL
+    // the emulator runs CTAs one after another: one launch per timestep, no inter-CTA waiting
+    p.flags = nullptr;
+    p.error = nullptr;
+    for (int t = 0; t < T; ++t) {
+        p.t_begin = t;
+        p.t_end = t + 1;
+        MMEGO_LAUNCH(lstm_resident_kernel, dim3(2 * RGROUPS), dim3(RT), smem, st, p);
+    }
+    return 0;
+#else
+    p.flags = flags;
+    p.error = flags + 2 * T;
+    p.t_begin = 0;
+    p.t_end = T;
+    if (cudaMemsetAsync(flags, 0, (size_t)(2 * T + 1) * sizeof(unsigned), st) != cudaSuccess) return -1;
+    void* args[] = {const_cast<ResParams*>(&p)};
+    ++t_launches;
+    return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_resident_kernel), dim3(2 * RGROUPS), dim3(RT), args, smem,
+                                       st) == cudaSuccess ? 0 : -1;
+#endif
+}
+
+void launch_res_fc1(const float* imu, const float* w, float* u, long long rows, cudaStream_t st) {
+    if (rows <= 0) return;
+    long long blocks = (rows * kImuH + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    MMEGO_LAUNCH(res_fc1_kernel, dim3((unsigned)blocks), dim3(256), 0, st, imu, w, u, rows);
+}
+
+}  // namespace mmego

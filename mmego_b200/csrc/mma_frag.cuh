@@ -126,6 +126,34 @@ __device__ __forceinline__ void dense_tile(const uint4* __restrict__ wf, const f
     }
 }
 
+// The same layer on TWO independent 16-row tiles of one warp: every B fragment is loaded from shared memory once and
+// feeds both tiles, and the two tiles' MMA chains interleave (the layer chains are latency-bound when a warp carries a
+// single tile: each layer's MMAs depend on the previous layer's epilogue).
+template <int KS, int NT, bool RELU, int NTW = NT>
+__device__ __forceinline__ void dense_tile2(const uint4* __restrict__ wf, const float* __restrict__ bias, float oscale,
+                                            const uint32_t (&ahi)[2][KS][4], const uint32_t (&alo)[2][KS][4],
+                                            float (&out)[2][NT][4], int lane, int j0 = 0) {
+    const int t = lane & 3;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        float big[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, small[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const uint4 b = wf[(s * NTW + j0 + j) * 32 + lane];
+            mma3(big[0], small[0], ahi[0][s], alo[0][s], b);
+            mma3(big[1], small[1], ahi[1][s], alo[1][s], b);
+        }
+        const float2 bv = *reinterpret_cast<const float2*>(bias + 8 * (j0 + j) + 2 * t);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float v = fmaf(big[u][i] + small[u][i], oscale, (i & 1) ? bv.y : bv.x);
+                out[u][j][i] = RELU ? fmaxf(v, 0.f) : v;
+            }
+    }
+}
+
 // C fragments of NT n-tiles -> A fragments of KS k-steps (k-step s = n-tiles 2s, 2s+1; missing tiles are zero)
 template <int NT, int KS>
 __device__ __forceinline__ void to_afrag(const float (&c)[NT][4], uint32_t (&ahi)[KS][4], uint32_t (&alo)[KS][4]) {

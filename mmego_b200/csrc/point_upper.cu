@@ -153,16 +153,19 @@ __global__ void __launch_bounds__(PT) upper_point_kernel(float* __restrict__ x, 
 // Per 16-point tile: 150 MMAs (50 fragment products x 3) against 6,144 FFMAs per POINT in the kernel above.
 // ================================================================================================================
 using UM = UpperMmaLayout;
-constexpr int MT = 256;                 // threads per CTA
-constexpr int MW = MT / 32;             // warps = 16-point tiles per chunk
+constexpr int MT = 128;                 // threads per CTA
+constexpr int MW = MT / 32;             // warps; a warp carries TWO 16-point tiles at a time (32 points)
 constexpr int PART_LD = 68;             // [64 channel sums | max | sum | pad]
 
 struct MmaSmem {
     uint32_t w[UM::TOTAL];              // fragment-ordered weights, biases, attention vector, scales
-    float tile[MW][16][8];              // transformed input points of each warp's tile (6 channels + 2 zero)
+    float tile[MW][32][8];              // transformed input points of each warp's tile pair (6 channels + 2 zero)
     float part[2][MW][PART_LD];         // per-warp softmax partials, double-buffered by frame parity
 };
 
+// Two tiles per warp: every B fragment read from shared memory feeds two MMA chains (half the fragment loads per MMA)
+// and the warp always has two independent dependency chains in flight -- with one tile per warp the kernel sat at 47 %
+// tensor-pipe / 53 % issue utilisation (profiles/r01small2_ncu_summary.txt): latency-bound on the layer-to-layer chain.
 __global__ void __launch_bounds__(MT, 2) upper_point_mma_kernel(float* __restrict__ x, const float* __restrict__ R,
                                                                 const float* __restrict__ t,
                                                                 const float* __restrict__ wblob,
@@ -186,25 +189,32 @@ __global__ void __launch_bounds__(MT, 2) upper_point_mma_kernel(float* __restric
         float gp[16];                    // weighted sums of channels 8j + 2*tq + {0,1}, over this lane's rows
 #pragma unroll
         for (int i = 0; i < 16; ++i) gp[i] = 0.f;
+        float rt[12];
+        {
+            const float* Rf = R + f * 9;
+            const float* tf = t + f * 3;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) rt[k] = __ldg(Rf + k);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rt[9 + k] = __ldg(tf + k);
+        }
 
-        for (int p0 = 0; p0 < N; p0 += MW * 16) {
-            const int pbase = p0 + warp * 16;
-            if (pbase >= N) break;       // warp-uniform: no live point in this tile
-            // ---- load + Transform2H (in place) of the tile's 16 points: one point per lane, lanes 0..15 -------
+        for (int p0 = 0; p0 < N; p0 += MW * 32) {
+            const int pbase = p0 + warp * 32;
+            if (pbase >= N) break;       // warp-uniform: no live point in this tile pair
+            // ---- load + Transform2H (in place) of the pair's 32 points: one point per lane -----------------------
             __syncwarp();
-            if (lane < 16) {
+            {
                 const int p = pbase + lane;
                 float in[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (p < N) {
                     const float2 v0 = *reinterpret_cast<const float2*>(xf + p * 6);
                     const float2 v1 = *reinterpret_cast<const float2*>(xf + p * 6 + 2);
                     const float2 v2 = *reinterpret_cast<const float2*>(xf + p * 6 + 4);
-                    const float* Rf = R + f * 9;
-                    const float* tf = t + f * 3;
-                    const float dx = v0.x - __ldg(tf), dy = v0.y - __ldg(tf + 1), dz = v1.x - __ldg(tf + 2);
-                    in[0] = __ldg(Rf + 0) * dx + __ldg(Rf + 1) * dy + __ldg(Rf + 2) * dz;
-                    in[1] = __ldg(Rf + 3) * dx + __ldg(Rf + 4) * dy + __ldg(Rf + 5) * dz;
-                    in[2] = __ldg(Rf + 6) * dx + __ldg(Rf + 7) * dy + __ldg(Rf + 8) * dz;
+                    const float dx = v0.x - rt[9], dy = v0.y - rt[10], dz = v1.x - rt[11];
+                    in[0] = rt[0] * dx + rt[1] * dy + rt[2] * dz;
+                    in[1] = rt[3] * dx + rt[4] * dy + rt[5] * dz;
+                    in[2] = rt[6] * dx + rt[7] * dy + rt[8] * dz;
                     in[3] = v1.y; in[4] = v2.x; in[5] = v2.y;
                     *reinterpret_cast<float2*>(xf + p * 6) = make_float2(in[0], in[1]);
                     xf[p * 6 + 2] = in[2];
@@ -213,86 +223,112 @@ __global__ void __launch_bounds__(MT, 2) upper_point_mma_kernel(float* __restric
                 *reinterpret_cast<float4*>(&s.tile[warp][lane][4]) = make_float4(in[4], in[5], 0.f, 0.f);
             }
             __syncwarp();
-            // ---- layer-1 A fragment: rows g, g+8; channels 2tq, 2tq+1 (k 8..15 are zero padding) --------------
-            uint32_t a1h[1][4], a1l[1][4];
-            {
-                const float2 r0 = *reinterpret_cast<const float2*>(&s.tile[warp][g][2 * tq]);
-                const float2 r1 = *reinterpret_cast<const float2*>(&s.tile[warp][g + 8][2 * tq]);
-                frag::split2(r0.x, r0.y, a1h[0][0], a1l[0][0]);
-                frag::split2(r1.x, r1.y, a1h[0][1], a1l[0][1]);
-                a1h[0][2] = a1h[0][3] = a1l[0][2] = a1l[0][3] = 0u;
+            // ---- layer-1 A fragments (tile u = points pbase + 16u ..): rows g, g+8; channels 2tq, 2tq+1 ------------
+            uint32_t a1h[2][1][4], a1l[2][1][4];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float2 r0 = *reinterpret_cast<const float2*>(&s.tile[warp][16 * u + g][2 * tq]);
+                const float2 r1 = *reinterpret_cast<const float2*>(&s.tile[warp][16 * u + g + 8][2 * tq]);
+                frag::split2(r0.x, r0.y, a1h[u][0][0], a1l[u][0][0]);
+                frag::split2(r1.x, r1.y, a1h[u][0][1], a1l[u][0][1]);
+                a1h[u][0][2] = a1h[u][0][3] = a1l[u][0][2] = a1l[u][0][3] = 0u;
             }
-            float psi[UM::NT6][4];
+            float psi[2][UM::NT6][4];
             {
-                float c1[UM::NT1][4];
-                frag::dense_tile<UM::KS1, UM::NT1, true>(wf + UM::F1 / 4, wfl + UM::BI1, osc[0], a1h, a1l, c1, lane);
-                uint32_t a2h[UM::KS2][4], a2l[UM::KS2][4];
-                frag::to_afrag<UM::NT1, UM::KS2>(c1, a2h, a2l);
-                float c2[UM::NT2][4];
-                frag::dense_tile<UM::KS2, UM::NT2, true>(wf + UM::F2 / 4, wfl + UM::BI2, osc[1], a2h, a2l, c2, lane);
-                uint32_t a3h[UM::KS3][4], a3l[UM::KS3][4];
-                frag::to_afrag<UM::NT2, UM::KS3>(c2, a3h, a3l);
-                float c3[UM::NT3][4];
-                frag::dense_tile<UM::KS3, UM::NT3, true>(wf + UM::F3 / 4, wfl + UM::BI3, osc[2], a3h, a3l, c3, lane);
+                float c1[2][UM::NT1][4];
+                frag::dense_tile2<UM::KS1, UM::NT1, true>(wf + UM::F1 / 4, wfl + UM::BI1, osc[0], a1h, a1l, c1, lane);
+                uint32_t a2h[2][UM::KS2][4], a2l[2][UM::KS2][4];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) frag::to_afrag<UM::NT1, UM::KS2>(c1[u], a2h[u], a2l[u]);
+                float c2[2][UM::NT2][4];
+                frag::dense_tile2<UM::KS2, UM::NT2, true>(wf + UM::F2 / 4, wfl + UM::BI2, osc[1], a2h, a2l, c2, lane);
+                uint32_t a3h[2][UM::KS3][4], a3l[2][UM::KS3][4];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) frag::to_afrag<UM::NT2, UM::KS3>(c2[u], a3h[u], a3l[u]);
+                float c3[2][UM::NT3][4];
+                frag::dense_tile2<UM::KS3, UM::NT3, true>(wf + UM::F3 / 4, wfl + UM::BI3, osc[2], a3h, a3l, c3, lane);
                 // layer 4 reads [feat 0..23 | x[0:4] | pad]: k-step 1 = feat 16..23 and, in its upper half, the
                 // first four input channels, which are exactly words 0/1 of the layer-1 fragment of lanes tq < 2
-                uint32_t a4h[UM::KS4][4], a4l[UM::KS4][4];
-                frag::to_afrag<UM::NT3, UM::KS4>(c3, a4h, a4l);
-                a4h[1][2] = tq < 2 ? a1h[0][0] : 0u;
-                a4h[1][3] = tq < 2 ? a1h[0][1] : 0u;
-                a4l[1][2] = tq < 2 ? a1l[0][0] : 0u;
-                a4l[1][3] = tq < 2 ? a1l[0][1] : 0u;
-                float c4[UM::NT4][4];
-                frag::dense_tile<UM::KS4, UM::NT4, true>(wf + UM::F4 / 4, wfl + UM::BI4, osc[3], a4h, a4l, c4, lane);
-                uint32_t a5h[UM::KS5][4], a5l[UM::KS5][4];
-                frag::to_afrag<UM::NT4, UM::KS5>(c4, a5h, a5l);
-                float c5[UM::NT5][4];
-                frag::dense_tile<UM::KS5, UM::NT5, true>(wf + UM::F5 / 4, wfl + UM::BI5, osc[4], a5h, a5l, c5, lane);
-                uint32_t a6h[UM::KS6][4], a6l[UM::KS6][4];
-                frag::to_afrag<UM::NT5, UM::KS6>(c5, a6h, a6l);
-                frag::dense_tile<UM::KS6, UM::NT6, true>(wf + UM::F6 / 4, wfl + UM::BI6, osc[5], a6h, a6l, psi, lane);
+                uint32_t a4h[2][UM::KS4][4], a4l[2][UM::KS4][4];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    frag::to_afrag<UM::NT3, UM::KS4>(c3[u], a4h[u], a4l[u]);
+                    a4h[u][1][2] = tq < 2 ? a1h[u][0][0] : 0u;
+                    a4h[u][1][3] = tq < 2 ? a1h[u][0][1] : 0u;
+                    a4l[u][1][2] = tq < 2 ? a1l[u][0][0] : 0u;
+                    a4l[u][1][3] = tq < 2 ? a1l[u][0][1] : 0u;
+                }
+                float c4[2][UM::NT4][4];
+                frag::dense_tile2<UM::KS4, UM::NT4, true>(wf + UM::F4 / 4, wfl + UM::BI4, osc[3], a4h, a4l, c4, lane);
+                uint32_t a5h[2][UM::KS5][4], a5l[2][UM::KS5][4];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) frag::to_afrag<UM::NT4, UM::KS5>(c4[u], a5h[u], a5l[u]);
+                float c5[2][UM::NT5][4];
+                frag::dense_tile2<UM::KS5, UM::NT5, true>(wf + UM::F5 / 4, wfl + UM::BI5, osc[4], a5h, a5l, c5, lane);
+                uint32_t a6h[2][UM::KS6][4], a6l[2][UM::KS6][4];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) frag::to_afrag<UM::NT5, UM::KS6>(c5[u], a6h[u], a6l[u]);
+                frag::dense_tile2<UM::KS6, UM::NT6, true>(wf + UM::F6 / 4, wfl + UM::BI6, osc[5], a6h, a6l, psi, lane);
             }
-            // ---- attention scores of rows g and g+8 (fp32 FFMA; quad reduce) -----------------------------------
-            float s0 = 0.f, s1 = 0.f;
+            // ---- attention scores of this lane's four rows (tile u: rows g, g+8) (fp32 FFMA; quad reduce) ----------
+            float sc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
             for (int j = 0; j < UM::NT6; ++j) {
                 const float2 wa = *reinterpret_cast<const float2*>(wfl + UM::WA + 8 * j + 2 * tq);
-                s0 = fmaf(wa.x, psi[j][0], s0);
-                s0 = fmaf(wa.y, psi[j][1], s0);
-                s1 = fmaf(wa.x, psi[j][2], s1);
-                s1 = fmaf(wa.y, psi[j][3], s1);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    sc[u][0] = fmaf(wa.x, psi[u][j][0], sc[u][0]);
+                    sc[u][0] = fmaf(wa.y, psi[u][j][1], sc[u][0]);
+                    sc[u][1] = fmaf(wa.x, psi[u][j][2], sc[u][1]);
+                    sc[u][1] = fmaf(wa.y, psi[u][j][3], sc[u][1]);
+                }
             }
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
             const float ba = wfl[UM::BA];
-            const bool live0 = pbase + g < N, live1 = pbase + g + 8 < N;
-            s0 = live0 ? s0 + ba : -INFINITY;
-            s1 = live1 ? s1 + ba : -INFINITY;
-            if (gwf && tq == 0) {          // raw scores; normalised after the frame's max and sum are known
-                if (live0) gwf[pbase + g] = s0;
-                if (live1) gwf[pbase + g + 8] = s1;
-            }
-            // ---- online softmax over this warp's points ---------------------------------------------------------
-            float cm = fmaxf(s0, s1);
+            bool live[2][2];
+            float cm = -INFINITY;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    float v = sc[u][hrow];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    const int p = pbase + 16 * u + g + 8 * hrow;
+                    live[u][hrow] = p < N;
+                    v = live[u][hrow] ? v + ba : -INFINITY;
+                    sc[u][hrow] = v;
+                    if (gwf && tq == 0 && live[u][hrow]) gwf[p] = v;   // raw scores; normalised once max and sum are known
+                    cm = fmaxf(cm, v);
+                }
+            // ---- online softmax over this warp's points -----------------------------------------------------------
 #pragma unroll
             for (int o = 4; o < 32; o <<= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
-            const float new_m = fmaxf(run_m, cm);          // finite: row 0 of the tile is live
-            const float e0 = live0 ? expf(s0 - new_m) : 0.f, e1 = live1 ? expf(s1 - new_m) : 0.f;
-            float es = e0 + e1;
+            const float new_m = fmaxf(run_m, cm);          // finite: row 0 of the pair is live
+            float e[2][2];
+            float es = 0.f;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    e[u][hrow] = live[u][hrow] ? expf(sc[u][hrow] - new_m) : 0.f;
+                    es += e[u][hrow];
+                }
 #pragma unroll
             for (int o = 4; o < 32; o <<= 1) es += __shfl_xor_sync(0xffffffffu, es, o);
             const float rescale = (run_m == -INFINITY) ? 0.f : expf(run_m - new_m);
 #pragma unroll
             for (int j = 0; j < UM::NT6; ++j) {
-                gp[2 * j] = fmaf(gp[2 * j], rescale, fmaf(e0, psi[j][0], e1 * psi[j][2]));
-                gp[2 * j + 1] = fmaf(gp[2 * j + 1], rescale, fmaf(e0, psi[j][1], e1 * psi[j][3]));
+                float a0 = fmaf(e[0][0], psi[0][j][0], e[0][1] * psi[0][j][2]);
+                float a1 = fmaf(e[0][0], psi[0][j][1], e[0][1] * psi[0][j][3]);
+                a0 = fmaf(e[1][0], psi[1][j][0], fmaf(e[1][1], psi[1][j][2], a0));
+                a1 = fmaf(e[1][0], psi[1][j][1], fmaf(e[1][1], psi[1][j][3], a1));
+                gp[2 * j] = fmaf(gp[2 * j], rescale, a0);
+                gp[2 * j + 1] = fmaf(gp[2 * j + 1], rescale, a1);
             }
             run_s = fmaf(run_s, rescale, es);
             run_m = new_m;
         }
-        // ---- merge the 8 warps ------------------------------------------------------------------------------------
+        // ---- merge the warps ------------------------------------------------------------------------------------
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             float v = gp[i];
@@ -315,9 +351,9 @@ __global__ void __launch_bounds__(MT, 2) upper_point_mma_kernel(float* __restric
 #pragma unroll
         for (int w = 0; w < MW; ++w) {
             const float mw = s.part[parity][w][64];
-            const float sc = (mw == -INFINITY) ? 0.f : expf(mw - M);
-            S = fmaf(sc, s.part[parity][w][65], S);
-            if (tid < 64) G = fmaf(sc, s.part[parity][w][tid], G);
+            const float scw = (mw == -INFINITY) ? 0.f : expf(mw - M);
+            S = fmaf(scw, s.part[parity][w][65], S);
+            if (tid < 64) G = fmaf(scw, s.part[parity][w][tid], G);
         }
         const float inv = __fdividef(1.0f, S);      // S in [1, N]; no IEEE slow path between warp-wide MMAs (see lstm_small.cu)
         if (tid < 64) gout[f * 64 + tid] = G * inv;
@@ -355,7 +391,7 @@ void launch_upper_point_mma(float* x, const float* R, const float* t, const floa
     if (first_use_on_device(attr_set)) {
         cudaFuncSetAttribute(upper_point_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MmaSmem));
     }
-    long long grid = F < (long long)sm_count * 2 ? F : (long long)sm_count * 2;
+    long long grid = F < (long long)sm_count * 2 ? F : (long long)sm_count * 2;     // 2 CTAs of 128 threads x 250 registers per SM
     MMEGO_LAUNCH(upper_point_mma_kernel, dim3((unsigned)grid), dim3(MT), sizeof(MmaSmem), st, x, R, t, wblob, g, gw, F,
                  N);
 }

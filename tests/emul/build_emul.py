@@ -17,7 +17,7 @@ OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libmmego_emul.so")
 
 SOURCES = ["api.cu", "gemm_ffma.cu", "point_upper.cu", "lower_frame.cu", "lstm_small.cu", "gcn.cu", "decode.cu", "snippet.cu", "heads_mma.cu",
-           "pack.cpp"]
+           "lstm_resident.cu", "pack.cpp"]
 FLAGS = ["-O2", "-std=c++17", "-fPIC", "-DMMEGO_EMUL", "-I", HERE, "-I", CSRC, "-Wno-unused-result", "-Wno-attributes"]
 
 

@@ -166,3 +166,20 @@ def test_boundary_validates_sizes_before_the_library_reads_them(handle):
     n_frames = raw["pt_start"].numel() - 1
     with pytest.raises(_capi.MMEgoError, match="raw frames"):
         handle.build_snippets(raw, torch.tensor([n_frames - 5], dtype=torch.int64))
+
+
+def test_imu_latency_path_matches_oracle_and_ffma_path(handle):
+    """The resident-weights fp32 LSTM kernels (small-batch latency path) on the emulator -- one launch per timestep there,
+    the same kernel code -- against the oracle and against the fp32 FFMA generation."""
+    from oracle import mmego_oracle as O
+    for B, L, n in ((1, 20, 20), (3, 5, 3), (3, 20, 2)):
+        sb = O.synth_batch(B, L=L, N=64, n_imu=n, seed=5 + B)
+        R1, t1 = handle.imu_forward(sb["imu"])
+        handle.set_option("imu_resident", 0)
+        try:
+            R0, t0 = handle.imu_forward(sb["imu"])
+        finally:
+            handle.set_option("imu_resident", 1)
+        Rr, tr = O.imu_forward(O.synth_imu_state_dict(0), sb["imu"])
+        assert P.rot_angle_deg(R1, Rr) < P.ANG_TOL / 2 and P.maxerr(t1, tr) < 1e-6
+        assert P.rot_angle_deg(R1, R0) < P.ANG_TOL / 2
