@@ -76,6 +76,28 @@ def pack(root, max_recordings=None):
                 t_R0R=np.asarray(t0), **ref)
 
 
+def pack_extras(root, max_recordings=None):
+    """The three loader fields the inference path never reads (Dataset_sample.py:182, 195-202): per frame the raw
+    foot-contact flags and the ground plane (sign-normalised as the loader does); R_RtW is a product of R_btc (already in
+    the main cache) with two constant matrices and is formed on the host.  Kept in a separate small file so that the
+    57 MB main cache stays untouched."""
+    foot, ground = [], []
+    for rec, mats in walk(root):
+        if max_recordings is not None and rec >= max_recordings:
+            break
+        for f in mats:
+            d = scio.loadmat(f)
+            if len(d["pc_xyziv_ti2"]) == 0:
+                continue
+            fc = np.asarray(d["foot_contact"])
+            foot.append([1 if fc[0, 0] else 0, 1 if fc[0, 1] else 0])
+            g = np.asarray(d["abcd_ground_2"], dtype=np.float64)
+            if g[0, 0] > 0:
+                g = -1 * g
+            ground.append(g.reshape(1, 4))
+    return dict(foot_contact_raw=np.asarray(foot, np.uint8), ground=np.asarray(ground, np.float64))
+
+
 def reference_tensors(checkout, n_snippets):
     for m in ("matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.animation", "seaborn", "imageio",
               "imageio.v2", "mpl_toolkits", "mpl_toolkits.mplot3d"):
@@ -96,7 +118,28 @@ def main():
     ap.add_argument("--out")
     ap.add_argument("--fixture")
     ap.add_argument("--recordings", type=int, default=3)
+    ap.add_argument("--extras", help="write the ground / foot-contact side file (Resource/Sample_data_packed/extras.npz)")
+    ap.add_argument("--extras-fixture", help="side file for the first --recordings recordings + the reference loader's own fields")
     a = ap.parse_args()
+    if a.extras:
+        d = pack_extras(a.root)
+        np.savez_compressed(a.extras, **d)
+        print(a.extras, "frames", len(d["ground"]), os.path.getsize(a.extras), "bytes")
+    if a.extras_fixture:
+        d = pack_extras(a.root, a.recordings)
+        main_d = pack(a.root, a.recordings)
+        nsn = int(sum((main_d["rec_start"][i + 1] - main_d["rec_start"][i]) // 20 for i in range(len(main_d["rec_start"]) - 1)))
+        for m in ("matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.animation", "seaborn", "imageio",
+                  "imageio.v2", "mpl_toolkits", "mpl_toolkits.mplot3d"):
+            sys.modules.setdefault(m, types.ModuleType(m))
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(a.root))))
+        from Util.Universal_Util.Dataset_sample import PosePC
+        np.random.seed(0)
+        ds = PosePC(train=False, vis=True, batch_length=20)
+        d.update(exp_ground=np.asarray(ds.ground_[:nsn]), exp_foot_contact=np.asarray(ds.foot_contact_[:nsn]),
+                 exp_R_RtW=np.asarray(ds.R_RtW_[:nsn]))
+        np.savez_compressed(a.extras_fixture, **d)
+        print(a.extras_fixture, "snippets", nsn, os.path.getsize(a.extras_fixture), "bytes")
     if a.out:
         d = pack(a.root)
         os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)

@@ -41,6 +41,7 @@ def main():
     dev = torch.device("cuda:0")
     pipe = MMEgoPipeline(dev)
     h = pipe.handle
+    h.set_option("imu_resident", 0)          # the sweep measures the throughput kernels
     out = {"peaks": {"hbm_gbs": PEAKS["hbm_gbs"], "bf16_tflops_sustained": PEAKS["bf16_tflops_sustained"]}, "config2": [],
            "config5": []}
     # ---- config 2: IMU_Net standalone, B=4096
@@ -97,12 +98,46 @@ def main():
                                "frac_of_measured_bf16_sustained": fl / lst / 1e9 / PEAKS["bf16_tflops_sustained"]}
             sm = row["ms"]["small_lstm"]
             row["small_lstm"] = {"gflops": F * (524288 + 655360) / sm / 1e6}
+            # ---- roofline fractions against the measured peaks (MEASURED_PEAKS.json; mma.sync peak from
+            # profiles/r01_ubench_mma_sync_rate.txt: 557 TFLOP/s f16 on this pool's B200).  "issued" = 3 fp16 MMA passes per
+            # algorithmic multiply (fp32-grade split products).
+            MMA_SYNC_PEAK = 557.0
+            bf16 = PEAKS["bf16_tflops_sustained"]
+
+            def tensor(name, alg_flops, ms_, passes=3, peak=MMA_SYNC_PEAK, peak_name="mma.sync f16 measured 557 TFLOP/s"):
+                alg = alg_flops / ms_ / 1e9
+                return {"stage": name, "bound": "tensor", "algorithmic_tflops": round(alg, 2), "issued_tflops": round(alg * passes, 2),
+                        "peak": peak, "peak_name": peak_name, "frac_issued": round(alg * passes / peak, 4),
+                        "frac_algorithmic": round(alg / peak, 4), "frac_of_bf16_sustained": round(alg / bf16, 4)}
+
+            def hbm(name, nbytes, ms_):
+                g = nbytes / ms_ / 1e6
+                return {"stage": name, "bound": "hbm", "gbs": round(g, 1), "peak": PEAKS["hbm_gbs"], "frac": round(g / PEAKS["hbm_gbs"], 4)}
+
+            gcn = row["ms"]["lower.gcn"]
+            row["rooflines"] = [
+                tensor("upper.point (mma.sync, 12,256 FLOP/point)", F * N * 12256, pt),
+                hbm("upper.point (cloud in, xyz back, weights out, g)", F * (N * 40 + 304), pt),
+                tensor("lower.frame (mma.sync, 1.40 MFLOP/frame, top-64 of N)", F * 1.40e6, fr),
+                hbm("lower.frame (cloud in, xyz back, K in, ak out)", F * (N * 36 + 15 * 64 * 4 + 192 * 4 + 48), fr),
+                tensor("small_lstm: grnn + rnn_pk (mma.sync, H=64, 1.18 MFLOP/frame)", F * (524288 + 655360), sm),
+                tensor("lower.gcn (tcgen05, 7.18 MFLOP/frame)", F * 7.18e6, gcn, peak=bf16,
+                       peak_name="dense bf16 sustained (MEASURED_PEAKS.json)"),
+                tensor("imu LSTMs (tcgen05, rnn_fast + rnn_slow)", fl, lst, peak=bf16,
+                       peak_name="dense bf16 sustained (MEASURED_PEAKS.json)"),
+                hbm("imu.pool (y1 planes in, s planes out)", F * (20 * 1024 * 4 + 1024 * 4), row["ms"]["imu.pool"]),
+                hbm("imu.fc1 (imu in, u planes out)", F * 20 * (15 * 4 + 512 * 4), row["ms"]["imu.fc1"]),
+            ]
             out["config5"].append(row)
             print(json.dumps(row), flush=True)
             del sb, data0, x, imu
             torch.cuda.empty_cache()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "w"), indent=1)
+    # compact table
+    for row in out["config5"]:
+        print(f"L={row['L']:3d} N={row['N']:3d} B={row['B']:4d}: " + "; ".join(
+            f"{r['stage'].split(' ')[0]} {r.get('frac_issued', r.get('frac'))}" for r in row["rooflines"]))
     print(json.dumps(out["config2"]))
 
 

@@ -102,6 +102,15 @@ def test_posepc_windows_split(handle, tmp_path):
     assert np.array_equal(item[0], b["data"][1].cpu().numpy())
     assert np.array_equal(item[1], z["exp_key"][5])
     assert np.array_equal(item[6], z["exp_R"][5]) and item[7].shape == (20, 1, 3)
+    # the loader fields the networks never read, against the reference's own PosePC (tests/golden/extras_subset.npz)
+    ex = dict(np.load(os.path.join(P.GOLDEN, "extras_subset.npz")))
+    ex_path = os.path.join(tmp_path, "extras.npz")
+    np.savez(ex_path, ground=ex["ground"], foot_contact_raw=ex["foot_contact_raw"])
+    vis2 = PosePC(train=False, vis=True, packed_path=path, lib_handle=handle, extras_path=ex_path)
+    for i in (0, 5, 11):
+        it = vis2[i]
+        assert np.array_equal(it[4], ex["exp_ground"][i]) and np.array_equal(it[5], ex["exp_foot_contact"][i])
+        assert np.abs(it[8] - ex["exp_R_RtW"][i]).max() < 1e-12
 
 
 def test_errors(handle):
