@@ -50,7 +50,9 @@ SIGNATURES = {
 }
 
 PROFILE_SPANS = ("imu.fc1", "imu.lstm_fast", "imu.lstm_slow", "imu.pool", "imu.decode", "upper.point", "small_lstm", "upper.head_decode",
-                 "lower.gcn", "lower.frame", "lower.head_decode", "assemble_metrics")
+                 "lower.gcn", "lower.frame", "lower.head_decode", "assemble_metrics", "imu.resident",
+                 "gcn.agg0", "gcn.gconv0", "gcn.tconv0", "gcn.agg1", "gcn.gconv1", "gcn.tconv1", "gcn.agg2", "gcn.gconv2",
+                 "gcn.tconv2", "gcn.fcn")
 
 
 class MMEgoError(RuntimeError):

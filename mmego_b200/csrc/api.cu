@@ -536,16 +536,34 @@ int run_gcn_tc(mmego_handle* h, int B, int L, const LowerWs& w, cudaStream_t st)
             cudaMemsetAsync(w.p_ya[0], 0, (size_t)FV * 8 * 2, st);
             cudaMemsetAsync(w.p_ya[1], 0, (size_t)FV * 8 * 2, st);
         }
-        tc_gcn_agg(y[0], y[1], W.gcn[i].ahat.p, w.p_ya[0], w.p_ya[1], F, creal, ystride, os, h->sm_count, st);
-        rc |= tc_gcn_gemm(h, W.tc_gconv[i], w.p_ya[0], w.p_ya[1], os, 1, nullptr, nullptr, 0, kGcnV, 1, w.p_u[0], w.p_u[1],
-                          nullptr, B, RP, st);
+        static const char* kAgg[3] = {"gcn.agg0", "gcn.agg1", "gcn.agg2"};
+        static const char* kGc[3] = {"gcn.gconv0", "gcn.gconv1", "gcn.gconv2"};
+        static const char* kTc[3] = {"gcn.tconv0", "gcn.tconv1", "gcn.tconv2"};
+        {
+            Prof p(h, kAgg[i], st);
+            tc_gcn_agg(y[0], y[1], W.gcn[i].ahat.p, w.p_ya[0], w.p_ya[1], F, creal, ystride, os, h->sm_count, st);
+        }
+        {
+            Prof p(h, kGc[i], st);
+            rc |= tc_gcn_gemm(h, W.tc_gconv[i], w.p_ya[0], w.p_ya[1], os, 1, nullptr, nullptr, 0, kGcnV, 1, w.p_u[0], w.p_u[1],
+                              nullptr, B, RP, st);
+        }
         void* const* out = w.p_y[i & 1];
-        rc |= tc_gcn_gemm(h, W.tc_tconv[i], w.p_u[0], w.p_u[1], cout, 9, y[0], y[1], ystride, 0, 1, out[0], out[1], nullptr,
-                          B, RP, st);
+        {
+            Prof p(h, kTc[i], st);
+            if (h->gcn_snip && tc_gcn_tconv_snip_supported(L))
+                rc |= tc_gcn_tconv_snip(h, W.tc_tconv[i], w.p_u[0], w.p_u[1], cout, y[0], y[1], ystride, creal, out[0], out[1], B, L, st);
+            else
+                rc |= tc_gcn_gemm(h, W.tc_tconv[i], w.p_u[0], w.p_u[1], cout, 9, y[0], y[1], ystride, 0, 1, out[0], out[1],
+                                  nullptr, B, RP, st);
+        }
         y = out;
         ystride = creal = cout;
     }
-    rc |= tc_gcn_gemm(h, W.tc_fcn, y[0], y[1], 128, 1, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, w.kf, B, RP, st);
+    {
+        Prof p(h, "gcn.fcn", st);
+        rc |= tc_gcn_gemm(h, W.tc_fcn, y[0], y[1], 128, 1, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, w.kf, B, RP, st);
+    }
     return rc;
 }
 #endif
@@ -631,6 +649,7 @@ int mmego_destroy(mmego_handle* h) {
     for (void* p : h->owned) cudaFree(p);
     if (h->stage_dev) cudaFree(h->stage_dev);
     if (h->tc_stats) cudaFree(h->tc_stats);
+    if (h->dev_error) cudaFree(h->dev_error);
     for (ProfSpan& sp : h->prof) {
         if (sp.e0) cudaEventDestroy(sp.e0);
         if (sp.e1) cudaEventDestroy(sp.e1);
@@ -745,6 +764,10 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
 #else
         h->tc_lo_drop = (int)value;
 #endif
+        return MMEGO_OK;
+    }
+    if (!strcmp(key, "gcn_snip")) {
+        h->gcn_snip = (int)value;
         return MMEGO_OK;
     }
     if (!strcmp(key, "imu_resident")) {
@@ -1427,6 +1450,16 @@ int mmego_profile_read(mmego_handle* h, const char* name, double* total_ms, long
 int mmego_debug_stats(mmego_handle* h, unsigned long long* out8, int reset) {
     if (!h || !out8) return MMEGO_EINVAL;
     for (int i = 0; i < 8; ++i) out8[i] = 0;
+    if (h->dev_error) {       // out8[7]: set by a kernel whose bounded wait gave up (must stay 0)
+        unsigned e = 0;
+        CUDA_TRY(h, cudaDeviceSynchronize());
+        unsigned long long raw[8];
+        CUDA_TRY(h, cudaMemcpy(raw, h->dev_error, sizeof(raw), cudaMemcpyDeviceToHost));
+        e = (unsigned)(raw[0] & 0xffffffffu);
+        out8[7] = e;
+        for (int i = 2; i < 7; ++i) out8[i - 2] = raw[i];      // cycle accounting of tconv_snip_kernel (test builds only)
+        if (reset) CUDA_TRY(h, cudaMemset(h->dev_error, 0, 64));
+    }
     if (!h->tc_stats) return MMEGO_OK;
     CUDA_TRY(h, cudaDeviceSynchronize());
     CUDA_TRY(h, cudaMemcpy(out8, h->tc_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));

@@ -262,6 +262,322 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant_
     }
 }
 
+// ================================================================================================================
+// Snippet-resident temporal convolution (the 64 % of the ST-GCN chain's time):
+//     Y'[c', (l, w)] = relu( sum_tau sum_c Wt_tau[c', c] U[c, (l + tau - 4, w)] + sum_c Wr[c', c] Y[c, (l, w)] + b[c'] )
+// TRANSPOSED with respect to gemm_tc_kernel above: the output CHANNELS are the MMA's M (the weight tile is the A operand,
+// zero-filled by TMA to 128 rows), the snippet's ROWS are its N.  One CTA owns a whole snippet:
+//   * per 64-channel block the snippet's activation window (L frames x 16 rows x 64 ch, both planes: 80 KB at L = 20) is
+//     loaded ONCE -- a 4-D TMA box over [snippet][frame][joint][channel] whose 16th joint is out of bounds, so the TMA
+//     unit pads every frame to 16 rows: a temporal shift of one frame is then 2048 bytes = two swizzle atoms, and the nine
+//     taps read the SAME window through UMMA descriptors with a different start address (B operand) and a different
+//     column range of the accumulator; rows that would come from outside the snippet are simply not part of the MMA's N
+//     range, which IS the convolution's zero padding (no MMA work is spent on it).  The 16th row of a frame only ever
+//     feeds the 16th column of a frame, which is never stored.
+//   * a weight tile (128 x 64, both planes: 32 KB) is streamed once per (tap, channel block) and feeds N = 16 L columns
+//     (320 at L = 20) instead of a 128-row tile: per snippet 0.8 MB cross L2 -> SM for the widest layer instead of 3.7 MB
+//     (three 128-row tiles, each re-loading nine shifted windows and the full weight matrix).
+//   * no rows are wasted: the row-tiled kernel computes 384 rows for a 300-row snippet.
+// Accumulator: one TMEM buffer of 16 L fp32 columns; after each activation window (9 taps x 12 MMAs per k-step) the 16
+// epilogue warps drain it into fp32 registers (round-to-nearest adds, see lstm_tc.cu), 4 L columns per thread.
+// ================================================================================================================
+constexpr int SN_FR = 16;                        // rows per frame in the window (15 joints + 1 pad row)
+constexpr int SN_LMAX = 20;                      // frames per snippet supported (accumulators per epilogue thread: 4 L <= 80)
+constexpr int SN_WIN_PLANE = SN_LMAX * SN_FR * BK * 2;     // 40 KB
+constexpr int SN_WIN = 2 * SN_WIN_PLANE;                   // hi + lo
+constexpr int SN_WT_PLANE = 128 * BK * 2;                  // 16 KB
+constexpr int SN_WT = 2 * SN_WT_PLANE;
+constexpr int SN_NWIN = 2;
+constexpr int SN_WRING = 2 * SN_WT;                        // 64 KB of weight tiles: 2 slots of 128 rows, 4 of 64, 8 of 32
+constexpr int SN_MAXWT = 8;
+constexpr int SN_SMEM = SN_WRING + SN_NWIN * SN_WIN + 1024 + 256;
+
+struct TconvSnipParams {
+    int B, L;
+    int kbu;                 // 64-channel blocks of U (1 or 2)
+    int Cout;                // real output channels (32 / 64 / 128)
+    int nwt;                 // weight-ring slots: a slot holds the Cout real rows of a tile, both planes (the MMA reads 128 rows:
+                             // the rows beyond belong to the next slot / the window area and only feed output lanes >= Cout)
+    int wk;                  // channels per weight tile: 64 (rows of 128 bytes, SWIZZLE_128B) or 32 (rows of 64 bytes, SWIZZLE_64B)
+    int chunk256;            // split a tap's N range as (256, rest) instead of two near-equal halves
+    int ksu, ksy;            // 16-channel k-steps that hold real channels in a U block (2 or 4) / in the Y block (1..4): the rest
+                             // of a 64-channel block is TMA zero fill and is not multiplied
+    const float* bias;       // [Cout]
+    float out_scale;
+    __half* out_hi;          // planes [B][L*15][Cout]
+    __half* out_lo;
+    unsigned* error;         // set when a wait gave up (the kernel then finishes without hanging)
+};
+
+// taps are processed with the zero shift first: it covers every column of the window's accumulator and clears it
+__device__ __forceinline__ int snip_tap(int tj) { return tj == 0 ? 4 : (tj <= 4 ? tj - 1 : tj); }
+
+// bounded mbarrier wait: a protocol bug must not hang the GPU box
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, unsigned* error) {
+    for (unsigned i = 0; i < (1u << 26); ++i) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    *error = 1u;
+    return false;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tconv_snip_kernel(const __grid_constant__ CUtensorMap mUhi, const __grid_constant__ CUtensorMap mUlo,
+                  const __grid_constant__ CUtensorMap mYhi, const __grid_constant__ CUtensorMap mYlo,
+                  const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo,
+                  const TconvSnipParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* swt = smem;                                    // weight ring: [nwt][hi rows | lo rows]
+    uint8_t* swin = smem + SN_WRING;                        // [SN_NWIN][hi | lo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(swin + SN_NWIN * SN_WIN);
+    uint64_t* wfull = bars;                  // window slot filled
+    uint64_t* wempty = bars + SN_NWIN;       // window slot consumed
+    uint64_t* tfullb = wempty + SN_NWIN;     // weight slot filled
+    uint64_t* temptyb = tfullb + SN_MAXWT;   // weight slot consumed
+    uint64_t* dfull = temptyb + SN_MAXWT;    // accumulator complete (a drain group's MMAs done)
+    uint64_t* dempty = dfull + 1;            // accumulator drained
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(dempty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwin = p.kbu + 1;              // windows per snippet: residual Y first, then the U channel blocks
+    // Weight tiles are HALF K blocks (32 channels = 2 k-steps; rows of 64 bytes, SWIZZLE_64B): the 64 KB ring then holds
+    // 4 tiles of the 128-channel layer instead of 2, i.e. three loads in flight behind the one being multiplied (with
+    // two slots the MMA thread waited for L2 on every tile: tensor pipe 40 % active, profiles/r02_gcn_snip_ncu.txt).
+    const int wt_plane = p.Cout * p.wk * 2;  // bytes of one plane of a weight tile (real rows only)
+    const int wt_slot = 2 * wt_plane;
+    const int kpt = p.wk / 16;               // k-steps per weight tile (2 or 4)
+    const int nhu = (p.ksu + kpt - 1) / kpt, nhy = (p.ksy + kpt - 1) / kpt;      // tiles per tap (U) / of the residual block (Y)
+    // Drain groups: {Y, U block 0} accumulate together (no drain after the one-tap residual window: the epilogue warps
+    // are still storing the previous snippet's rows then), {U block 1} is the second group of the 128-channel layer.
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&mUhi);
+        prefetch_tensormap(&mUlo);
+        prefetch_tensormap(&mYhi);
+        prefetch_tensormap(&mYlo);
+        prefetch_tensormap(&mWhi);
+        prefetch_tensormap(&mWlo);
+        for (int s = 0; s < SN_NWIN; ++s) {
+            mbar_init(&wfull[s], 1);
+            mbar_init(&wempty[s], 1);
+        }
+        for (int s = 0; s < SN_MAXWT; ++s) {
+            mbar_init(&tfullb[s], 1);
+            mbar_init(&temptyb[s], 1);
+        }
+        mbar_init(dfull, 1);
+        mbar_init(dempty, kEpiWarps);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_holder, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+      if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            uint32_t wi = 0, ti = 0;         // running window / weight-tile counters
+            bool ok = true;
+            for (int b = blockIdx.x; b < p.B && ok; b += gridDim.x) {
+                for (int w = 0; w < nwin && ok; ++w, ++wi) {
+                    const int ws = wi % SN_NWIN;
+                    ok = mbar_wait_bounded(&wempty[ws], ((wi / SN_NWIN) & 1) ^ 1, p.error);
+                    if (!ok) break;
+                    uint8_t* dst = swin + ws * SN_WIN;
+                    mbar_expect_tx(&wfull[ws], 2 * p.L * SN_FR * BK * 2);
+                    if (w == 0) {
+                        tma_load_4d(dst, &mYhi, &wfull[ws], 0, 0, 0, b);
+                        tma_load_4d(dst + SN_WIN_PLANE, &mYlo, &wfull[ws], 0, 0, 0, b);
+                    } else {
+                        tma_load_4d(dst, &mUhi, &wfull[ws], (w - 1) * BK, 0, 0, b);
+                        tma_load_4d(dst + SN_WIN_PLANE, &mUlo, &wfull[ws], (w - 1) * BK, 0, 0, b);
+                    }
+                    const int ntile = w == 0 ? nhy : 9 * nhu;
+                    for (int tl = 0; tl < ntile && ok; ++tl, ++ti) {
+                        const int ts = ti % p.nwt;
+                        ok = mbar_wait_bounded(&temptyb[ts], ((ti / p.nwt) & 1) ^ 1, p.error);
+                        if (!ok) break;
+                        // packed K order of the weights: [tap 0: U blocks][tap 1: ...] ... [residual block]
+                        const int kcol = (w == 0 ? 9 * p.kbu * BK + tl * p.wk
+                                                 : (snip_tap(tl / nhu) * p.kbu + (w - 1)) * BK + (tl % nhu) * p.wk);
+                        uint8_t* wd = swt + ts * wt_slot;
+                        mbar_expect_tx(&tfullb[ts], wt_slot);
+                        tma_load_2d(wd, &mWhi, &tfullb[ts], kcol, 0);
+                        tma_load_2d(wd + wt_plane, &mWlo, &tfullb[ts], kcol, 0);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+      } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            uint32_t wi = 0, ti = 0, di = 0;
+            bool ok = true;
+#ifdef MMEGO_DEBUG_SWITCHES
+            long long c_total = clock64(), c_d = 0, c_w = 0, c_t = 0, c0;
+#define SNIP_T0() c0 = clock64()
+#define SNIP_T1(acc) acc += clock64() - c0
+#else
+#define SNIP_T0()
+#define SNIP_T1(acc)
+#endif
+            for (int b = blockIdx.x; b < p.B && ok; b += gridDim.x) {
+                for (int w = 0; w < nwin && ok; ++w, ++wi) {
+                    const int ws = wi % SN_NWIN;
+                    if (w != 1) {            // start of a drain group: the accumulator must have been drained
+                        SNIP_T0();
+                        ok = mbar_wait_bounded(dempty, (di & 1) ^ 1, p.error);
+                        SNIP_T1(c_d);
+                        if (!ok) break;
+                    }
+                    SNIP_T0();
+                    ok = mbar_wait_bounded(&wfull[ws], (wi / SN_NWIN) & 1, p.error);
+                    SNIP_T1(c_w);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t win_hi = smem_u32(swin + ws * SN_WIN), win_lo = win_hi + SN_WIN_PLANE;
+                    const int ntile = w == 0 ? nhy : 9 * nhu;
+                    // tap order (snip_tap): the zero-shift tap first -- it covers every column and clears the accumulator
+                    for (int tl = 0; tl < ntile && ok; ++tl, ++ti) {
+                        const int ts = ti % p.nwt;
+                        SNIP_T0();
+                        ok = mbar_wait_bounded(&tfullb[ts], (ti / p.nwt) & 1, p.error);
+                        SNIP_T1(c_t);
+                        if (!ok) break;
+                        tc_fence_after();
+                        const uint32_t w_hi = smem_u32(swt + ts * wt_slot), w_lo = w_hi + wt_plane;
+                        const int tap = w == 0 ? 4 : snip_tap(tl / nhu);  // same order as the producer; shift = tap - 4
+                        const int half = w == 0 ? tl : tl % nhu;          // which part of the 64-channel block this tile covers
+                        const int ks_real = w == 0 ? p.ksy : p.ksu;
+                        const int nk = ks_real - kpt * half < kpt ? ks_real - kpt * half : kpt;
+                        const int sh = tap - 4;
+                        const int f0 = sh < 0 ? -sh : 0, f1 = sh > 0 ? p.L - sh : p.L;     // output frames [f0, f1)
+                        if (f1 > f0) {
+                            const int total = (f1 - f0) * SN_FR;
+                            const int n0 = total <= 256 ? total : (p.chunk256 ? 256 : ((total / 2 + 15) / 16) * 16);
+                            for (int c0 = 0; c0 < total; c0 += n0) {
+                                const int n = (total - c0) < n0 ? (total - c0) : n0;
+                                const uint32_t idesc = make_idesc_f16(128, n, 0 /*fp16*/);
+                                const uint32_t d_tmem = tmem_base + (uint32_t)(f0 * SN_FR + c0);
+                                const uint32_t boff = (uint32_t)((f0 + sh) * SN_FR + c0) * 128u;      // source rows
+                                for (int k = 0; k < nk; ++k) {
+                                    const uint64_t dw_hi = p.wk == 32 ? make_sw64_kmajor_desc(w_hi + k * 32) : make_sw128_kmajor_desc(w_hi + k * 32);
+                                    const uint64_t dw_lo = p.wk == 32 ? make_sw64_kmajor_desc(w_lo + k * 32) : make_sw128_kmajor_desc(w_lo + k * 32);
+                                    const uint64_t da_hi = make_sw128_kmajor_desc(win_hi + boff + (kpt * half + k) * 32);
+                                    const uint64_t da_lo = make_sw128_kmajor_desc(win_lo + boff + (kpt * half + k) * 32);
+                                    const uint32_t acc0 = (w == 1 || tl > 0 || k > 0) ? 1u : 0u;   // block 0 adds to the residual
+                                    mma_f16_ss(d_tmem, dw_hi, da_lo, idesc, acc0);
+                                    mma_f16_ss(d_tmem, dw_lo, da_hi, idesc, 1);
+                                    mma_f16_ss(d_tmem, dw_hi, da_hi, idesc, 1);
+                                }
+                            }
+                        }
+                        mma_commit(&temptyb[ts]);
+                    }
+                    mma_commit(&wempty[ws]);
+                    if (w >= 1) {            // end of a drain group
+                        mma_commit(dfull);
+                        ++di;
+                    }
+                }
+            }
+#ifdef MMEGO_DEBUG_SWITCHES
+            {   // MMA-thread cycle accounting (test builds): [2] total, [3] waiting for drains, [4] for windows, [5] for weights
+                unsigned long long* st = reinterpret_cast<unsigned long long*>(p.error);
+                atomicAdd(st + 2, (unsigned long long)(clock64() - c_total));
+                atomicAdd(st + 3, (unsigned long long)c_d);
+                atomicAdd(st + 4, (unsigned long long)c_w);
+                atomicAdd(st + 5, (unsigned long long)c_t);
+                atomicAdd(st + 6, 1ull);
+            }
+#endif
+        }
+        __syncwarp();
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        // ===================================================================== epilogue (16 warps)
+        constexpr int CPT = 4 * SN_LMAX;          // accumulator columns per thread (80): part x CPT .. + 4 L
+        const int q = warp & 3;                   // TMEM lane quarter = channels 32 q .. 32 q + 31
+        const int part = (warp - 4) >> 2;         // quarter of the columns
+        const int ch = q * 32 + lane;
+        const int cpp = 4 * p.L;                  // live columns per part (multiple of 4; L frames x 16 rows / 4 parts)
+        const float bias = ch < p.Cout ? p.bias[ch] : 0.f;
+        uint32_t di = 0;
+        bool ok = true;
+        for (int b = blockIdx.x; b < p.B && ok; b += gridDim.x) {
+            float acc[CPT];
+            for (int w = 0; w < p.kbu && ok; ++w, ++di) {          // one pass per drain group
+                ok = mbar_wait_bounded(dfull, di & 1, p.error);
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * cpp);
+#pragma unroll
+                for (int g8 = 0; g8 < CPT / 8; ++g8) {
+                    if (g8 * 8 < cpp) {           // warp-uniform
+                        uint32_t r[8];
+                        tmem_ld_x8(taddr + g8 * 8, r);
+                        tmem_ld_wait();
+                        if (w == 0) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc[g8 * 8 + j] = __uint_as_float(r[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc[g8 * 8 + j] += __uint_as_float(r[j]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dempty);
+            }
+            if (!ok) break;
+            if (ch < p.Cout) {
+                __half* oh = p.out_hi + (long long)b * p.L * kGcnV * p.Cout + ch;
+                __half* ol = p.out_lo + (long long)b * p.L * kGcnV * p.Cout + ch;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const int col = part * cpp + j;                   // padded row: frame * 16 + joint
+                    const int jt = col & (SN_FR - 1);
+                    if (j < cpp && jt < kGcnV) {
+                        const int row = (col >> 4) * kGcnV + jt;
+                        const float v = sat16(fmaxf(fmaf(acc[j], p.out_scale, bias), 0.f) * kGcnActScale);
+                        const __half hh = __float2half_rn(v);
+                        oh[(long long)row * p.Cout] = hh;
+                        ol[(long long)row * p.Cout] = __float2half_rn(v - __half2float(hh));
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- memory-bound glue
 // Lower_Net front (Net/Lower_Net.py:229, Net/GCN.py:339-344): Transform2H of the upper-body joints + data_bn.
 //   upper [F,15,3] -> uh [F,45] fp32 (also the 45 extra inputs of fusion.fc0), y0 planes [F*15][8] (3 channels + zeros)
@@ -569,6 +885,74 @@ int tc_gcn_gemm(mmego_handle* h, const TcGemmW& w, const void* a0hi, const void*
     else if (w.N == 64) launch_gemm_tc<64>(m0h, m0l, m1h, m1l, wh, wl, p, h->sm_count, st);
     else if (w.N == 32) launch_gemm_tc<32>(m0h, m0l, m1h, m1l, wh, wl, p, h->sm_count, st);
     else return -3;
+    return 0;
+}
+
+// activation planes [B][L][15][C] fp16 as a 4-D tensor; box = 64 channels x 16 joints x L frames x 1 snippet: the 16th
+// joint is out of bounds, so every frame arrives padded to 16 rows (zero row), channels beyond C as zeros
+static bool make_snip_map(CUtensorMap* m, const void* base, int B, int L, int C) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)kGcnV, (cuuint64_t)L, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)kGcnV * C * 2, (cuuint64_t)L * kGcnV * C * 2};
+    cuuint32_t box[4] = {BK, SN_FR, (cuuint32_t)L, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// weights [rows][K] fp16; box = 32 x rows: half a K block, the real rows of a tile, 64-byte rows with SWIZZLE_64B (the
+// MMA's M is always 128, see TconvSnipParams::nwt)
+static bool make_w128_map(CUtensorMap* m, const void* base, int rows, int K, int wk) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)wk, (cuuint32_t)rows};
+    cuuint32_t es[2] = {1, 1};
+    return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, wk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool tc_gcn_tconv_snip_supported(int L) { return L >= 1 && L <= SN_LMAX; }
+
+// Temporal conv + residual of one ST-GCN layer, snippet-resident (tconv_snip_kernel): U planes [B][L*15][cu] (9 taps),
+// Y planes [B][L*15][cy] (residual 1x1 conv), weights packed as for tc_gcn_gemm -> out planes [B][L*15][w.N].
+int tc_gcn_tconv_snip(mmego_handle* h, const TcGemmW& w, const void* uhi, const void* ulo, int cu, const void* yhi,
+                      const void* ylo, int cy, int cy_real, void* outhi, void* outlo, int B, int L, cudaStream_t st) {
+    if (!tc_gcn_tconv_snip_supported(L) || cu != w.N) return -4;
+    const int kbu = (cu + BK - 1) / BK;
+    if ((9 * kbu + (cy + BK - 1) / BK) * BK != w.K64 || (cy + BK - 1) / BK != 1) return -2;
+    const int wk = (h->gcn_snip & 2) ? 32 : 64;
+    CUtensorMap mUh, mUl, mYh, mYl, mWh, mWl;
+    if (!make_snip_map(&mUh, uhi, B, L, cu) || !make_snip_map(&mUl, ulo, B, L, cu) || !make_snip_map(&mYh, yhi, B, L, cy) ||
+        !make_snip_map(&mYl, ylo, B, L, cy) || !make_w128_map(&mWh, w.whi, w.N, w.K64, wk) || !make_w128_map(&mWl, w.wlo, w.N, w.K64, wk))
+        return -1;
+    if (!h->dev_error) {
+        if (cudaMalloc(reinterpret_cast<void**>(&h->dev_error), 64) != cudaSuccess) return -1;
+        cudaMemset(h->dev_error, 0, 64);
+    }
+    TconvSnipParams p{};
+    p.B = B;
+    p.L = L;
+    p.kbu = kbu;
+    p.Cout = w.N;
+    p.wk = wk;
+    p.chunk256 = (h->gcn_snip & 4) ? 1 : 0;
+    p.nwt = SN_WRING / (2 * w.N * wk * 2);
+    if (p.nwt > SN_MAXWT) p.nwt = SN_MAXWT;
+    if (w.N % 8 != 0 || w.N > 128 || p.nwt < 2) return -3;
+    p.ksu = cu >= BK ? 4 : (cu + 31) / 32 * 2;              // real 16-channel k-steps per U block (rounded to a half block)
+    p.ksy = (cy_real + 15) / 16;
+    p.bias = w.bias;
+    p.out_scale = w.out_scale * kGcnActInv;
+    p.out_hi = static_cast<__half*>(outhi);
+    p.out_lo = static_cast<__half*>(outlo);
+    p.error = h->dev_error;
+    static bool attr_set[64] = {false};
+    if (first_use_on_device(attr_set))
+        cudaFuncSetAttribute(tconv_snip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_SMEM);
+    const int grid = B < h->sm_count ? B : h->sm_count;
+    ++t_launches;
+    tconv_snip_kernel<<<grid, kThreads, SN_SMEM, st>>>(mUh, mUl, mYh, mYl, mWh, mWl, p);
     return 0;
 }
 

@@ -282,6 +282,9 @@ bool tc_pack_gemm(mmego_handle* h, const HostPackedGemm& g, TcGemmW& out);
 int tc_gcn_gemm(mmego_handle* h, const TcGemmW& w, const void* a0hi, const void* a0lo, int c0, int n0, const void* a1hi,
                 const void* a1lo, int c1, int rowmod, int relu, void* outhi, void* outlo, float* out_f6, int B, int RP,
                 cudaStream_t st);
+bool tc_gcn_tconv_snip_supported(int L);
+int tc_gcn_tconv_snip(mmego_handle* h, const TcGemmW& w, const void* uhi, const void* ulo, int cu, const void* yhi,
+                      const void* ylo, int cy, int cy_real, void* outhi, void* outlo, int B, int L, cudaStream_t st);
 void tc_gcn_prep(const float* upper, const float* R, const float* t, const float* bn, float* uh, void* yhi, void* ylo,
                  long long F, cudaStream_t st);
 void tc_gcn_prep_raw(const float* x, const float* bn, void* yhi, void* ylo, int B, int T, cudaStream_t st);
@@ -321,6 +324,8 @@ struct mmego_handle {
     int small_lstm_gemm = 1;  // H=64 LSTMs: 0 = fp32 FFMA, 1 = mma.sync fp16x3 (default)
     int tc_kb_chunk0 = 8;     // ... of the first two chunks of every tile
     int tc_kb_chunk = 4;      // fp16x3 mode: K blocks (of 64) per TMEM partial accumulation (see lstm_tc.cu)
+    int gcn_snip = 1;         // ST-GCN temporal convs: 1 = snippet-resident transposed kernel (L <= 20), 0 = row-tiled GEMM
+    unsigned* dev_error = nullptr;   // device word set by a kernel whose bounded wait gave up (mmego_debug_stats out8[7])
     int imu_resident = 1;     // small batches (B*L <= kResMaxSeq): persistent fp32 LSTM with weights resident in shared memory
     mmego::ImuWeights imu;
     mmego::UpperWeights upper;

@@ -68,6 +68,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder, uint32_t ncols) {   // whole warp, .sync.aligned
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)), "r"(ncols)
@@ -194,6 +202,17 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     d |= (uint64_t)(1024 >> 4) << 32;       // SBO: 8 rows * 128 B
     d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// The same for rows of 64 bytes (32 x 16-bit) written by TMA with CU_TENSOR_MAP_SWIZZLE_64B: 8-row groups are 512 bytes
+// apart, the tile base is 512-byte aligned; layout type SWIZZLE_64B = 4.
+__device__ __forceinline__ uint64_t make_sw64_kmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;        // SBO: 8 rows * 64 B
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
     return d;
 }
 // Instruction descriptor, kind::f16: D fp32, A/B fp16 (fmt 0) or bf16 (fmt 1), both K-major, dense.

@@ -361,6 +361,7 @@ def test_lstm_residual_rounding_and_pdl_options():
     results = {}
     for drop in (0, 4):
         h = _capi.Handle()
+        h.set_option("imu_resident", 0)         # the tcgen05 path (one snippet would otherwise take the fp32 latency path)
         h.set_option("tc_lo_drop", drop)
         h.set_weights(_capi.NET_IMU, P.O.synth_imu_state_dict(0))
         er, et = P.check_imu_golden(h, "synth")
