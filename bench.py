@@ -565,7 +565,13 @@ def main():
                 e = {"ms": round(ms_s, 3)}
                 if name in hbm_bytes:
                     gbs = hbm_bytes[name] / (ms_s * 1e-3) / 1e9
-                    e.update({"hbm_bytes": hbm_bytes[name], "gbs": round(gbs, 1), "hbm_frac": round(gbs / peaks["hbm_gbs"], 3)})
+                    e.update({"hbm_bytes": hbm_bytes[name], "gbs": round(gbs, 1)})
+                    if name.endswith("head_decode"):
+                        # the former HBM-bound decode / assembly / metrics kernels no longer exist: they run inside the head
+                        # GEMM kernel (heads_mma.cu), whose time is the mma.sync chain + the per-frame decode, not its bytes
+                        e["bound"] = "fused into the head GEMM (mma.sync chain + per-frame decode); bytes are the compulsory ones"
+                    else:
+                        e["hbm_frac"] = round(gbs / peaks["hbm_gbs"], 3)
                 if name in flops:
                     e["algorithmic_tflops"] = round(flops[name] / (ms_s * 1e-3) / 1e12, 2)
                 if len(e) > 1:
