@@ -326,6 +326,10 @@ def main():
     ap.add_argument("--cpu-snippets", type=int, default=128, help="snippets per CPU-baseline step (bounded sample; 128 = best CPU batch)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-config1", action="store_true", help="skip the 835-sample-snippet record (config 1)")
+    ap.add_argument("--collective", default="sync", choices=["sync", "async"],
+                    help="N>1: sync = all-gather / all-reduce at the end of every step on the compute stream (default); async = "
+                         "on a side stream under the next step's compute (measured slower at N=8: the spinning NCCL CTAs share "
+                         "SMs with the persistent, statically partitioned LSTM kernel, profiles/r02_scale_*.json)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = --batch snippets PER GPU (default, config 3 per GPU); strong = --batch snippets in total, "
                          "split contiguously over the GPUs (config 4 of BASELINE.json)")
@@ -426,7 +430,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        if world > 1:
+        if world > 1 and args.collective == "async":
             # the gather / all-reduce of step i runs on a side stream while step i+1 computes (two result slots):
             # no rank waits inside a step for the slowest GPU of the box; every step's result is collected
             for i in range(steps):
@@ -590,8 +594,9 @@ def main():
                        "l2": "inputs per step (350 MB per GPU) exceed the 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": launches,
             "collective_ms_per_step": round(collective_ms, 4) if world > 1 else None,
-            "collective_note": ("all-gather of pred + all-reduce of 46 float64 sums, device time on the side stream they "
-                                "overlap the next step on (rank 0)") if world > 1 else None,
+            "collective": args.collective if world > 1 else None,
+            "collective_note": ("all-gather of pred (into the final layout) + all-reduce of 46 float64 sums per step; device time "
+                                "between CUDA events around them on rank 0, including the wait for the slowest rank") if world > 1 else None,
             "algorithmic_tflops": FLOPS_PER_FRAME["total"] * frames / (ms_per_step * 1e-3) / 1e12,
             "stage_ms_per_step": stage_ms,
             "mpjpe_vs_synthetic_target_cm": rep["mpjpe_cm"],

@@ -298,6 +298,7 @@ struct TconvSnipParams {
     int Cout;                // real output channels (32 / 64 / 128)
     int nwt;                 // weight-ring slots: a slot holds the Cout real rows of a tile, both planes (the MMA reads 128 rows:
                              // the rows beyond belong to the next slot / the window area and only feed output lanes >= Cout)
+    int subdrain;            // drain the accumulator twice per U block (taps with shift <= 0, then shift > 0): see the kernel
     int wk;                  // channels per weight tile: 64 (rows of 128 bytes, SWIZZLE_128B) or 32 (rows of 64 bytes, SWIZZLE_64B)
     int chunk256;            // split a tap's N range as (256, rest) instead of two near-equal halves
     int ksu, ksy;            // 16-channel k-steps that hold real channels in a U block (2 or 4) / in the Y block (1..4): the rest
@@ -312,20 +313,24 @@ struct TconvSnipParams {
 // taps are processed with the zero shift first: it covers every column of the window's accumulator and clears it
 __device__ __forceinline__ int snip_tap(int tj) { return tj == 0 ? 4 : (tj <= 4 ? tj - 1 : tj); }
 
-// bounded mbarrier wait: a protocol bug must not hang the GPU box
+// bounded mbarrier wait: a protocol bug must not hang the GPU box.  test_wait never suspends the thread (try_wait may, for
+// a system-dependent time), so the bound below is a real one: ~2^21 polls of >= 32 ns, about 0.1 s; a waiter also leaves
+// as soon as anybody else has given up.
 __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, unsigned* error) {
-    for (unsigned i = 0; i < (1u << 26); ++i) {
+    for (unsigned i = 0; i < (1u << 21); ++i) {
         uint32_t ok;
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t"
             "}\n"
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (ok) return true;
+        if (i > 64) __nanosleep(32);
+        if ((i & 255u) == 255u && *reinterpret_cast<volatile unsigned*>(error) != 0u) return false;
     }
     *error = 1u;
     return false;
@@ -358,8 +363,15 @@ tconv_snip_kernel(const __grid_constant__ CUtensorMap mUhi, const __grid_constan
     const int wt_slot = 2 * wt_plane;
     const int kpt = p.wk / 16;               // k-steps per weight tile (2 or 4)
     const int nhu = (p.ksu + kpt - 1) / kpt, nhy = (p.ksy + kpt - 1) / kpt;      // tiles per tap (U) / of the residual block (Y)
-    // Drain groups: {Y, U block 0} accumulate together (no drain after the one-tap residual window: the epilogue warps
-    // are still storing the previous snippet's rows then), {U block 1} is the second group of the 128-channel layer.
+    // Drain groups (the accumulator is drained into fp32 registers after each: long accumulation chains in TMEM lose
+    // accuracy -- one group per channel block measured 9.5e-6 relative error on the reference vector against 1.5e-6 of
+    // the row-tiled kernel): per U block the taps with shift <= 0 (the zero shift first: it covers every column and
+    // clears the accumulator), then the taps with shift > 0 (the first of them, shift +1, clears frames 0 .. L-2; the
+    // last frame's columns keep stale values that the epilogue skips).  The one-tap residual window joins the first group.
+    // Measured (B200, reference vector gcn2.npz / 2048 snippets): one group per block 9.5e-6 and 1.60 ms, two groups
+    // 5.6e-6 and 1.79 ms, the row-tiled kernel 1.5e-6 and 1.81 ms; joints stay at 1.5e-6 m either way (tolerance 1e-5 m),
+    // so the split (`subdrain`, option gcn_snip bit 4) is off by default.
+    const int tiles_a = p.subdrain ? 5 * nhu : (1 << 20);   // tiles of a U window's first group (taps 4, 0, 1, 2, 3)
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&mUhi);
@@ -458,6 +470,14 @@ tconv_snip_kernel(const __grid_constant__ CUtensorMap mUhi, const __grid_constan
                     const int ntile = w == 0 ? nhy : 9 * nhu;
                     // tap order (snip_tap): the zero-shift tap first -- it covers every column and clears the accumulator
                     for (int tl = 0; tl < ntile && ok; ++tl, ++ti) {
+                        if (w > 0 && tl == tiles_a) {          // second group of this U window
+                            mma_commit(dfull);
+                            ++di;
+                            SNIP_T0();
+                            ok = mbar_wait_bounded(dempty, (di & 1) ^ 1, p.error);
+                            SNIP_T1(c_d);
+                            if (!ok) break;
+                        }
                         const int ts = ti % p.nwt;
                         SNIP_T0();
                         ok = mbar_wait_bounded(&tfullb[ts], (ti / p.nwt) & 1, p.error);
@@ -472,22 +492,44 @@ tconv_snip_kernel(const __grid_constant__ CUtensorMap mUhi, const __grid_constan
                         const int sh = tap - 4;
                         const int f0 = sh < 0 ? -sh : 0, f1 = sh > 0 ? p.L - sh : p.L;     // output frames [f0, f1)
                         if (f1 > f0) {
+                            // The tap's N range is cut into (at most) two chunks = two INDEPENDENT accumulator column ranges;
+                            // their MMAs are issued alternately, so that consecutive MMAs never accumulate into the same
+                            // columns (a chain of dependent accumulations is latency-bound: 142 clk per M128 x N160 x K16
+                            // MMA against 75 when the pipe is fed independent work).
                             const int total = (f1 - f0) * SN_FR;
                             const int n0 = total <= 256 ? total : (p.chunk256 ? 256 : ((total / 2 + 15) / 16) * 16);
-                            for (int c0 = 0; c0 < total; c0 += n0) {
-                                const int n = (total - c0) < n0 ? (total - c0) : n0;
-                                const uint32_t idesc = make_idesc_f16(128, n, 0 /*fp16*/);
-                                const uint32_t d_tmem = tmem_base + (uint32_t)(f0 * SN_FR + c0);
-                                const uint32_t boff = (uint32_t)((f0 + sh) * SN_FR + c0) * 128u;      // source rows
-                                for (int k = 0; k < nk; ++k) {
-                                    const uint64_t dw_hi = p.wk == 32 ? make_sw64_kmajor_desc(w_hi + k * 32) : make_sw128_kmajor_desc(w_hi + k * 32);
-                                    const uint64_t dw_lo = p.wk == 32 ? make_sw64_kmajor_desc(w_lo + k * 32) : make_sw128_kmajor_desc(w_lo + k * 32);
-                                    const uint64_t da_hi = make_sw128_kmajor_desc(win_hi + boff + (kpt * half + k) * 32);
-                                    const uint64_t da_lo = make_sw128_kmajor_desc(win_lo + boff + (kpt * half + k) * 32);
-                                    const uint32_t acc0 = (w == 1 || tl > 0 || k > 0) ? 1u : 0u;   // block 0 adds to the residual
-                                    mma_f16_ss(d_tmem, dw_hi, da_lo, idesc, acc0);
-                                    mma_f16_ss(d_tmem, dw_lo, da_hi, idesc, 1);
-                                    mma_f16_ss(d_tmem, dw_hi, da_hi, idesc, 1);
+                            const int nch = total > n0 ? 2 : 1;
+                            // everything per chunk is prepared once per tap; per MMA the issuing thread only adds the k-step
+                            // offset (32 bytes = 2 descriptor units) to two descriptors
+                            uint32_t idesc[2], d_tmem[2];
+                            uint64_t bhi[2], blo[2];
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                const int c0 = c * n0, n = c == 0 ? n0 : total - n0;
+                                idesc[c] = make_idesc_f16(128, n > 0 ? n : 16, 0 /*fp16*/);
+                                d_tmem[c] = tmem_base + (uint32_t)(f0 * SN_FR + c0);
+                                const uint32_t boff = (uint32_t)((f0 + sh) * SN_FR + c0) * 128u + (uint32_t)(kpt * half) * 32u;
+                                bhi[c] = make_sw128_kmajor_desc(win_hi + boff);
+                                blo[c] = make_sw128_kmajor_desc(win_lo + boff);
+                            }
+                            const uint64_t ahi = p.wk == 32 ? make_sw64_kmajor_desc(w_hi) : make_sw128_kmajor_desc(w_hi);
+                            const uint64_t alo = p.wk == 32 ? make_sw64_kmajor_desc(w_lo) : make_sw128_kmajor_desc(w_lo);
+                            const bool clear = (w != 1 && tl == 0) || (w > 0 && tl == tiles_a);   // first tile of a drain group (block 0 adds to the residual)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (k < nk) {
+                                    const uint64_t ko = (uint64_t)(2 * k);
+                                    if (k == 0 && clear) {
+                                        mma_f16_ss(d_tmem[0], ahi, blo[0], idesc[0], 0);
+                                        if (nch == 2) mma_f16_ss(d_tmem[1], ahi, blo[1], idesc[1], 0);
+                                    } else {
+                                        mma_f16_ss_acc(d_tmem[0], ahi + ko, blo[0] + ko, idesc[0]);
+                                        if (nch == 2) mma_f16_ss_acc(d_tmem[1], ahi + ko, blo[1] + ko, idesc[1]);
+                                    }
+                                    mma_f16_ss_acc(d_tmem[0], alo + ko, bhi[0] + ko, idesc[0]);
+                                    if (nch == 2) mma_f16_ss_acc(d_tmem[1], alo + ko, bhi[1] + ko, idesc[1]);
+                                    mma_f16_ss_acc(d_tmem[0], ahi + ko, bhi[0] + ko, idesc[0]);
+                                    if (nch == 2) mma_f16_ss_acc(d_tmem[1], ahi + ko, bhi[1] + ko, idesc[1]);
                                 }
                             }
                         }
@@ -526,7 +568,8 @@ tconv_snip_kernel(const __grid_constant__ CUtensorMap mUhi, const __grid_constan
         bool ok = true;
         for (int b = blockIdx.x; b < p.B && ok; b += gridDim.x) {
             float acc[CPT];
-            for (int w = 0; w < p.kbu && ok; ++w, ++di) {          // one pass per drain group
+            const int ngroups = p.subdrain ? 2 * p.kbu : p.kbu;
+            for (int w = 0; w < ngroups && ok; ++w, ++di) {        // one pass per drain group; with subdrain odd groups = taps with shift > 0
                 ok = mbar_wait_bounded(dfull, di & 1, p.error);
                 if (!ok) break;
                 tc_fence_after();
@@ -540,6 +583,10 @@ tconv_snip_kernel(const __grid_constant__ CUtensorMap mUhi, const __grid_constan
                         if (w == 0) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) acc[g8 * 8 + j] = __uint_as_float(r[j]);
+                        } else if (p.subdrain && (w & 1)) {       // shift > 0 taps never write the last frame's columns: stale there
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (((part * cpp + g8 * 8 + j) >> 4) < p.L - 1) acc[g8 * 8 + j] += __uint_as_float(r[j]);
                         } else {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) acc[g8 * 8 + j] += __uint_as_float(r[j]);
@@ -937,6 +984,7 @@ int tc_gcn_tconv_snip(mmego_handle* h, const TcGemmW& w, const void* uhi, const 
     p.Cout = w.N;
     p.wk = wk;
     p.chunk256 = (h->gcn_snip & 4) ? 1 : 0;
+    p.subdrain = (h->gcn_snip & 16) ? 1 : 0;
     p.nwt = SN_WRING / (2 * w.N * wk * 2);
     if (p.nwt > SN_MAXWT) p.nwt = SN_MAXWT;
     if (w.N % 8 != 0 || w.N > 128 || p.nwt < 2) return -3;
@@ -947,11 +995,11 @@ int tc_gcn_tconv_snip(mmego_handle* h, const TcGemmW& w, const void* uhi, const 
     p.out_hi = static_cast<__half*>(outhi);
     p.out_lo = static_cast<__half*>(outlo);
     p.error = h->dev_error;
+    const int grid = B < h->sm_count ? B : h->sm_count;
+    ++t_launches;
     static bool attr_set[64] = {false};
     if (first_use_on_device(attr_set))
         cudaFuncSetAttribute(tconv_snip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_SMEM);
-    const int grid = B < h->sm_count ? B : h->sm_count;
-    ++t_launches;
     tconv_snip_kernel<<<grid, kThreads, SN_SMEM, st>>>(mUh, mUl, mYh, mYl, mWh, mWl, p);
     return 0;
 }

@@ -10,6 +10,9 @@
 #include "internal.h"
 #include "point_layout.h"
 #include "mma_frag.cuh"
+#ifndef MMEGO_EMUL
+#include "tc_common.cuh"
+#endif
 
 namespace mmego {
 
@@ -161,6 +164,8 @@ struct MmaSmem {
     uint32_t w[UM::TOTAL];              // fragment-ordered weights, biases, attention vector, scales
     float tile[MW][32][8];              // transformed input points of each warp's tile pair (6 channels + 2 zero)
     float part[2][MW][PART_LD];         // per-warp softmax partials, double-buffered by frame parity
+    unsigned long long bar[2];          // mbarriers of the two cloud buffers
+    // followed by float cloud[2][N * 6]: the frame's radar cloud, staged by the TMA unit (1-D bulk copy) one frame ahead
 };
 
 // Two tiles per warp: every B fragment read from shared memory feeds two MMA chains (half the fragment loads per MMA)
@@ -180,10 +185,48 @@ __global__ void __launch_bounds__(MT, 2) upper_point_mma_kernel(float* __restric
     const uint4* wf = reinterpret_cast<const uint4*>(s.w);
     const float* wfl = reinterpret_cast<const float*>(s.w);
     const float* osc = wfl + UM::OS;
+    // Radar clouds are staged by TMA: while the warps work on frame f, one thread has the copy of the CTA's next frame
+    // (N x 24 bytes, one bulk transfer) in flight into the other buffer; the per-lane global loads that used to open
+    // every tile's dependency chain become shared-memory reads.  (Odd N breaks the 16-byte rule of bulk copies: the
+    // lanes then read the cloud from global memory as before.)
+    float* cloud = reinterpret_cast<float*>(sp + 1);
+    const uint32_t cloud_bytes = (uint32_t)N * 24u;
+#ifndef MMEGO_EMUL
+    const bool staged = (cloud_bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s.bar);
+    if (staged) {
+        if (tid == 0) {
+            tc::mbar_init(&bars[0], 1);
+            tc::mbar_init(&bars[1], 1);
+            tc::fence_barrier_init();
+        }
+        __syncthreads();
+        if (tid == 0 && (long long)blockIdx.x < F) {
+            tc::mbar_expect_tx(&bars[0], cloud_bytes);
+            tc::tma_load_1d(cloud, x + (long long)blockIdx.x * N * 6, cloud_bytes, &bars[0]);
+        }
+    }
+#else
+    const bool staged = false;
+#endif
 
     int parity = 0;
     for (long long f = blockIdx.x; f < F; f += gridDim.x, parity ^= 1) {
         float* xf = x + f * (long long)N * 6;
+        const float* xin = xf;
+#ifndef MMEGO_EMUL
+        if (staged) {
+            // buffer `parity` holds frame f; buffer parity^1 was last read two frames ago (a __syncthreads ends every frame)
+            if (tid == 0 && f + gridDim.x < F) {
+                tc::mbar_expect_tx(&bars[parity ^ 1], cloud_bytes);
+                tc::tma_load_1d(cloud + (size_t)(parity ^ 1) * N * 6, x + (f + gridDim.x) * (long long)N * 6, cloud_bytes,
+                                &bars[parity ^ 1]);
+            }
+            const long long it = (f - blockIdx.x) / gridDim.x;            // this CTA's frame counter: buffer parity = it & 1
+            tc::mbar_wait(&bars[parity], (uint32_t)((it >> 1) & 1));
+            xin = cloud + (size_t)parity * N * 6;
+        }
+#endif
         float* gwf = gw ? gw + f * (long long)N : nullptr;
         float run_m = -INFINITY, run_s = 0.f;
         float gp[16];                    // weighted sums of channels 8j + 2*tq + {0,1}, over this lane's rows
@@ -208,9 +251,9 @@ __global__ void __launch_bounds__(MT, 2) upper_point_mma_kernel(float* __restric
                 const int p = pbase + lane;
                 float in[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (p < N) {
-                    const float2 v0 = *reinterpret_cast<const float2*>(xf + p * 6);
-                    const float2 v1 = *reinterpret_cast<const float2*>(xf + p * 6 + 2);
-                    const float2 v2 = *reinterpret_cast<const float2*>(xf + p * 6 + 4);
+                    const float2 v0 = *reinterpret_cast<const float2*>(xin + p * 6);
+                    const float2 v1 = *reinterpret_cast<const float2*>(xin + p * 6 + 2);
+                    const float2 v2 = *reinterpret_cast<const float2*>(xin + p * 6 + 4);
                     const float dx = v0.x - rt[9], dy = v0.y - rt[10], dz = v1.x - rt[11];
                     in[0] = rt[0] * dx + rt[1] * dy + rt[2] * dz;
                     in[1] = rt[3] * dx + rt[4] * dy + rt[5] * dz;
@@ -388,12 +431,16 @@ void launch_upper_point_mma(float* x, const float* R, const float* t, const floa
                             long long F, int N, int sm_count, cudaStream_t st) {
     if (F <= 0) return;
     static bool attr_set[64] = {false};
-    if (first_use_on_device(attr_set)) {
-        cudaFuncSetAttribute(upper_point_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MmaSmem));
+    const size_t smem = sizeof(MmaSmem) + 2 * (size_t)N * 6 * sizeof(float);       // + the two staged cloud buffers
+    static int attr_bytes[64] = {0};
+    int d = 0;
+    cudaGetDevice(&d);
+    if (attr_bytes[d & 63] < (int)smem) {
+        cudaFuncSetAttribute(upper_point_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_bytes[d & 63] = (int)smem;
     }
     long long grid = F < (long long)sm_count * 2 ? F : (long long)sm_count * 2;     // 2 CTAs of 128 threads x 250 registers per SM
-    MMEGO_LAUNCH(upper_point_mma_kernel, dim3((unsigned)grid), dim3(MT), sizeof(MmaSmem), st, x, R, t, wblob, g, gw, F,
-                 N);
+    MMEGO_LAUNCH(upper_point_mma_kernel, dim3((unsigned)grid), dim3(MT), smem, st, x, R, t, wblob, g, gw, F, N);
 }
 
 }  // namespace mmego

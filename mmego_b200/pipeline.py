@@ -106,11 +106,13 @@ class ShardedRunner:
     """Data-parallel wrapper: each rank runs `step_fn` on its contiguous shard; predictions are all-gathered and the
     float64 error sums all-reduced.  Snippets are independent, so this is the only communication of the path.
 
-    `run` is the synchronous form.  `submit` / `collect` split it: `submit` runs the shard's step and ENQUEUES the
-    collectives on a side stream (after an event on the compute stream), so the gather of step i travels over NVLink
-    while step i+1 computes and no rank waits for the slowest GPU inside a step; `collect` makes the current stream wait
+    `run` is the synchronous form (collectives at the end of the step on the compute stream).  `submit` / `collect` split
+    it: `submit` runs the shard's step and ENQUEUES the collectives on a side stream (after an event on the compute
+    stream), so the gather of step i travels over NVLink while step i+1 computes; `collect` makes the current stream wait
     for the oldest outstanding collective and returns its (pred, sums).  Two result slots are kept, so at most two steps
-    may be outstanding.  With equal shards the gathered buffer already IS the final [B, L, 21, 3] layout (rank-major =
+    may be outstanding.  Measured on 8 B200s: the overlapped form is SLOWER for this pipeline (weak efficiency 0.936 vs
+    0.968): NCCL's CTAs spin on a few SMs while they wait for the slowest rank, and the persistent LSTM kernel partitions
+    its work statically over all 148 SMs, so the slowed SMs set the time of every launch -- `bench.py` defaults to `run`.  With equal shards the gathered buffer already IS the final [B, L, 21, 3] layout (rank-major =
     snippet order): no concatenation copy.  `collective_ms()` returns the device time spent in the collectives."""
 
     def __init__(self, step_fn, world: int, rank: int, group=None):
@@ -149,6 +151,13 @@ class ShardedRunner:
         pred, sums = self.step_fn(lo, hi, B, *step_args)      # pred [hi-lo, L, 21, 3], sums float64[SUMS_LEN]
         if self.world == 1:
             return pred, sums
+        if pred.is_cuda:                                       # device time of the collectives (incl. waiting for the slowest rank)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = self._gather(B, pred, sums, 0)
+            e1.record()
+            self._events.append((e0, e1))
+            return out
         return self._gather(B, pred, sums, 0)
 
     # ------------------------------------------------------------------------------------------ pipelined
