@@ -766,6 +766,10 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
 #endif
         return MMEGO_OK;
     }
+    if (!strcmp(key, "point_stage")) {
+        h->point_stage = value != 0;
+        return MMEGO_OK;
+    }
     if (!strcmp(key, "gcn_snip")) {
         h->gcn_snip = (int)value;
         return MMEGO_OK;
@@ -1051,7 +1055,7 @@ int mmego_upper_forward(mmego_handle* h, float* x, const float* h0, const float*
             launch_upper_point(x, R, t, W.point.p, w.g, global_w, F, N, h->sm_count, st);
         else
 #endif
-            launch_upper_point_mma(x, R, t, W.point_mma.p, w.g, global_w, F, N, h->sm_count, st);   // Upper_Net.py:379-381 (+gpointnet)
+            launch_upper_point_mma(x, R, t, W.point_mma.p, w.g, global_w, F, N, h->sm_count, h->point_stage, st);   // Upper_Net.py:379-381 (+gpointnet)
     }
     tap(h, "upper.g", w.g, (size_t)F * 64 * 4, st);
     const float* hs = run_small_lstm(h, W.lstm, w.g, 64, h0, c0, hn, cn, B, L, w.lstm, st);   // :339

@@ -87,7 +87,7 @@ void launch_upper_point(float* x, const float* R, const float* t, const float* w
 void launch_lstm_small(const float* gx, const float* whh, const float* h0, const float* c0, float* y, float* hn,
                        float* cn, int S, int T, cudaStream_t st);
 void launch_upper_point_mma(float* x, const float* R, const float* t, const float* wblob, float* g, float* gw,
-                            long long F, int N, int sm_count, cudaStream_t st);
+                            long long F, int N, int sm_count, int stage_clouds, cudaStream_t st);
 void launch_lstm_small_mma(const float* x, long long ldx, int In, const float* blob, float* gx, const float* h0,
                            const float* c0, float* y, float* hn, float* cn, int S, int T, int sm_count,
                            cudaStream_t st);
@@ -324,6 +324,7 @@ struct mmego_handle {
     int small_lstm_gemm = 1;  // H=64 LSTMs: 0 = fp32 FFMA, 1 = mma.sync fp16x3 (default)
     int tc_kb_chunk0 = 8;     // ... of the first two chunks of every tile
     int tc_kb_chunk = 4;      // fp16x3 mode: K blocks (of 64) per TMEM partial accumulation (see lstm_tc.cu)
+    int point_stage = 0;      // upper point encoder: 1 = radar clouds staged into shared memory by TMA bulk copies one frame ahead
     int gcn_snip = 1;         // ST-GCN temporal convs: 1 = snippet-resident transposed kernel (L <= 20), 0 = row-tiled GEMM
     unsigned* dev_error = nullptr;   // device word set by a kernel whose bounded wait gave up (mmego_debug_stats out8[7])
     int imu_resident = 1;     // small batches (B*L <= kResMaxSeq): persistent fp32 LSTM with weights resident in shared memory

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(MT, 2) upper_point_mma_kernel(float* __restric
                                                                 const float* __restrict__ t,
                                                                 const float* __restrict__ wblob,
                                                                 float* __restrict__ gout, float* __restrict__ gw,
-                                                                long long F, int N) {
+                                                                long long F, int N, int stage_clouds) {
     MMEGO_DYN_SMEM(MmaSmem, sp);
     MmaSmem& s = *sp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(MT, 2) upper_point_mma_kernel(float* __restric
     float* cloud = reinterpret_cast<float*>(sp + 1);
     const uint32_t cloud_bytes = (uint32_t)N * 24u;
 #ifndef MMEGO_EMUL
-    const bool staged = (cloud_bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+    const bool staged = stage_clouds && (cloud_bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s.bar);
     if (staged) {
         if (tid == 0) {
@@ -428,7 +428,7 @@ void launch_upper_point(float* x, const float* R, const float* t, const float* w
 
 // wblob: UpperMmaLayout (pack_upper_point_mma)
 void launch_upper_point_mma(float* x, const float* R, const float* t, const float* wblob, float* g, float* gw,
-                            long long F, int N, int sm_count, cudaStream_t st) {
+                            long long F, int N, int sm_count, int stage_clouds, cudaStream_t st) {
     if (F <= 0) return;
     static bool attr_set[64] = {false};
     const size_t smem = sizeof(MmaSmem) + 2 * (size_t)N * 6 * sizeof(float);       // + the two staged cloud buffers
@@ -440,7 +440,7 @@ void launch_upper_point_mma(float* x, const float* R, const float* t, const floa
         attr_bytes[d & 63] = (int)smem;
     }
     long long grid = F < (long long)sm_count * 2 ? F : (long long)sm_count * 2;     // 2 CTAs of 128 threads x 250 registers per SM
-    MMEGO_LAUNCH(upper_point_mma_kernel, dim3((unsigned)grid), dim3(MT), smem, st, x, R, t, wblob, g, gw, F, N);
+    MMEGO_LAUNCH(upper_point_mma_kernel, dim3((unsigned)grid), dim3(MT), smem, st, x, R, t, wblob, g, gw, F, N, stage_clouds);
 }
 
 }  // namespace mmego
