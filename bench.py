@@ -428,6 +428,8 @@ def main():
         pipe.handle.profile_begin()
         n0 = pipe.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            runner.collective_ms()      # drop the warm-up steps' events: the figure below covers the timed steps only
         barrier()
         e0.record()
         if world > 1 and args.collective == "async":

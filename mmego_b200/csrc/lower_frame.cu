@@ -233,8 +233,14 @@ struct MmaCarve {
     float *pts, *key, *Kf, *vp, *psum, *asum;
     int* sel;
     uint32_t *kph, *kpl;
+    unsigned long long* srt;   // composite sort keys, only carved for N > kRankSelectMax
+    int P;                     // N rounded up to a power of two
     size_t bytes;
 };
+// Up to this many points the O(N^2) rank select (one pass, one barrier) is the cheaper top-64; above it the frame's keys
+// are sorted as 64-bit composites (key descending, slot ascending) by a shared-memory bitonic network, O(N log^2 N).
+constexpr int kRankSelectMax = 256;
+
 __host__ __device__ inline MmaCarve lower_mma_carve(unsigned char* base, int N) {
     MmaCarve c;
     size_t off = 0;
@@ -249,8 +255,45 @@ __host__ __device__ inline MmaCarve lower_mma_carve(unsigned char* base, int N) 
     c.sel = reinterpret_cast<int*>(take(sizeof(int) * kLowerPts));
     c.key = reinterpret_cast<float*>(take(sizeof(float) * N));
     c.pts = reinterpret_cast<float*>(take(sizeof(float) * N * 6));
+    c.P = 1;
+    while (c.P < N) c.P <<= 1;
+    c.srt = N > kRankSelectMax ? reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * c.P)) : nullptr;
     c.bytes = off;
     return c;
+}
+
+// Top-64 of a frame with more than kRankSelectMax points.  Same total order as the rank select: key descending, equal
+// keys by ascending slot (-0 == +0; NaN keys were replaced by +inf).  The float is mapped to an unsigned that ascends
+// with it, inverted, and the slot goes in the low word; padding up to the power of two sorts last.  Not inlined: the
+// main loop's register allocation stays what it is for the N <= 256 case.
+__device__ __noinline__ void bitonic_top64(unsigned long long* srt, const float* key, int* sel, int N, int P) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < P; i += NT) {
+        unsigned long long c = ~0ull;
+        if (i < N) {
+            const float kx = key[i];
+            const uint32_t b = __float_as_uint(kx == 0.f ? 0.f : kx);
+            const uint32_t asc = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+            c = ((unsigned long long)(~asc) << 32) | (uint32_t)i;
+        }
+        srt[i] = c;
+    }
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < (P >> 1); i += NT) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int hi = lo | j;
+                const unsigned long long a = srt[lo], b = srt[hi];
+                if ((a > b) == ((lo & k) == 0)) {
+                    srt[lo] = b;
+                    srt[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < kLowerPts; i += NT) sel[i] = (int)(uint32_t)srt[i];
 }
 
 __global__ void __launch_bounds__(NT, 4) lower_frame_mma_kernel(float* __restrict__ x, const float* __restrict__ R,
@@ -303,28 +346,32 @@ __global__ void __launch_bounds__(NT, 4) lower_frame_mma_kernel(float* __restric
         // rank(p) = #{q < p: key[q] >= key[p]} + #{q > p: key[q] > key[p]}; keys are read four at a time (broadcast
         // 16-byte loads), one compare per key: with 'x >= k' for slots below p and 'x > k' above, the tie rule needs no
         // second compare.
-        for (int p = tid; p < N; p += NT) {
-            const float kx = s.key[p];
-            int rank = 0;
-            const int n4 = N & ~3;
-            for (int q = 0; q < n4; q += 4) {
-                const float4 k4 = *reinterpret_cast<const float4*>(s.key + q);
-                if (q + 3 < p) {
-                    rank += (k4.x >= kx) + (k4.y >= kx) + (k4.z >= kx) + (k4.w >= kx);
-                } else if (q > p) {
-                    rank += (k4.x > kx) + (k4.y > kx) + (k4.z > kx) + (k4.w > kx);
-                } else {                                  // the group that contains p
-                    rank += (q < p ? k4.x >= kx : (q > p && k4.x > kx));
-                    rank += (q + 1 < p ? k4.y >= kx : (q + 1 > p && k4.y > kx));
-                    rank += (q + 2 < p ? k4.z >= kx : (q + 2 > p && k4.z > kx));
-                    rank += (q + 3 < p ? k4.w >= kx : (q + 3 > p && k4.w > kx));
+        if (N <= kRankSelectMax) {
+            for (int p = tid; p < N; p += NT) {
+                const float kx = s.key[p];
+                int rank = 0;
+                const int n4 = N & ~3;
+                for (int q = 0; q < n4; q += 4) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(s.key + q);
+                    if (q + 3 < p) {
+                        rank += (k4.x >= kx) + (k4.y >= kx) + (k4.z >= kx) + (k4.w >= kx);
+                    } else if (q > p) {
+                        rank += (k4.x > kx) + (k4.y > kx) + (k4.z > kx) + (k4.w > kx);
+                    } else {                                  // the group that contains p
+                        rank += (q < p ? k4.x >= kx : (q > p && k4.x > kx));
+                        rank += (q + 1 < p ? k4.y >= kx : (q + 1 > p && k4.y > kx));
+                        rank += (q + 2 < p ? k4.z >= kx : (q + 2 > p && k4.z > kx));
+                        rank += (q + 3 < p ? k4.w >= kx : (q + 3 > p && k4.w > kx));
+                    }
                 }
+                for (int q = n4; q < N; ++q) {
+                    const float kq = s.key[q];
+                    rank += (q < p ? kq >= kx : (q > p && kq > kx));
+                }
+                if (rank < kLowerPts) s.sel[rank] = p;
             }
-            for (int q = n4; q < N; ++q) {
-                const float kq = s.key[q];
-                rank += (q < p ? kq >= kx : (q > p && kq > kx));
-            }
-            if (rank < kLowerPts) s.sel[rank] = p;
+        } else {
+            bitonic_top64(s.srt, s.key, s.sel, N, s.P);
         }
         // ---- B2: to_k (warps 0,1) / to_v (warps 2,3) of the joint features: 4 n-tiles each ----------------------
         {

@@ -359,3 +359,39 @@ def check_nan_inputs_do_not_corrupt(h):
     assert torch.isnan(ll_bad[1]).any()
     l_again, ll_again = run(g["data"], R, t)  # and the handle still works
     assert torch.equal(ll_again, ll_ref) and torch.equal(l_again, l_ref)
+
+
+def check_top64_sort_path(h_mma, h_ffma, N):
+    """Above 256 points per frame the top-64 is a bitonic sort of (key, slot) composites instead of the O(N^2) rank
+    select; both must realise the reference's order (Net/Lower_Net.py:218 with a stable tie rule): key descending, equal
+    keys by ascending slot, -0 == +0, NaN first.  Frames are built with heavy ties (x quantised to 0.05 m, different
+    y/z/doppler per slot), signed zeros and one NaN, and the tensor-core path (`h_mma`, option point_gemm=1) is compared
+    with the FFMA generation (`h_ffma`, point_gemm=0), which always rank-selects; a wrong pick among tied keys swaps in
+    a different point and moves the output by far more than the 1e-4 allowed here."""
+    gen = torch.Generator().manual_seed(100 + N)
+    B, L = 2, 3
+    data = torch.randn(B, L, N, 6, generator=gen) * 0.5
+    data[..., 0] = torch.round(data[..., 0] / 0.05) * 0.05
+    data[0, 0, 5::7, 0] = 0.0
+    data[0, 0, 6::7, 0] = -0.0
+    data[0, 1, :80, 0] = 1.25                       # 80 equal largest keys: the cut falls inside a run of ties
+    data[1, 1, 11, 0] = float("nan")                # NaN stays in snippet 1
+    skl = dev(h_mma, golden("synth3.npz")["skl"][:B])
+    R = torch.eye(3).expand(B, L, 3, 3).contiguous()
+    t = torch.zeros(B, L, 3)
+    h0 = torch.zeros(6, B, 64)
+    outs = []
+    for h, pg in ((h_mma, 1), (h_ffma, 0)):
+        h.set_option("point_gemm", pg)
+        try:
+            x = dev(h, data.clone())
+            l = h.upper_forward(x, dev(h, h0), dev(h, h0), dev(h, skl.cpu()), dev(h, R), dev(h, t))[0]
+            outs.append((l, h.lower_forward(l, x, dev(h, skl.cpu()), dev(h, R), dev(h, t))[0]))
+        finally:
+            h.set_option("point_gemm", 1)
+    (l1, ll1), (l0, ll0) = outs
+    assert torch.isfinite(ll1[0]).all() and torch.isfinite(ll0[0]).all()
+    d = (ll1[0].cpu() - ll0[0].cpu()).abs().max().item()
+    assert d < 1e-4, d
+    assert torch.equal(torch.isnan(ll1[1]).cpu(), torch.isnan(ll0[1]).cpu())
+    return d

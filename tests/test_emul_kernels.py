@@ -46,6 +46,11 @@ def test_upper_lower_sweep_shape(handle):
     P.check_sweep_golden(handle, "sweep_L20_N512.npz")
 
 
+@pytest.mark.parametrize("N", [257, 300, 512])
+def test_top64_bitonic_sort_path_matches_rank_select(handle, N):
+    P.check_top64_sort_path(handle, handle, N)
+
+
 def test_nan_inputs_stay_in_their_snippet(handle):
     P.check_nan_inputs_do_not_corrupt(handle)
 
