@@ -234,12 +234,18 @@ struct MmaCarve {
     int* sel;
     uint32_t *kph, *kpl;
     unsigned long long* srt;   // composite sort keys, only carved for N > kRankSelectMax
+    unsigned long long* xch;   // two 128-entry exchange buffers of the register sort, only carved for N <= kRegSortMax
     int P;                     // N rounded up to a power of two
     size_t bytes;
 };
 // Up to this many points the O(N^2) rank select (one pass, one barrier) is the cheaper top-64; above it the frame's keys
 // are sorted as 64-bit composites (key descending, slot ascending) by a shared-memory bitonic network, O(N log^2 N).
 constexpr int kRankSelectMax = 256;
+// Up to one point per thread (the configuration's N = 128) the (key, slot) composites are sorted in REGISTERS: a 128-wide
+// bitonic network whose 25 in-warp stages are shuffles and whose 3 cross-warp stages go through shared memory.  ~0.9k
+// warp instructions per frame instead of the rank select's ~3.5k (it was 40 % of this kernel's issue slots).
+constexpr int kRegSortMax = 128;
+static_assert(kRegSortMax == 128, "sort128_top64 assumes 128 threads = 128 elements");
 
 __host__ __device__ inline MmaCarve lower_mma_carve(unsigned char* base, int N) {
     MmaCarve c;
@@ -258,6 +264,7 @@ __host__ __device__ inline MmaCarve lower_mma_carve(unsigned char* base, int N) 
     c.P = 1;
     while (c.P < N) c.P <<= 1;
     c.srt = N > kRankSelectMax ? reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * c.P)) : nullptr;
+    c.xch = N <= kRegSortMax ? reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * 2 * kRegSortMax)) : nullptr;
     c.bytes = off;
     return c;
 }
@@ -294,6 +301,44 @@ __device__ __noinline__ void bitonic_top64(unsigned long long* srt, const float*
         }
     }
     for (int i = tid; i < kLowerPts; i += NT) sel[i] = (int)(uint32_t)srt[i];
+}
+
+// One element per thread, ascending by composite = (inverted sortable key, slot): position i ends up in thread i.
+__device__ __forceinline__ void sort128_top64(const float* key, int* sel, unsigned long long* xch, int N) {
+    const int i = threadIdx.x;
+    uint32_t hi = 0xffffffffu, lo = (uint32_t)i;          // padding sorts last
+    if (i < N) {
+        const float kx = key[i];
+        const uint32_t b = __float_as_uint(kx == 0.f ? 0.f : kx);
+        hi = ~((b & 0x80000000u) ? ~b : (b | 0x80000000u));
+    }
+    int buf = 0;
+#pragma unroll
+    for (int k = 2; k <= 128; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            uint32_t ph, pl;
+            if (j < 32) {
+                ph = __shfl_xor_sync(0xffffffffu, hi, j);
+                pl = __shfl_xor_sync(0xffffffffu, lo, j);
+            } else {
+                unsigned long long* x = xch + buf * 128;
+                buf ^= 1;
+                x[i] = ((unsigned long long)hi << 32) | lo;
+                __syncthreads();
+                const unsigned long long p = x[i ^ j];
+                ph = (uint32_t)(p >> 32);
+                pl = (uint32_t)p;
+            }
+            const bool partner_less = ph < hi || (ph == hi && pl < lo);
+            const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+            if (partner_less == keep_min) {
+                hi = ph;
+                lo = pl;
+            }
+        }
+    }
+    if (i < kLowerPts) sel[i] = (int)lo;
 }
 
 __global__ void __launch_bounds__(NT, 4) lower_frame_mma_kernel(float* __restrict__ x, const float* __restrict__ R,
@@ -346,7 +391,9 @@ __global__ void __launch_bounds__(NT, 4) lower_frame_mma_kernel(float* __restric
         // rank(p) = #{q < p: key[q] >= key[p]} + #{q > p: key[q] > key[p]}; keys are read four at a time (broadcast
         // 16-byte loads), one compare per key: with 'x >= k' for slots below p and 'x > k' above, the tie rule needs no
         // second compare.
-        if (N <= kRankSelectMax) {
+        if (N <= kRegSortMax) {
+            sort128_top64(s.key, s.sel, s.xch, N);
+        } else if (N <= kRankSelectMax) {
             for (int p = tid; p < N; p += NT) {
                 const float kx = s.key[p];
                 int rank = 0;

@@ -46,7 +46,7 @@ def test_upper_lower_sweep_shape(handle):
     P.check_sweep_golden(handle, "sweep_L20_N512.npz")
 
 
-@pytest.mark.parametrize("N", [257, 300, 512])
+@pytest.mark.parametrize("N", [64, 100, 128, 257, 300, 512])
 def test_top64_bitonic_sort_path_matches_rank_select(handle, N):
     P.check_top64_sort_path(handle, handle, N)
 
