@@ -71,10 +71,23 @@ const char* mmego_last_error(const mmego_handle* h);
  *          "head_gemm"   (fully connected heads: 1 = one fused mma.sync kernel per head, default; 0 = fp32 FFMA GEMMs),
  *          "host_chunk"  (mmego_infer_host: snippets per stage of its H2D / compute / D2H pipeline, default 2048; the
  *                         first stage is an eighth of that so the un-overlappable first copy stays short),
+ *          "imu_resident" (1, default: IMU_Net calls of at most 64 frames (B*L) take the latency path -- fp32 weights
+ *                         resident in shared memory, one persistent cooperative launch per bi-LSTM layer, 7 launches per
+ *                         call; 0 = always the tcgen05 path),
+ *          "gcn_snip"    (ST-GCN temporal convolutions, L <= 20: bit 0 (default on) = snippet-resident transposed kernel
+ *                         (one CTA per snippet, window loaded once for the nine taps); bit 4 = a second accumulator drain
+ *                         per 64-channel block (relative error 5.6e-6 instead of 9.5e-6 on tests/golden/gcn2.npz, 12 %
+ *                         slower); 0 = row-tiled GEMM),
+ *          "point_stage" (upper point encoder: 1 = radar clouds staged into shared memory by cp.async.bulk under the
+ *                         previous frame's MMAs; default 0 -- measured 2-3 % slower than per-lane loads on a B200),
  *          "tc_kb_chunk" (imu_gemm=1: K blocks of 64 accumulated in TMEM before draining into fp32 registers, default 4;
  *                         longer chunks are NOT faster -- the MMA work is the limit -- and ~1.5x noisier at 8,
  *                         profiles/r01_lstm_chunk_accuracy.txt),
  *          "tc_cta_pair" (H=512 LSTM kernel on CTA pairs, cta_group::2 M=256 tiles, default 1),
+ *          "tc_persist"  (H=512 LSTM kernel: timesteps 1..T-1 of a layer run as ONE launch whose work items wait for the
+ *                         h_{t-1} they read; bit 0 = rnn_slow (default on: -1.1 ms per 4096 snippets, its 256 items per
+ *                         step no longer pay 4 rounds for 3.46), bit 1 = rnn_fast (default off: that kernel is power
+ *                         bound and measured slower without its idle tails); results are bit-identical either way),
  *          "tc_pdl"      (H=512 LSTM timestep launches use programmatic dependent launch: the prologue of step t+1
  *                         overlaps the tail of step t, default 1),
  *          "tc_lo_drop"  (imu_gemm=1: low mantissa bits rounded away in the residual (lo) fp16 planes of the H=512 LSTM

@@ -397,9 +397,9 @@ int imu_chunk_fast_tc(mmego_handle* h, const float* imu, long long f0, long long
     int rc = 0;
     {
         Prof p(h, "imu.lstm_fast", st);
-        rc |= tc_lstm_layer(h, W.tc_fast[0], w.u[0], lo(w.u), w.y0[0], lo(w.y0), w.cst, S, w.Spad, n, npass, st);   // :80
+        rc |= tc_lstm_layer(h, W.tc_fast[0], w.u[0], lo(w.u), w.y0[0], lo(w.y0), w.cst, S, w.Spad, n, npass, (h->tc_persist & 2) != 0, st);   // :80
         tap_split("imu.y0", w.y0, S * n * 2 * kImuH);
-        rc |= tc_lstm_layer(h, W.tc_fast[1], w.y0[0], lo(w.y0), w.y1[0], lo(w.y1), w.cst, S, w.Spad, n, npass, st);
+        rc |= tc_lstm_layer(h, W.tc_fast[1], w.y0[0], lo(w.y0), w.y1[0], lo(w.y1), w.cst, S, w.Spad, n, npass, (h->tc_persist & 2) != 0, st);
     }
     tap_split("imu.f", w.y1, S * n * 2 * kImuH);
     {
@@ -428,8 +428,8 @@ int imu_slow_decode_tc(mmego_handle* h, float* R, float* t, long long B, int L, 
     int rc = 0;
     {
         Prof p(h, "imu.lstm_slow", st);
-        rc |= tc_lstm_layer(h, W.tc_slow[0], w.s[0], lo(w.s), w.z0[0], lo(w.z0), w.cst, B, w.Spad, L, npass, st);  // :85
-        rc |= tc_lstm_layer(h, W.tc_slow[1], w.z0[0], lo(w.z0), w.z1[0], lo(w.z1), w.cst, B, w.Spad, L, npass, st);
+        rc |= tc_lstm_layer(h, W.tc_slow[0], w.s[0], lo(w.s), w.z0[0], lo(w.z0), w.cst, B, w.Spad, L, npass, (h->tc_persist & 1) != 0, st);  // :85
+        rc |= tc_lstm_layer(h, W.tc_slow[1], w.z0[0], lo(w.z0), w.z1[0], lo(w.z1), w.cst, B, w.Spad, L, npass, (h->tc_persist & 1) != 0, st);
     }
     tap_split("imu.g", w.z1, S * 2 * kImuH);
     {
@@ -650,6 +650,7 @@ int mmego_destroy(mmego_handle* h) {
     if (h->stage_dev) cudaFree(h->stage_dev);
     if (h->tc_stats) cudaFree(h->tc_stats);
     if (h->dev_error) cudaFree(h->dev_error);
+    if (h->tc_sync) cudaFree(h->tc_sync);
     for (ProfSpan& sp : h->prof) {
         if (sp.e0) cudaEventDestroy(sp.e0);
         if (sp.e1) cudaEventDestroy(sp.e1);
@@ -776,6 +777,11 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
     }
     if (!strcmp(key, "imu_resident")) {
         h->imu_resident = value != 0;
+        return MMEGO_OK;
+    }
+    if (!strcmp(key, "tc_persist")) {
+        if (value < 0 || value > 3) return fail(h, MMEGO_EINVAL, "tc_persist must be in 0..3");
+        h->tc_persist = (int)value;
         return MMEGO_OK;
     }
     if (!strcmp(key, "tc_pdl")) {
@@ -1389,8 +1395,12 @@ int mmego_infer_host(mmego_handle* h, const float* imu_host, const float* data_h
         }
     }
     if (metrics) CUDA_TRY(h, cudaMemcpyAsync(sums_host, sums, MMEGO_SUMS_LEN * sizeof(double), cudaMemcpyDeviceToHost, st));
+    unsigned dev_err = 0;
+    if (h->dev_error) CUDA_TRY(h, cudaMemcpyAsync(&dev_err, h->dev_error, sizeof(dev_err), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
     CUDA_TRY(h, cudaStreamSynchronize(h->d2h_stream));
+    if (dev_err)      // a kernel's bounded wait (item dependency / mbarrier) gave up: the outputs are not to be trusted
+        return fail(h, MMEGO_ECUDA, "infer_host: a device-side wait timed out (flag %u); results are invalid", dev_err);
     return MMEGO_OK;
 }
 

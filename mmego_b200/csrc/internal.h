@@ -269,7 +269,7 @@ struct StateDict;
 bool tc_supported();
 bool tc_pack_layer(mmego_handle* h, const StateDict& sd, const std::string& prefix, int layer, int In, TcLstmLayer& out);
 int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const void* xlo, void* yhi, void* ylo,
-                  float* cstate, long long S, long long Spad, int T, int npass, cudaStream_t st);
+                  float* cstate, long long S, long long Spad, int T, int npass, bool persist_steps, cudaStream_t st);
 void tc_imu_fc1(const float* imu, const float* fc1_mma, void* uhi, void* ulo, long long rows, int sm_count, int lo_drop,
                 cudaStream_t st);
 void tc_imu_pool(const void* yhi, const void* ylo, const float* attn, void* shi, void* slo, long long F, int n,
@@ -316,6 +316,9 @@ struct mmego_handle {
     int tc_cta_pair = 1;      // H=512 LSTM kernel: 1 = CTA pairs (cta_group::2, M = 256)
     int tc_lo_drop = 4;       // H=512 LSTM operands: low mantissa bits rounded away in the residual (lo) planes, 0..6 (power, lstm_tc.cu)
     int tc_lo_drop_w = 0;     // ... already applied to the packed weight planes (one-way)
+    int tc_persist = 1;       // H=512 LSTM kernel: timesteps 1..T-1 of a layer as ONE launch with item-level dependencies; bit 0 = rnn_slow, bit 1 = rnn_fast (0 = one launch per step)
+    unsigned* tc_sync = nullptr;   // its arrival counters
+    size_t tc_sync_words = 0;
     int tc_pdl = 1;           // H=512 LSTM kernel: 1 = programmatic dependent launch (step t+1's prologue overlaps step t's tail)
     int gcn_gemm = 0;         // ST-GCN GEMMs: 0 = fp32 FFMA, 1 = tcgen05 fp16x3 (default when available)
     int point_gemm = 1;       // point encoders + cross attention: 0 = fp32 FFMA, 1 = mma.sync fp16x3 (default)

@@ -82,8 +82,11 @@ struct StepParams {
     int m_tiles;
     int kb_in, kb_rec;   // K blocks of the input segment / of the recurrent segment (0 on the first step)
     int in_features;     // column of W where the recurrent block starts
-    int tt0, tt1, tp0, tp1;   // per direction: time index of this step, and of the previous one (no arrays: dynamic
-                         // indexing of kernel parameters would force a local-memory copy)
+    int step0, nsteps;   // this launch covers timesteps step0 .. step0+nsteps-1 (forward direction: time = step,
+                         // backward: T-1-step); nsteps > 1 = persistent over timesteps, see dep_wait()
+    unsigned* sync;      // nsteps > 1: arrival counters [nsteps-1][m_tiles_pad][2], zeroed before the launch
+    int m_tiles_pad;     // m_tiles rounded up to a whole number of CTA groups
+    unsigned* error;     // set when a bounded dependency wait gives up (mmego_debug_stats out8[7])
     int T;
     const float* bias;   // [2][2048], packed row order
     float* cstate;       // [2][512][Spad]
@@ -154,6 +157,34 @@ __device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po
 #define TC_DBG(p) 0
 #endif
 
+// Persistent mode (StepParams::nsteps > 1): work item (step, m tile, direction, unit tile) may read h_{step-1} of its 128
+// sequences only when all unit tiles of (step-1, m tile, direction) have stored it.  Every epilogue warp of such an item
+// makes its stores visible (generic -> async proxy fence, device fence) and adds 1 to the counter of (step, m, dir); the
+// TMA producer of a dependent item polls the counter before its first recurrent K block.  Items are walked in (step,
+// item) order by every CTA and the grid is co-resident (1 CTA per SM), so a dependency is always on an item that has
+// already been started: no deadlock.  The poll is bounded and raises a device flag instead of hanging.
+__device__ __forceinline__ void dep_wait(const unsigned* cnt, unsigned target, unsigned* err) {
+    unsigned v = 0;
+    for (int polls = 0;; ++polls) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+        if (v >= target) break;
+        if ((polls & 255) == 255) {
+            unsigned e = 0;
+            if (err) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(err) : "memory");
+            if (e) break;
+            if (polls > (1 << 21)) {
+                if (err) atomicExch(err, 2u);
+                break;
+            }
+        }
+        __nanosleep(64);
+    }
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+__device__ __forceinline__ void dep_signal(unsigned* cnt) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
+}
+
 template <int NPASS, int NCTA, int BN, bool MUFU_CELL = (NPASS == 1)>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtensorMap mXlo,
@@ -178,6 +209,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
     for (int i = threadIdx.x; i < 2 * 4 * kImuH; i += kThreads) sbias[i] = p.bias[i];
     // work items: (sequence-tile group, direction, unit tile); a group is NCTA consecutive sequence tiles, one per CTA
     const int total_tiles = ((p.m_tiles + NCTA - 1) / NCTA) * 2 * kNTiles;
+    const int total_items = total_tiles * p.nsteps;      // (step, tile), step-major
     const int kb_total = p.kb_in + p.kb_rec;
     const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0;
     const int first_item = blockIdx.x / NCTA, item_stride = gridDim.x / NCTA;
@@ -232,11 +264,14 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = first_item; tile < total_tiles; tile += item_stride) {
+            for (int item = first_item; item < total_items; item += item_stride) {
+                const int sl = item / total_tiles, tile = item - sl * total_tiles, step = p.step0 + sl;
                 const int nt = tile % kNTiles, dir = (tile / kNTiles) & 1, m = (tile / (2 * kNTiles)) * NCTA + (int)rank;
                 const int wrow = dir * 4 * kImuH + nt * BN + (int)rank * (BN / NCTA);
-                const int tt = dir ? p.tt1 : p.tt0, tp = dir ? p.tp1 : p.tp0;
+                const int tt = dir ? p.T - 1 - step : step, tp = dir ? p.T - step : step - 1;
                 for (int kb = 0; kb < kb_total; ++kb) {
+                    if (kb == p.kb_in && sl > 0)       // h_{step-1} of these sequences: written inside this launch
+                        dep_wait(p.sync + ((long long)(sl - 1) * p.m_tiles_pad + m) * 2 + dir, kNTiles * kEpiWarps, p.error);
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
                     uint8_t* sw = sa + C::PLANES * A_TILE;
@@ -282,7 +317,7 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
             uint32_t cc = 0;      // running chunk counter (same sequence in the epilogue warps)
             long long ms_epi = 0, ms_tma = 0, ms_tiles = 0;
             const long long ms_start = (TC_DBG(p) & 4) ? clock64() : 0;
-            for (int tile = first_item; tile < total_tiles; tile += item_stride) {
+            for (int item = first_item; item < total_items; item += item_stride) {
                 if (TC_DBG(p) & 4) ++ms_tiles;
                 for (int c0 = 0, ci = 0; c0 < kb_total; ++cc, ++ci) {
                     const int clen = ci < 2 ? p.kb_chunk0 : p.kb_chunk;
@@ -350,7 +385,8 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
         const int u0 = part * kUnitsPerEpiWarp;
         uint32_t cc = 0;
         const uint32_t tempty_remote0 = NCTA == 2 ? mapa_u32(smem_u32(&tempty[0]), 0) : 0;   // + 8 bytes per buffer
-        for (int tile = first_item; tile < total_tiles; tile += item_stride) {
+        for (int item = first_item; item < total_items; item += item_stride) {
+            const int sl = item / total_tiles, tile = item - sl * total_tiles, step = p.step0 + sl;
             const int nt = tile % kNTiles, dir = (tile / kNTiles) & 1, m = (tile / (2 * kNTiles)) * NCTA + (int)rank;
             float acc[4][kUnitsPerEpiWarp];     // i, f, g, o pre-activations (scaled) of this thread's row
             const long long row = (long long)m * BM + q * 32 + lane;
@@ -399,13 +435,13 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
             // no L1, so a spilled register costs an L2 round trip: the 16 units are processed in two halves of 8 whose
             // temporaries (cell state, packed outputs) are kept small, with a scheduling fence between the halves.
             const float* bias = sbias + dir * 4 * kImuH + nt * BN + u0;
-            const long long o = (row * p.T + (dir ? p.tt1 : p.tt0)) * (2 * kImuH) + dir * kImuH + nt * kUnitsPerTile + u0;
+            const long long o = (row * p.T + (dir ? p.T - 1 - step : step)) * (2 * kImuH) + dir * kImuH + nt * kUnitsPerTile + u0;
 #pragma unroll
             for (int half = 0; half < kUnitsPerEpiWarp / 8; ++half) {
                 float cprev[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)      // 8 independent coalesced loads in flight
-                    cprev[j] = (has_state && ok) ? __ldcs(cbase + (long long)(half * 8 + j) * p.Spad) : 0.f;
+                    cprev[j] = (has_state && ok) ? __ldcg(cbase + (long long)(half * 8 + j) * p.Spad) : 0.f;   // L2: another SM wrote it
                 uint32_t ph[4], pl[4];
 #pragma unroll
                 for (int j2 = 0; j2 < 4; ++j2) {
@@ -433,6 +469,13 @@ lstm_tc_step_kernel(const __grid_constant__ CUtensorMap mXhi, const __grid_const
                     if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + o + half * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                 }
                 asm volatile("" ::: "memory");
+            }
+            if (sl + 1 < p.nsteps) {
+                // h_step and c of this warp's rows and units are stored: publish them to the next step's items
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) dep_signal(p.sync + ((long long)sl * p.m_tiles_pad + m) * 2 + dir);
             }
         }
     }
@@ -880,7 +923,7 @@ void launch_step(int grid, cudaStream_t st, const CUtensorMap& mXhi, const CUten
 
 // One bidirectional layer: x planes [S][T][In] -> y planes [S][T][1024]; cstate [2][512][Spad] fp32 scratch.
 int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const void* xlo, void* yhi, void* ylo,
-                  float* cstate, long long S, long long Spad, int T, int npass, cudaStream_t st) {
+                  float* cstate, long long S, long long Spad, int T, int npass, bool persist_steps, cudaStream_t st) {
     CUtensorMap mXhi, mXlo, mYhi, mYlo;
     const int In = lw.in_features;
     if (!make_act_map(&mXhi, xhi, S, T, In) || !make_act_map(&mYhi, yhi, S, T, 2 * kImuH)) return -1;
@@ -919,21 +962,47 @@ int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const
     p.stats = static_cast<unsigned long long*>(h->tc_stats);
     const int ncta = pair ? 2 : 1;
     const int total = ((p.m_tiles + ncta - 1) / ncta) * 2 * (4 * kImuH / bn);  // work items (one per CTA or CTA pair)
-    int grid = (total < h->sm_count / ncta ? total : h->sm_count / ncta) * ncta;
-    for (int step = 0; step < T; ++step) {
+    const int slots = h->sm_count / ncta;     // co-resident CTAs (pairs): the kernel takes a whole SM
+    p.m_tiles_pad = ((p.m_tiles + ncta - 1) / ncta) * ncta;
+    if (!h->dev_error) {
+        if (cudaMalloc(reinterpret_cast<void**>(&h->dev_error), 64) != cudaSuccess) return -1;
+        cudaMemsetAsync(h->dev_error, 0, 64, st);
+    }
+    p.error = h->dev_error;
+    // Steps 1 .. T-1 have the same shape (step 0 has no recurrent K blocks): with `tc_persist` they run as ONE launch
+    // whose work items carry their timestep and wait for the h_{t-1} they read (dep_wait) -- no per-step tail where
+    // the last round of items leaves most CTA pairs idle (rnn_slow: 256 items on 74 pairs = 3.46 rounds paid as 4).
+    const bool persist = persist_steps && T > 2 && !(p.dbg & 3);
+    if (persist) {
+        const size_t words = (size_t)(T - 2) * p.m_tiles_pad * 2;
+        if (h->tc_sync_words < words) {
+            if (h->tc_sync) cudaFree(h->tc_sync);
+            h->tc_sync = nullptr;
+            h->tc_sync_words = 0;
+            if (cudaMalloc(reinterpret_cast<void**>(&h->tc_sync), words * sizeof(unsigned)) != cudaSuccess) return -1;
+            h->tc_sync_words = words;
+        }
+        cudaMemsetAsync(h->tc_sync, 0, words * sizeof(unsigned), st);
+        p.sync = h->tc_sync;
+    }
+    for (int step = 0; step < T;) {
+        const int nsteps = (persist && step > 0) ? T - step : 1;
+        p.step0 = step;
+        p.nsteps = nsteps;
         p.kb_rec = step > 0 ? kImuH / BK : 0;
         p.kb_chunk = (npass == 3 && chunk_opt > 0) ? chunk_opt : (p.kb_in + p.kb_rec);
         // with four TMEM buffers (BN = 128) the MMA thread has enough run-ahead without longer first chunks
         p.kb_chunk0 = (npass == 3 && chunk_opt > 0) ? (bn == 128 ? chunk_opt : std::max(chunk_opt, h->tc_kb_chunk0)) : p.kb_chunk;
-        p.tt0 = step;
-        p.tt1 = T - 1 - step;
-        p.tp0 = step > 0 ? step - 1 : 0;
-        p.tp1 = step > 0 ? p.tt1 + 1 : p.tt1;
+        // a persistent launch may use every slot even when one step has fewer items: items of later steps start on the
+        // idle pairs, multiply their input K blocks and wait (in the TMA producer) only for the recurrent ones
+        const long long items = (long long)total * nsteps;
+        const int grid = (int)(items < slots ? items : slots) * ncta;
         ++t_launches;
 #define MMEGO_STEP(NP, NC, BNV) launch_step<NP, NC, BNV>(grid, st, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p)
         if (npass == 3) { if (pair) MMEGO_STEP(3, 2, 256); else MMEGO_STEP(3, 1, 256); }
         else { if (pair) MMEGO_STEP(1, 2, 256); else MMEGO_STEP(1, 1, 256); }
 #undef MMEGO_STEP
+        step += nsteps;
     }
     return 0;
 }

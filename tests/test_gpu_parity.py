@@ -384,6 +384,32 @@ def test_lstm_residual_rounding_and_pdl_options():
     assert float((results[0][2] - results[4][2]).abs().max()) < 2e-5
 
 
+@pytest.mark.parametrize("B,L,n", [(1, 20, 20), (3, 20, 20), (7, 5, 3), (130, 20, 20), (40, 20, 7)])
+def test_lstm_persistent_timesteps_bit_identical(B, L, n):
+    """tc_persist (default 1): timesteps 1..T-1 of an H=512 layer run as one launch whose work items wait for the
+    h_{t-1} they read.  Same arithmetic in the same order, so the result must equal the one-launch-per-step form bit
+    for bit, in the fp32-grade and the single-pass mode, and no dependency wait may have timed out."""
+    h = _capi.Handle()
+    try:
+        h.set_option("imu_resident", 0)
+        h.set_weights(_capi.NET_IMU, P.O.synth_imu_state_dict(0))
+        imu = torch.randn(B, L, n, 15, generator=torch.Generator().manual_seed(B * 100 + n)).to(h.device)
+        for mode in (1, 2):
+            h.set_option("imu_gemm", mode)
+            out = {}
+            for persist in (0, 3, 3):
+                h.set_option("tc_persist", persist)
+                R, t = h.imu_forward(imu)
+                out.setdefault(persist, []).append((R.clone(), t.clone()))
+            assert h.debug_stats(reset=True)[7] == 0
+            (R0, t0), = out[0]
+            for R1, t1 in out[3]:
+                assert torch.equal(R0, R1) and torch.equal(t0, t1)
+            assert torch.isfinite(R0).all()
+    finally:
+        h.close()
+
+
 def test_top64_tie_rule_equals_torch_cuda_sort(handle):
     """Net/Lower_Net.py:218 calls torch.sort(descending=True) WITHOUT stable=True, and 8 % of the sample frames hold
     different radar points with bit-identical xyz at the 64th/65th boundary (profiles/r02_top64_tie_count.json), so the
