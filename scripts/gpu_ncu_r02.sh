@@ -4,8 +4,10 @@ mkdir -p gpurun_out
 TAG=${1:-r02}
 CMD="python bench.py --batch 2048 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-half --no-config1"
 timeout 200 $CMD > gpurun_out/ncu_plain_${TAG}.log 2>&1 || { echo "plain run failed"; tail gpurun_out/ncu_plain_${TAG}.log; exit 1; }
-# 4 steps x ~140 launches: skip the first three steps (warm-up), list the timed one
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 420 -c 160 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launches_${TAG}.log 2>&1
+# skip the three warm-up steps, list the timed one (launches per step read from the plain run's own count)
+PER=$(python -c "import json;print(json.load(open('gpurun_out/ncu_plain_${TAG}.log'))['gpu_launches'])")
+echo "launches per step: $PER"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $((3 * PER)) -c $((PER + 8)) --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launches_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_launches_${TAG}.log
 timeout 200 $CMD > gpurun_out/ncu_plain2_${TAG}.log 2>&1 || exit 1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:lstm_tc_step -s 100 -c 3 -f -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
