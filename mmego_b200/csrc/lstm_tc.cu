@@ -623,39 +623,20 @@ __device__ __forceinline__ void pool_unpack(const PoolRow& r, bool has_lo, float
         }
     }
 }
-__device__ __forceinline__ void pool_unpack8(const PoolRow& r, int i, bool has_lo, float* v) {
-    const __half2* ah = reinterpret_cast<const __half2*>(&r.h[i]);
-    const __half2* bh = reinterpret_cast<const __half2*>(&r.l[i]);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float2 f = __half22float2(ah[k]);
-        if (has_lo) {
-            const float2 g = __half22float2(bh[k]);
-            f.x += g.x;
-            f.y += g.y;
-        }
-        v[2 * k] = f.x * kActInv;
-        v[2 * k + 1] = f.y * kActInv;
-    }
-}
 constexpr int POOL_WARPS = 4;
-// 128 registers per thread = 4 CTAs (16 warps, 128 KB of loads in flight) per SM: the attention vector lives in shared
-// memory (float4 [i][half][lane]: conflict-free), not in 32 registers -- at 157 registers the kernel ran 12 warps per SM
-// and lost bandwidth whenever the power cap lowered the SM clock (0.90 of the HBM peak alone, 0.71 inside a step).
-__global__ void __launch_bounds__(POOL_WARPS * 32, 4) imu_pool_split_kernel(const __half* __restrict__ yhi,
-                                                                           const __half* __restrict__ ylo,
-                                                                           const float* __restrict__ attn,
-                                                                           __half* __restrict__ shi, __half* __restrict__ slo,
-                                                                           long long F, int n, uint32_t lo_add, uint32_t lo_mask) {
-    __shared__ float4 saw[4 * 2 * 32];
-    for (int j = threadIdx.x; j < 4 * 2 * 32; j += POOL_WARPS * 32) {
-        const int i = j >> 6, hh = (j >> 5) & 1, l = j & 31;
-        saw[j] = *reinterpret_cast<const float4*>(attn + i * 256 + l * 8 + hh * 4);
-    }
-    __syncthreads();
+__global__ void __launch_bounds__(POOL_WARPS * 32) imu_pool_split_kernel(const __half* __restrict__ yhi,
+                                                                        const __half* __restrict__ ylo,
+                                                                        const float* __restrict__ attn,
+                                                                        __half* __restrict__ shi, __half* __restrict__ slo,
+                                                                        long long F, int n, uint32_t lo_add, uint32_t lo_mask) {
     const int lane = threadIdx.x & 31;
     const long long f = (long long)blockIdx.x * POOL_WARPS + (threadIdx.x >> 5);
     if (f >= F) return;
+    float aw[32];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) aw[i * 8 + k] = attn[i * 256 + lane * 8 + k];
     const float ab = attn[1024];
     const bool has_lo = ylo != nullptr;
     const long long base = f * (long long)n * 1024;
@@ -666,17 +647,11 @@ __global__ void __launch_bounds__(POOL_WARPS * 32, 4) imu_pool_split_kernel(cons
     pool_load(yhi, ylo, base, lane, cur);
     for (int s0 = 0; s0 < n; ++s0) {
         if (s0 + 1 < n) pool_load(yhi, ylo, base + (long long)(s0 + 1) * 1024, lane, nxt);
-        // two passes over the packed row (score, then accumulation): the 32 unpacked values are never all live, which
-        // is what keeps the kernel at 128 registers
+        float v[32];
+        pool_unpack(cur, has_lo, v);
         float a = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float v[8];
-            pool_unpack8(cur, i, has_lo, v);
-            const float4 w0 = saw[(2 * i) * 32 + lane], w1 = saw[(2 * i + 1) * 32 + lane];
-            a = fmaf(v[0], w0.x, a); a = fmaf(v[1], w0.y, a); a = fmaf(v[2], w0.z, a); a = fmaf(v[3], w0.w, a);
-            a = fmaf(v[4], w1.x, a); a = fmaf(v[5], w1.y, a); a = fmaf(v[6], w1.z, a); a = fmaf(v[7], w1.w, a);
-        }
+        for (int k = 0; k < 32; ++k) a = fmaf(v[k], aw[k], a);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         a += ab;
@@ -685,12 +660,7 @@ __global__ void __launch_bounds__(POOL_WARPS * 32, 4) imu_pool_split_kernel(cons
         const float w = expf(a - nm);
         sum = fmaf(sum, r, w);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float v[8];
-            pool_unpack8(cur, i, has_lo, v);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[i * 8 + k] = fmaf(acc[i * 8 + k], r, w * v[k]);
-        }
+        for (int k = 0; k < 32; ++k) acc[k] = fmaf(acc[k], r, w * v[k]);
         m = nm;
         cur = nxt;
     }
