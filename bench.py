@@ -533,7 +533,7 @@ def main():
             return {"bound": "tensor", "kernel": "H=512 LSTM timestep launch (rnn_fast): " + KERNEL_NAMES[mode_],
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": NCU_TRAFFIC.get(mode_) if B >= 2048 else None,
-                    "traffic_note": f"ncu dram read+write of a layer-1 step launch (M=40,960) from {traffic_src}; algorithmic bytes 1.03e9",
+                    "traffic_note": f"ncu dram read+write of the rnn_fast launch with the most traffic in {traffic_src}: a second-layer timestep (M = 40,960 sequences, K = 1536); its algorithmic bytes are 1.06e9",
                     "peak_source": peaks["source"] + ", sustained dense bf16 (kernel timed inside a long step)",
                     "avg_launch_ms": per_launch_ms, "launches": lst["launches"], "flops_per_launch": per_launch_flops,
                     "mma_passes": passes, "tensor_pipe_tflops_issued": ach * passes,

@@ -30,8 +30,10 @@ if os.path.exists(p):
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"{k:80s} n={v[0]:5d} us={v[1]:12.1f} share={v[1] / tot * 100:5.1f}%")
     out.append(f"total us {tot:.1f}\n")
-rep = os.path.join(root, "gpurun_out", f"prof_{tag}.ncu-rep")
-if os.path.exists(rep):
+import glob
+for rep in [os.path.join(root, "gpurun_out", f"prof_{tag}.ncu-rep")] + sorted(glob.glob(os.path.join(root, "gpurun_out", f"prof_{tag}_*.ncu-rep"))):
+    if not os.path.exists(rep):
+        continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -41,7 +43,7 @@ if os.path.exists(rep):
                      r"l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum$|smsp__inst_executed.avg.per_cycle_active|"
                      r"launch__shared_mem_per_block_dynamic|sm__inst_executed_pipe_tensor|smsp__cycles_active.avg$")
     idx = [i for i, h in enumerate(hdr) if pat.search(h)]
-    out.append(f"# ncu --set full ({tag}), per launch")
+    out.append(f"# ncu --set full ({os.path.basename(rep)}), per launch")
     for row in rows[2:]:
         out.append("---")
         for i in idx:

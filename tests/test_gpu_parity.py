@@ -127,10 +127,16 @@ def test_imu_golden(handle, handle_ffma, tag, mode):
 def test_default_mode_is_tensor_core_fp16x3(handle):
     # the default is the tcgen05 path, and launch counts are per handle (another handle's work is not counted)
     sb = P.O.synth_batch(1, seed=3)
-    n0 = handle.launch_count()
-    handle.imu_forward(sb["imu"].cuda())
-    n_tc = handle.launch_count() - n0
-    assert n_tc == 83                           # fc1 + 4 layers x 20 steps + pool + decode
+    imu = sb["imu"].cuda()
+    counts = {}
+    for persist in (1, 0, 3):                   # default; one launch per step; rnn_fast persistent as well
+        handle.set_option("tc_persist", persist)
+        n0 = handle.launch_count()
+        handle.imu_forward(imu)
+        counts[persist] = handle.launch_count() - n0
+    handle.set_option("tc_persist", 1)
+    # fc1 + pool + decode = 3, plus per H=512 layer: 20 step launches, or step 0 + one persistent launch for steps 1..19
+    assert counts == {0: 3 + 4 * 20, 1: 3 + 2 * 20 + 2 * 2, 3: 3 + 4 * 2}
 
 
 @pytest.mark.parametrize("mode", [0, 2])
