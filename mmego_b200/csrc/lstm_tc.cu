@@ -172,7 +172,7 @@ __device__ __forceinline__ void dep_wait(const unsigned* cnt, unsigned target, u
             unsigned e = 0;
             if (err) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(err) : "memory");
             if (e) break;
-            if (polls > (1 << 21)) {
+            if (polls > (1 << 23)) {      // several seconds: only a lost dependency, never a slow neighbour, ends here
                 if (err) atomicExch(err, 2u);
                 break;
             }
