@@ -898,8 +898,8 @@ bool tc_pack_layer(mmego_handle* h, const StateDict& sd, const std::string& pref
 }
 
 template <int NPASS, int NCTA, int BN, bool MUFU_CELL = (NPASS == 1)>
-void launch_step(int grid, cudaStream_t st, const CUtensorMap& mXhi, const CUtensorMap& mXlo, const CUtensorMap& mYhi,
-                 const CUtensorMap& mYlo, const CUtensorMap& mWhi, const CUtensorMap& mWlo, const StepParams& p) {
+cudaError_t launch_step(int grid, cudaStream_t st, const CUtensorMap& mXhi, const CUtensorMap& mXlo, const CUtensorMap& mYhi,
+                        const CUtensorMap& mYlo, const CUtensorMap& mWhi, const CUtensorMap& mWlo, const StepParams& p) {
     static bool attr_set[64] = {false};
     if (first_use_on_device(attr_set))
         cudaFuncSetAttribute(lstm_tc_step_kernel<NPASS, NCTA, BN, MUFU_CELL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -914,11 +914,21 @@ void launch_step(int grid, cudaStream_t st, const CUtensorMap& mXhi, const CUten
     attr[0].val.clusterDim.x = NCTA;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    int na = 1;
+    if (p.nsteps > 1) {
+        // items of this launch wait for each other: the grid must be co-resident as a whole.  A cooperative launch is
+        // placed all-or-nothing, so another stream's (or process's) kernels can never hold the SMs part of it needs.
+        attr[na].id = cudaLaunchAttributeCooperative;
+        attr[na].val.cooperative = 1;
+        ++na;
+    } else if (p.pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = p.pdl ? 2 : 1;
-    cudaLaunchKernelEx(&cfg, lstm_tc_step_kernel<NPASS, NCTA, BN, MUFU_CELL>, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, lstm_tc_step_kernel<NPASS, NCTA, BN, MUFU_CELL>, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p);
 }
 
 // One bidirectional layer: x planes [S][T][In] -> y planes [S][T][1024]; cstate [2][512][Spad] fp32 scratch.
@@ -985,10 +995,12 @@ int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const
         cudaMemsetAsync(h->tc_sync, 0, words * sizeof(unsigned), st);
         p.sync = h->tc_sync;
     }
+    bool use_persist = persist;
     for (int step = 0; step < T;) {
-        const int nsteps = (persist && step > 0) ? T - step : 1;
+        const int nsteps = (use_persist && step > 0) ? T - step : 1;
         p.step0 = step;
         p.nsteps = nsteps;
+        p.pdl = nsteps > 1 ? 0 : h->tc_pdl;      // the persistent launch is cooperative, not programmatic
         p.kb_rec = step > 0 ? kImuH / BK : 0;
         p.kb_chunk = (npass == 3 && chunk_opt > 0) ? chunk_opt : (p.kb_in + p.kb_rec);
         // with four TMEM buffers (BN = 128) the MMA thread has enough run-ahead without longer first chunks
@@ -997,11 +1009,20 @@ int tc_lstm_layer(mmego_handle* h, const TcLstmLayer& lw, const void* xhi, const
         // idle pairs, multiply their input K blocks and wait (in the TMA producer) only for the recurrent ones
         const long long items = (long long)total * nsteps;
         const int grid = (int)(items < slots ? items : slots) * ncta;
-        ++t_launches;
-#define MMEGO_STEP(NP, NC, BNV) launch_step<NP, NC, BNV>(grid, st, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p)
+        cudaError_t le;
+#define MMEGO_STEP(NP, NC, BNV) le = launch_step<NP, NC, BNV>(grid, st, mXhi, mXlo, mYhi, mYlo, mWhi, mWlo, p)
         if (npass == 3) { if (pair) MMEGO_STEP(3, 2, 256); else MMEGO_STEP(3, 1, 256); }
         else { if (pair) MMEGO_STEP(1, 2, 256); else MMEGO_STEP(1, 1, 256); }
 #undef MMEGO_STEP
+        if (le != cudaSuccess) {
+            cudaGetLastError();
+            if (nsteps > 1) {          // the device cannot place the whole grid at once: one launch per timestep instead
+                use_persist = false;
+                continue;
+            }
+            return -1;
+        }
+        ++t_launches;
         step += nsteps;
     }
     return 0;
