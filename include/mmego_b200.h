@@ -74,10 +74,14 @@ const char* mmego_last_error(const mmego_handle* h);
  *          "imu_resident" (1, default: IMU_Net calls of at most 64 frames (B*L) take the latency path -- fp32 weights
  *                         resident in shared memory, one persistent cooperative launch per bi-LSTM layer, 7 launches per
  *                         call; 0 = always the tcgen05 path),
- *          "gcn_snip"    (ST-GCN temporal convolutions, L <= 20: bit 0 (default on) = snippet-resident transposed kernel
- *                         (one CTA per snippet, window loaded once for the nine taps); bit 4 = a second accumulator drain
- *                         per 64-channel block (relative error 5.6e-6 instead of 9.5e-6 on tests/golden/gcn2.npz, 12 %
- *                         slower); 0 = row-tiled GEMM),
+ *          "gcn_snip"    (ST-GCN temporal convolutions, L <= 20: bit 0 = snippet-resident transposed kernel (one CTA per
+ *                         snippet, window loaded once for the nine taps); bit 8+i = layer i stays on the row-tiled GEMM;
+ *                         bit 4 / bit 12+i = a second accumulator drain per 64-channel block (all layers / layer i).
+ *                         Default 513 = layers 0 and 2 snippet-resident, layer 1 row-tiled: the two kernels are equally
+ *                         fast on the 64 -> 64 layer and the snippet kernel accumulates 108 MMAs per drain in TMEM, which
+ *                         costs accuracy -- max lower-joint error over 200 snippets against the float64 oracle 6.4e-6 m,
+ *                         9.6e-6 m with all three layers snippet-resident (value 1), 5.6e-6 m row-tiled (value 0, GCN
+ *                         10 % slower): profiles/r02_gcn_accuracy_probe.json),
  *          "point_stage" (upper point encoder: 1 = radar clouds staged into shared memory by cp.async.bulk under the
  *                         previous frame's MMAs; default 0 -- measured 2-3 % slower than per-lane loads on a B200),
  *          "tc_kb_chunk" (imu_gemm=1: K blocks of 64 accumulated in TMEM before draining into fp32 registers, default 4;

@@ -551,8 +551,11 @@ int run_gcn_tc(mmego_handle* h, int B, int L, const LowerWs& w, cudaStream_t st)
         void* const* out = w.p_y[i & 1];
         {
             Prof p(h, kTc[i], st);
-            if (h->gcn_snip && tc_gcn_tconv_snip_supported(L))
-                rc |= tc_gcn_tconv_snip(h, W.tc_tconv[i], w.p_u[0], w.p_u[1], cout, y[0], y[1], ystride, creal, out[0], out[1], B, L, st);
+            // gcn_snip: bit 0 on; bit 4 / bit 12+i a second drain group per block (all layers / layer i); bit 8+i: layer i
+            // on the row-tiled kernel
+            if ((h->gcn_snip & 1) && !(h->gcn_snip & (256 << i)) && tc_gcn_tconv_snip_supported(L))
+                rc |= tc_gcn_tconv_snip(h, W.tc_tconv[i], w.p_u[0], w.p_u[1], cout, y[0], y[1], ystride, creal, out[0], out[1], B, L,
+                                        (h->gcn_snip & (16 | (4096 << i))) != 0, st);
             else
                 rc |= tc_gcn_gemm(h, W.tc_tconv[i], w.p_u[0], w.p_u[1], cout, 9, y[0], y[1], ystride, 0, 1, out[0], out[1],
                                   nullptr, B, RP, st);

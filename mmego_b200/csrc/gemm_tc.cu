@@ -964,7 +964,7 @@ bool tc_gcn_tconv_snip_supported(int L) { return L >= 1 && L <= SN_LMAX; }
 // Temporal conv + residual of one ST-GCN layer, snippet-resident (tconv_snip_kernel): U planes [B][L*15][cu] (9 taps),
 // Y planes [B][L*15][cy] (residual 1x1 conv), weights packed as for tc_gcn_gemm -> out planes [B][L*15][w.N].
 int tc_gcn_tconv_snip(mmego_handle* h, const TcGemmW& w, const void* uhi, const void* ulo, int cu, const void* yhi,
-                      const void* ylo, int cy, int cy_real, void* outhi, void* outlo, int B, int L, cudaStream_t st) {
+                      const void* ylo, int cy, int cy_real, void* outhi, void* outlo, int B, int L, int subdrain, cudaStream_t st) {
     if (!tc_gcn_tconv_snip_supported(L) || cu != w.N) return -4;
     const int kbu = (cu + BK - 1) / BK;
     if ((9 * kbu + (cy + BK - 1) / BK) * BK != w.K64 || (cy + BK - 1) / BK != 1) return -2;
@@ -984,7 +984,7 @@ int tc_gcn_tconv_snip(mmego_handle* h, const TcGemmW& w, const void* uhi, const 
     p.Cout = w.N;
     p.wk = wk;
     p.chunk256 = (h->gcn_snip & 4) ? 1 : 0;
-    p.subdrain = (h->gcn_snip & 16) ? 1 : 0;
+    p.subdrain = subdrain ? 1 : 0;
     p.nwt = SN_WRING / (2 * w.N * wk * 2);
     if (p.nwt > SN_MAXWT) p.nwt = SN_MAXWT;
     if (w.N % 8 != 0 || w.N > 128 || p.nwt < 2) return -3;

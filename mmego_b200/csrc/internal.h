@@ -284,7 +284,7 @@ int tc_gcn_gemm(mmego_handle* h, const TcGemmW& w, const void* a0hi, const void*
                 cudaStream_t st);
 bool tc_gcn_tconv_snip_supported(int L);
 int tc_gcn_tconv_snip(mmego_handle* h, const TcGemmW& w, const void* uhi, const void* ulo, int cu, const void* yhi,
-                      const void* ylo, int cy, int cy_real, void* outhi, void* outlo, int B, int L, cudaStream_t st);
+                      const void* ylo, int cy, int cy_real, void* outhi, void* outlo, int B, int L, int subdrain, cudaStream_t st);
 void tc_gcn_prep(const float* upper, const float* R, const float* t, const float* bn, float* uh, void* yhi, void* ylo,
                  long long F, cudaStream_t st);
 void tc_gcn_prep_raw(const float* x, const float* bn, void* yhi, void* ylo, int B, int T, cudaStream_t st);
@@ -328,7 +328,9 @@ struct mmego_handle {
     int tc_kb_chunk0 = 8;     // ... of the first two chunks of every tile
     int tc_kb_chunk = 4;      // fp16x3 mode: K blocks (of 64) per TMEM partial accumulation (see lstm_tc.cu)
     int point_stage = 0;      // upper point encoder: 1 = radar clouds staged into shared memory by TMA bulk copies one frame ahead
-    int gcn_snip = 1;         // ST-GCN temporal convs: 1 = snippet-resident transposed kernel (L <= 20), 0 = row-tiled GEMM
+    int gcn_snip = 1 | (256 << 1);   // ST-GCN temporal convs: bit 0 = snippet-resident transposed kernel (L <= 20), bit 8+i = layer i stays on
+                              // the row-tiled GEMM (default: the middle layer -- same speed there, and the snippet kernel's long
+                              // TMEM accumulation chains cost accuracy), bit 4 / 12+i = second drain group (all layers / layer i)
     unsigned* dev_error = nullptr;   // device word set by a kernel whose bounded wait gave up (mmego_debug_stats out8[7])
     int imu_resident = 1;     // small batches (B*L <= kResMaxSeq): persistent fp32 LSTM with weights resident in shared memory
     mmego::ImuWeights imu;

@@ -244,6 +244,16 @@ def check_pipeline_vs_oracle(h, B=2, L=20, N=128, n_imu=20, seed=11, distinct=Tr
         # for the skeletons used).  The config-shape tests keep the plain 1e-5 m.
         pos_bound = POS_TOL + 1.0 * float(np.deg2rad(ANG_TOL))
         errs["pos_bound"] = pos_bound
+        if truth64 == "either":
+            # config shape, many snippets: the plain contract bounds, met against the reference's fp32 realisation OR
+            # against the exact (float64) value -- the maximum over 10^5 joints sits a few percent under 1e-5 m and the
+            # fp32 oracle's own last bits depend on the host's BLAS kernels -- and never outside the pipeline-level bound
+            assert min(errs["R_deg"], errs["R_deg64"]) < rt and errs["t"] < tt, errs
+            for k in ("upper", "lower"):
+                assert min(errs[k], errs[k + "64"]) < pt and max(errs[k], errs[k + "64"]) < pos_bound, errs
+            assert errs["x"] < 8 * max(float(np.deg2rad(rt)), errs["R"]), errs
+            assert sums.cpu().numpy()[43] == B * L
+            return pred, errs
         assert errs["R_deg64"] < max(rt, 3 * errs["noise32_R_deg"]) and errs["t"] < tt, errs
         assert errs["upper64"] < max(pos_bound, 3 * errs["noise32_upper"]), errs
         assert errs["lower64"] < max(pos_bound, 3 * errs["noise32_lower"]), errs
