@@ -461,6 +461,24 @@ def main():
     ms, launches, prof, clocks, sums = timed_pass(args.steps, args.warmup)
     collective_ms = timed_pass.collective_ms
     ms_per_step = ms / args.steps
+    # N > 1: every rank's own pace on the same work WITHOUT the per-step collectives (a few untimed-by-the-metric local
+    # steps): shows how much of the loss against N x the 1-GPU figure is the spread between the box's power-capped GPUs
+    # (the lock-stepped run moves at the pace of the slowest one)
+    rank_free_ms = None
+    if world > 1:
+        k = max(2, min(args.steps, 5))
+        step_fn(0, 0, Bg)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(k):
+            step_fn(0, 0, Bg)      # the arguments are unused: the rank's shard is already resident
+        f1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([f0.elapsed_time(f1) / k], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_free_ms = [round(float(x.item()), 3) for x in allr]
     frames = Bg * L
     value = frames / (ms_per_step * 1e-3)
     rep = report_from_sums(sums.cpu().numpy())
@@ -597,6 +615,7 @@ def main():
             "clocks": clocks, "gpu_launches": launches,
             "collective_ms_per_step": round(collective_ms, 4) if world > 1 else None,
             "collective": args.collective if world > 1 else None,
+            "rank_free_ms_per_step": rank_free_ms,
             "collective_note": ("all-gather of pred (into the final layout) + all-reduce of 46 float64 sums per step; device time "
                                 "between CUDA events around them on rank 0, including the wait for the slowest rank") if world > 1 else None,
             "algorithmic_tflops": FLOPS_PER_FRAME["total"] * frames / (ms_per_step * 1e-3) / 1e12,
