@@ -774,6 +774,10 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
         h->point_stage = value != 0;
         return MMEGO_OK;
     }
+    if (!strcmp(key, "gcn_w_res")) {
+        h->gcn_w_res = value != 0;
+        return MMEGO_OK;
+    }
     if (!strcmp(key, "gcn_snip")) {
         h->gcn_snip = (int)value;
         return MMEGO_OK;

@@ -60,6 +60,11 @@ struct GemmTcParams {
     __half* out_hi;          // planes [B][RP][N] (epilogue 0)
     __half* out_lo;
     float* out_f6;           // fp32 [B][N][RP] (epilogue 1), used when out_hi == nullptr
+    int stages, stage_bytes; // shared-memory ring: stages of stage_bytes (A tile pair [+ W tile pair])
+    int w_res;               // 1: the whole weight matrix (kb_total K blocks, both planes) is loaded ONCE per CTA into a
+                             // resident region behind the ring and the stages carry activations only -- the graph convs
+                             // and fcn were bound by L2 -> shared-memory traffic, a third of it the same weight tiles
+                             // re-loaded for every 128-row tile
 };
 
 template <int BN>
@@ -70,12 +75,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant_
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    constexpr int kMaxStages = 6;
+    const int ring_bytes = p.stages * p.stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ring_bytes);
     uint64_t* full = bars;
-    uint64_t* empty = bars + C::STAGES;
-    uint64_t* tfull = bars + 2 * C::STAGES;
+    uint64_t* empty = bars + kMaxStages;
+    uint64_t* tfull = bars + 2 * kMaxStages;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* wbar = tempty + 2;                       // resident weights have landed
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(wbar + 1);
+    uint8_t* wres = smem + ((ring_bytes + 256 + C::BIAS_BYTES + 1023) & ~1023);   // 1024-aligned: SWIZZLE_128B tiles
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.B * p.rtiles;
@@ -87,7 +96,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant_
         prefetch_tensormap(&mA0lo);
         prefetch_tensormap(&mWhi);
         prefetch_tensormap(&mWlo);
-        for (int s = 0; s < C::STAGES; ++s) {
+        for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
@@ -95,6 +104,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant_
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], kEpiWarps);
         }
+        mbar_init(wbar, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -104,7 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant_
     // bias table in shared memory: with rowmod > 0 (the graph conv's per-joint bias) every lane of an epilogue warp needs a
     // different table row, and reading it from global was a 15-sector gather per load that throttled the LSU
     // (ncu: lg_throttle 7.5, 2.6 M requests x 14.7 sectors on the N=128 graph conv)
-    float* sbias = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+    float* sbias = reinterpret_cast<float*>(smem + ring_bytes + 256);
     {
         const int rows = p.rowmod > 0 ? p.rowmod : 1;
         for (int i = threadIdx.x; i < rows * BN; i += kThreads) sbias[(i / BN) * C::BIAS_LD + (i % BN)] = p.bias[i];
@@ -121,12 +131,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            if (p.w_res && blockIdx.x < total_tiles) {
+                mbar_expect_tx(wbar, kb_total * 2 * C::W_TILE);
+                for (int kbi = 0; kbi < kb_total; ++kbi) {
+                    tma_load_2d(wres + kbi * 2 * C::W_TILE, &mWhi, wbar, kbi * BK, 0);
+                    tma_load_2d(wres + kbi * 2 * C::W_TILE + C::W_TILE, &mWlo, wbar, kbi * BK, 0);
+                }
+            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int b = tile / p.rtiles, r0 = (tile % p.rtiles) * BM;
                 for (int kbi = 0; kbi < kb_total; ++kbi) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-                    uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], p.w_res ? 2 * A_TILE : C::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * p.stage_bytes;
                     uint8_t* sw = sa + 2 * A_TILE;
                     if (kbi < kb_a0) {
                         const int seg = kbi / p.kb0, kb = kbi - seg * p.kb0;
@@ -138,9 +155,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant_
                         tma_load_3d(sa, &mA1hi, &full[stage], kb * BK, r0, b);
                         tma_load_3d(sa + A_TILE, &mA1lo, &full[stage], kb * BK, r0, b);
                     }
-                    tma_load_2d(sw, &mWhi, &full[stage], kbi * BK, 0);
-                    tma_load_2d(sw + C::W_TILE, &mWlo, &full[stage], kbi * BK, 0);
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (!p.w_res) {
+                        tma_load_2d(sw, &mWhi, &full[stage], kbi * BK, 0);
+                        tma_load_2d(sw + C::W_TILE, &mWlo, &full[stage], kbi * BK, 0);
+                    }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -152,6 +171,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             uint32_t cc = 0;
+            if (p.w_res && blockIdx.x < total_tiles) {
+                mbar_wait(wbar, 0);
+                tc_fence_after();
+            }
+            const uint32_t wres_u32 = smem_u32(wres);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 for (int c0 = 0; c0 < kb_total; c0 += p.kb_chunk, ++cc) {
                     const uint32_t buf = cc & 1, bph = (cc >> 1) & 1;
@@ -162,9 +186,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant_
                     for (int kb = c0; kb < c1; ++kb) {
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
-                        const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+                        const uint32_t a_hi = smem_u32(smem + stage * p.stage_bytes);
                         const uint32_t a_lo = a_hi + A_TILE;
-                        const uint32_t w_hi = a_hi + 2 * A_TILE;
+                        const uint32_t w_hi = p.w_res ? wres_u32 + kb * 2 * C::W_TILE : a_hi + 2 * A_TILE;
                         const uint32_t w_lo = w_hi + C::W_TILE;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
@@ -177,7 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0hi, const __grid_constant_
                             mma_f16_ss(d_tmem, da_hi, dw_hi, idesc, 1);
                         }
                         mma_commit(&empty[stage]);
-                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                     mma_commit(&tfull[buf]);
                 }
@@ -829,14 +853,33 @@ bool make_w_map(CUtensorMap* m, const void* base, int rows, int K) {
 
 template <int BN>
 void launch_gemm_tc(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l,
-                    const CUtensorMap& wh, const CUtensorMap& wl, const GemmTcParams& p, int sm_count, cudaStream_t st) {
-    static bool attr_set[64] = {false};
-    if (first_use_on_device(attr_set))
-        cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+                    const CUtensorMap& wh, const CUtensorMap& wl, GemmTcParams p, int w_res_opt, int sm_count, cudaStream_t st) {
+    using C = Cfg<BN>;
+    constexpr int kBudget = 208 * 1024;                 // ring + resident weights
+    const int kb_total = p.n0 * p.kb0 + p.kb1;
+    const int wres_bytes = kb_total * 2 * C::W_TILE;
+    // resident weights when they leave room for at least three activation-only stages
+    p.w_res = (w_res_opt && wres_bytes + 3 * 2 * A_TILE <= kBudget) ? 1 : 0;
+    if (p.w_res) {
+        p.stage_bytes = 2 * A_TILE;
+        p.stages = std::min(6, (kBudget - wres_bytes) / p.stage_bytes);
+    } else {
+        p.stage_bytes = C::STAGE_BYTES;
+        p.stages = C::STAGES;
+    }
+    const int smem = p.stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + C::BIAS_BYTES + 1024 /*W alignment*/ +
+                     (p.w_res ? wres_bytes : 0);
+    static int attr_bytes[64] = {0};
+    int d = 0;
+    cudaGetDevice(&d);
+    if (attr_bytes[d & 63] < smem) {
+        cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_bytes[d & 63] = smem;
+    }
     const int total = p.B * p.rtiles;
     const int grid = total < sm_count ? total : sm_count;
     ++t_launches;
-    gemm_tc_kernel<BN><<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(a0h, a0l, a1h, a1l, wh, wl, p);
+    gemm_tc_kernel<BN><<<grid, kThreads, smem, st>>>(a0h, a0l, a1h, a1l, wh, wl, p);
 }
 
 }  // namespace
@@ -928,9 +971,10 @@ int tc_gcn_gemm(mmego_handle* h, const TcGemmW& w, const void* a0hi, const void*
     if ((p.n0 * p.kb0 + p.kb1) * BK != w.K64) return -2;
     const CUtensorMap& wh = *reinterpret_cast<const CUtensorMap*>(&w.map_hi);
     const CUtensorMap& wl = *reinterpret_cast<const CUtensorMap*>(&w.map_lo);
-    if (w.N == 128) launch_gemm_tc<128>(m0h, m0l, m1h, m1l, wh, wl, p, h->sm_count, st);
-    else if (w.N == 64) launch_gemm_tc<64>(m0h, m0l, m1h, m1l, wh, wl, p, h->sm_count, st);
-    else if (w.N == 32) launch_gemm_tc<32>(m0h, m0l, m1h, m1l, wh, wl, p, h->sm_count, st);
+    const int wr = h->gcn_w_res;
+    if (w.N == 128) launch_gemm_tc<128>(m0h, m0l, m1h, m1l, wh, wl, p, wr, h->sm_count, st);
+    else if (w.N == 64) launch_gemm_tc<64>(m0h, m0l, m1h, m1l, wh, wl, p, wr, h->sm_count, st);
+    else if (w.N == 32) launch_gemm_tc<32>(m0h, m0l, m1h, m1l, wh, wl, p, wr, h->sm_count, st);
     else return -3;
     return 0;
 }

@@ -328,6 +328,7 @@ struct mmego_handle {
     int tc_kb_chunk0 = 8;     // ... of the first two chunks of every tile
     int tc_kb_chunk = 4;      // fp16x3 mode: K blocks (of 64) per TMEM partial accumulation (see lstm_tc.cu)
     int point_stage = 0;      // upper point encoder: 1 = radar clouds staged into shared memory by TMA bulk copies one frame ahead
+    int gcn_w_res = 1;        // row-tiled ST-GCN GEMMs: weights resident in shared memory when they fit next to >= 3 activation stages
     int gcn_snip = 1 | (256 << 1);   // ST-GCN temporal convs: bit 0 = snippet-resident transposed kernel (L <= 20), bit 8+i = layer i stays on
                               // the row-tiled GEMM (default: the middle layer -- same speed there, and the snippet kernel's long
                               // TMEM accumulation chains cost accuracy), bit 4 / 12+i = second drain group (all layers / layer i)
