@@ -311,7 +311,9 @@ def config1_record(dev):
         mm.eval_model()
         n = int(mm.data.shape[0])
         rec[key] = {"it_per_s": n / mm.seconds, "frames_per_s": n * 20 / mm.seconds, "ms_per_snippet": mm.seconds / n * 1e3,
-                    "what": f"full chain incl. IMU_Net (seeded stand-in weights), host tensors in, batch = {bs} snippet(s) per call"}
+                    "cuda_graph_replay": bool(mm.graphed),
+                    "what": f"full chain incl. IMU_Net (seeded stand-in weights), pinned host tensors in, batch = {bs} snippet(s) "
+                            "per call" + (", the step captured once as a CUDA graph and replayed per call" if mm.graphed else "")}
     return rec
 
 

@@ -310,7 +310,7 @@ int imu_chunk_forward(mmego_handle* h, const float* imu, float* R, float* t, lon
 // Small batches (B*L <= kResMaxSeq): fp32 throughout, persistent LSTM kernels with the gate weights resident in shared
 // memory (lstm_resident.cu).  7 launches per call instead of 83.
 struct ImuResWs {
-    float *u, *y0, *y1, *s, *z0, *z1, *cst;
+    float *u, *y0, *y1, *s, *z0, *z1, *cst, *gxs;
     unsigned* flags;
 };
 void plan_imu_res(Carver& c, long long B, int L, int n, ImuResWs& w) {
@@ -323,6 +323,9 @@ void plan_imu_res(Carver& c, long long B, int L, int n, ImuResWs& w) {
     w.z1 = c.f(S * 2 * kImuH);
     w.cst = c.f(2 * S * kImuH);
     w.flags = reinterpret_cast<unsigned*>(c.f(2 * (size_t)(n > L ? n : L) + 8));
+    const size_t gfast = S <= (size_t)kResPreMaxSeq ? resident_gx_floats((int)S, n) : 0;
+    const size_t gslow = B <= kResPreMaxSeq ? resident_gx_floats((int)B, L) : 0;
+    w.gxs = c.f(gfast > gslow ? gfast : gslow);
 }
 bool use_resident(const mmego_handle* h, long long B, int L) {
     return h->imu_resident && h->imu.res_ready && B * L <= kResMaxSeq && resident_supported(h->sm_count);
@@ -334,12 +337,13 @@ int imu_res_forward(mmego_handle* h, const float* imu, float* R, float* t, long 
     Prof p(h, "imu.resident", st);
     launch_res_fc1(imu, W.res_fc1.p, w.u, S * n, st);                                                            // Net/IMU_Net.py:79
     int rc = 0;
-    rc |= launch_lstm_resident(w.u, kImuH, w.y0, W.res_w[0].p, W.res_b[0].p, w.cst, w.flags, (int)S, n, st);      // :80
-    rc |= launch_lstm_resident(w.y0, 2 * kImuH, w.y1, W.res_w[1].p, W.res_b[1].p, w.cst, w.flags, (int)S, n, st);
+    float* const gxs = h->imu_res_pre ? w.gxs : nullptr;
+    rc |= launch_lstm_resident(w.u, kImuH, w.y0, W.res_w[0].p, W.res_b[0].p, w.cst, w.flags, gxs, (int)S, n, st);      // :80
+    rc |= launch_lstm_resident(w.y0, 2 * kImuH, w.y1, W.res_w[1].p, W.res_b[1].p, w.cst, w.flags, gxs, (int)S, n, st);
     tap(h, "imu.f", w.y1, (size_t)S * n * 2 * kImuH * 4, st);
     launch_imu_pool(w.y1, W.attn.p, w.s, S, n, st);                                                              // :82-83
-    rc |= launch_lstm_resident(w.s, 2 * kImuH, w.z0, W.res_w[2].p, W.res_b[2].p, w.cst, w.flags, (int)B, L, st);  // :85
-    rc |= launch_lstm_resident(w.z0, 2 * kImuH, w.z1, W.res_w[3].p, W.res_b[3].p, w.cst, w.flags, (int)B, L, st);
+    rc |= launch_lstm_resident(w.s, 2 * kImuH, w.z0, W.res_w[2].p, W.res_b[2].p, w.cst, w.flags, gxs, (int)B, L, st);  // :85
+    rc |= launch_lstm_resident(w.z0, 2 * kImuH, w.z1, W.res_w[3].p, W.res_b[3].p, w.cst, w.flags, gxs, (int)B, L, st);
     launch_imu_decode(w.z1, W.fc2.p, R, t, S, st);                                                               // :87-93
     if (rc) return fail(h, MMEGO_ECUDA, "imu_forward: launching the resident-weights LSTM kernel failed (%s)",
                         cudaGetErrorString(cudaGetLastError()));
@@ -780,6 +784,10 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
     }
     if (!strcmp(key, "gcn_snip")) {
         h->gcn_snip = (int)value;
+        return MMEGO_OK;
+    }
+    if (!strcmp(key, "imu_res_pre")) {
+        h->imu_res_pre = value != 0;
         return MMEGO_OK;
     }
     if (!strcmp(key, "imu_resident")) {

@@ -142,8 +142,10 @@ struct StateDict;
 void pack_resident_layer(const StateDict& sd, const std::string& prefix, int layer, int In, std::vector<float>& w,
                          std::vector<float>& bias);
 bool resident_supported(int sm_count);
+constexpr int kResPreMaxSeq = 4;     // up to this many sequences a layer's input projections are computed for all timesteps up front
+size_t resident_gx_floats(int S, int T);
 int launch_lstm_resident(const float* x, int In, float* y, const float* w, const float* bias, float* cstate,
-                         unsigned* flags, int S, int T, cudaStream_t st);
+                         unsigned* flags, float* gxs, int S, int T, cudaStream_t st);
 void launch_res_fc1(const float* imu, const float* w, float* u, long long rows, cudaStream_t st);
 
 // snippet builder (snippet.cu): device views of the packed raw cache (scripts/pack_sample_data.py)
@@ -333,6 +335,7 @@ struct mmego_handle {
                               // the row-tiled GEMM (default: the middle layer -- same speed there, and the snippet kernel's long
                               // TMEM accumulation chains cost accuracy), bit 4 / 12+i = second drain group (all layers / layer i)
     unsigned* dev_error = nullptr;   // device word set by a kernel whose bounded wait gave up (mmego_debug_stats out8[7])
+    int imu_res_pre = 1;      // latency path: input projections of all timesteps up front when a layer has <= kResPreMaxSeq sequences
     int imu_resident = 1;     // small batches (B*L <= kResMaxSeq): persistent fp32 LSTM with weights resident in shared memory
     mmego::ImuWeights imu;
     mmego::UpperWeights upper;

@@ -47,6 +47,7 @@ struct ResParams {
     float* cstate;         // [2][S][512]
     unsigned* flags;       // [2][T] arrival counters, zero at launch (null: no inter-CTA waiting, one step per launch)
     unsigned* error;       // set to 1 when a wait gave up
+    float* gxs;            // [128 CTAs][S][T][32] input projections of ALL timesteps (S <= 4 only, else null), see precompute_inputs
     int S, T, In, K;
     int t_begin, t_end;
 };
@@ -133,6 +134,42 @@ __device__ __forceinline__ void segment(const float* __restrict__ sw, float* __r
     copy_wait_prior<0>();
 }
 
+// S <= 4 sequences (rnn_slow at the reference's one snippet per call): a step's input half x_t W_ih^T would read the
+// CTA's whole W_ih slice (128 KB) from shared memory for ONE activation row, once per timestep and inside the lock-step
+// cycle of the 64 CTAs (signal -> input half -> recurrent half -> cell).  The timesteps of a sequence are independent
+// rows for that product, so it is done up front for all of them, 20 timesteps per pass through the 4 x 5 register tile
+// that rnn_fast uses for 20 sequences: W_ih is read T/20 times instead of T times, and the per-step cycle keeps only the
+// recurrent half.  gx [S][T][32] (this CTA's gate rows) lives in global scratch: written and read by this CTA only.
+__device__ __forceinline__ void precompute_inputs(const ResParams& p, const float* sw, float* abuf, float* gx) {
+    constexpr int SQ = 5, SP = 4 * SQ;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, rg = lane >> 2, sg = lane & 3;
+    for (int s = 0; s < p.S; ++s) {
+        for (int t0 = 0; t0 < p.T; t0 += SP) {
+            const int nrow = (p.T - t0) < SP ? (p.T - t0) : SP;
+            float acc[4][SQ];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int j = 0; j < SQ; ++j) acc[r][j] = 0.f;
+            segment<SQ>(sw, abuf, p.x + ((size_t)s * p.T + t0) * p.In, (size_t)p.In, nrow, 0, p.In, tid, acc);
+            float* red = abuf;                                   // [RW][SP][32]
+#pragma unroll
+            for (int j = 0; j < SQ; ++j)
+                *reinterpret_cast<float4*>(red + ((size_t)(warp * SP + sg * SQ + j)) * RR + 4 * rg) =
+                    make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+            __syncthreads();
+            for (int i = tid; i < nrow * RR; i += RT) {
+                const int sl = i / RR, col = i % RR;
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < RW; ++w) v += red[(w * SP + sl) * RR + col];
+                gx[((size_t)s * p.T + t0 + sl) * RR + col] = v;
+            }
+            __syncthreads();
+        }
+    }
+}
+
 template <int SQ>
 __device__ __forceinline__ void run_steps(const ResParams& p, float* sw, float* abuf, int dir, int ug) {
     constexpr int SP = 4 * SQ;
@@ -141,6 +178,11 @@ __device__ __forceinline__ void run_steps(const ResParams& p, float* sw, float* 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, rg = lane >> 2, sg = lane & 3;
     const int H2 = 2 * kImuH;
     const float* bsrc = p.bias + (dir * RGROUPS + ug) * RR;      // 32 floats, L1-resident
+    float* gx = nullptr;
+    if (SQ == 1 && p.gxs) {
+        gx = p.gxs + (size_t)blockIdx.x * p.S * p.T * RR;
+        if (p.t_begin == 0) precompute_inputs(p, sw, abuf, gx);  // (the emulator's later one-step launches find it in place)
+    }
     for (int t = p.t_begin; t < p.t_end; ++t) {
         const int tt = dir ? p.T - 1 - t : t, tp = dir ? tt + 1 : tt - 1;
         const int nblocks = (p.S + SP - 1) / SP;
@@ -153,7 +195,7 @@ __device__ __forceinline__ void run_steps(const ResParams& p, float* sw, float* 
 #pragma unroll
                 for (int j = 0; j < SQ; ++j) acc[r][j] = 0.f;
             // ---- input half: x_t W_ih^T (independent of the other CTAs; runs before the wait for h_{t-1}) ------------
-            segment<SQ>(sw, abuf, p.x + ((size_t)s0 * p.T + tt) * p.In, (size_t)p.T * p.In, nseq, 0, p.In, tid, acc);
+            if (!gx) segment<SQ>(sw, abuf, p.x + ((size_t)s0 * p.T + tt) * p.In, (size_t)p.T * p.In, nseq, 0, p.In, tid, acc);
             if (t > 0) {
                 if (!waited) {
                     // ---- wait for h_{t-1} of all 64 unit groups of this direction ------------------------------------
@@ -191,6 +233,7 @@ __device__ __forceinline__ void run_steps(const ResParams& p, float* sw, float* 
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     float v = bsrc[g * RU + u];
+                    if (gx) v += RES_LDCG(gx + ((size_t)s * p.T + tt) * RR + g * RU + u);
 #pragma unroll
                     for (int w = 0; w < RW; ++w) v += red[(w * SP + sl) * RR + g * RU + u];
                     pre[g] = v;
@@ -273,6 +316,7 @@ void pack_resident_layer(const StateDict& sd, const std::string& prefix, int lay
     }
 }
 
+size_t resident_gx_floats(int S, int T) { return (size_t)2 * RGROUPS * (S < kResPreMaxSeq ? S : kResPreMaxSeq) * T * RR; }
 size_t resident_smem_bytes(int K) { return ((size_t)K * RR + ABUF) * sizeof(float); }
 
 #ifdef MMEGO_EMUL
@@ -282,11 +326,12 @@ bool resident_supported(int sm_count) { return sm_count >= 2 * RGROUPS; }   // a
 #endif
 
 // One bidirectional H=512 layer over T steps for S <= kResMaxSeq sequences, fp32: x [S][T][In] -> y [S][T][1024].
-// cstate: [2][S][512] floats, flags: [2][T] unsigned + 1 error word (all scratch).  Returns 0, or -1 on a launch error.
+// cstate: [2][S][512] floats, flags: [2][T] unsigned + 1 error word, gxs: resident_gx_floats(S, T) floats or null (all scratch).  Returns 0, or -1 on a launch error.
 int launch_lstm_resident(const float* x, int In, float* y, const float* w, const float* bias, float* cstate,
-                         unsigned* flags, int S, int T, cudaStream_t st) {
+                         unsigned* flags, float* gxs, int S, int T, cudaStream_t st) {
     ResParams p{};
     p.x = x; p.y = y; p.w = w; p.bias = bias; p.cstate = cstate;
+    p.gxs = S <= kResPreMaxSeq ? gxs : nullptr;
     p.S = S; p.T = T; p.In = In; p.K = In + kImuH;
     const size_t smem = resident_smem_bytes(p.K);
     static int attr_bytes[64] = {0};

@@ -95,6 +95,65 @@ class MMEgoPipeline:
         return self.handle.infer_host(imu, data, skl, target, self.body_mode, b_offset, B_global, out_pred, out_sums)
 
 
+class GraphedStep:
+    """One pipeline step at a FIXED shape captured as a CUDA graph: the latency form of `MMEgoPipeline.forward` for the
+    reference's own operating point, one snippet per call (Processor/Test/Demo_test.py:61).  At that size a step is ~35
+    launches of a few microseconds each and the host side (argument checks, tensor-map encoding, the launches themselves)
+    is as long as the kernels; a replay is ONE driver call.  The caller copies a batch into the static input tensors
+    (`imu`, `data`, `skl`, `target`) and calls `replay()`; `sums` accumulates over replays exactly as in `forward`, and
+    `pred` is the static output (None when not wanted).  The graph holds the device addresses it was captured with: the
+    workspace is kept alive here, and `valid()` tells whether the handle still holds the weights it was captured with."""
+
+    def __init__(self, pipe: "MMEgoPipeline", B: int, L: int, N: int, n_imu: int, want_pred: bool = False,
+                 with_target: bool = True):
+        dev = pipe.device
+        pipe._sync()
+        self.pipe, self.handle = pipe, pipe.handle
+        self.imu = torch.zeros(B, L, n_imu, 15, device=dev)
+        self.data = torch.zeros(B, L, N, 6, device=dev)
+        self.skl = torch.zeros(B, 20, 3, device=dev)
+        self.target = torch.zeros(B, L, 21, 3, device=dev) if with_target else None
+        self.sums = torch.zeros(SUMS_LEN, dtype=torch.float64, device=dev) if with_target else None
+        self.pred = None
+        h = self.handle
+
+        def step():
+            return h.pipeline_forward(self.imu, self.data, self.skl, self.target, self.sums, pipe.body_mode, 0, None, None,
+                                      want_pred)
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):            # warm-up off the capture: lazy allocations, function attributes, workspace size
+            step()
+            step()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._ws = h._ws                         # the captured launches point into this workspace: keep it alive
+        self._owner = dict(h.weights_owner)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.pred = step()
+        if self.sums is not None:
+            self.sums.zero_()                    # the warm-up steps added to it
+        self.launches_per_replay = None
+
+    def valid(self) -> bool:
+        self.pipe._sync()
+        return all(self.handle.weights_owner.get(k) is v for k, v in self._owner.items()) and self.handle._ws is self._ws
+
+    def load(self, imu, data, skl, target=None):
+        """Copies one batch (host or device tensors of the captured shape) into the static inputs, asynchronously."""
+        self.imu.copy_(imu, non_blocking=True)
+        self.data.copy_(data, non_blocking=True)
+        self.skl.copy_(skl, non_blocking=True)
+        if target is not None and self.target is not None:
+            self.target.copy_(target, non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.pred
+
+
 def shard_bounds(B: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous split of the snippet dimension; the first B % world ranks take one extra snippet."""
     base, rem = divmod(B, world)

@@ -532,11 +532,46 @@ def test_eval_driver_uses_each_snippets_own_skeleton():
     assert P.maxerr(ref_mode, want[0:3]) > 1e-3      # the r % B replay with B = 3 really is a different result
 
 
-@pytest.mark.parametrize("B,L,n", [(1, 20, 20), (2, 20, 20), (3, 20, 20), (3, 5, 3), (1, 1, 1), (9, 7, 40)])
+@pytest.mark.parametrize("bs", [1, 2])
+def test_eval_driver_graph_replay_matches_eager_calls(bs):
+    """At the reference's own batch size (one snippet per call, Demo_test.py:61) the drop-in driver replays ONE captured
+    CUDA graph of the whole step per batch.  Same kernels, same inputs: the error sums must agree with the eager fused
+    call (up to the order of the float64 atomics) and with the three drop-in modules chained as Demo_test.py:111-123;
+    a ragged tail batch runs eagerly; edited weights invalidate the captured graph."""
+    from mmego_b200.Processor.Test.Demo_test import MMEgo
+    n = 49
+    reps, drivers = {}, {}
+    for name, kw in (("graph", dict(use_graph=True)), ("eager", dict(use_graph=False)), ("modules", dict(fused=False))):
+        m = MMEgo(batch_size=bs, imu_surrogate=False, quiet=True, **kw)
+        for f in ("data", "target", "skl", "imu"):
+            setattr(m, f, getattr(m, f)[:n])
+        m.eval_model()
+        m.eval_model()                                # the second pass re-uses the captured graph
+        assert m.graphed == (name == "graph")
+        reps[name], drivers[name] = m.report, m
+    assert reps["graph"]["frames"] == n * 20
+    for k in ("mpjpe_cm", "upper_cm", "lower_cm", "angle_deg"):
+        assert abs(reps["graph"][k] - reps["eager"][k]) <= 1e-9 * abs(reps["eager"][k]), k
+        assert abs(reps["graph"][k] - reps["modules"][k]) <= 1e-4, k
+    # in-place weight edit: both drivers must see it (the graph is re-captured: its packed weights may have moved)
+    for name in ("graph", "eager"):
+        m = drivers[name]
+        with torch.no_grad():
+            m.pipe.upper_net.get_parameter("module0.conv1.weight").mul_(1.5)
+        m.eval_model()
+        reps[name + "2"] = m.report
+    assert abs(reps["graph2"]["mpjpe_cm"] - reps["eager2"]["mpjpe_cm"]) <= 1e-9 * reps["eager2"]["mpjpe_cm"]
+    assert abs(reps["graph2"]["mpjpe_cm"] - reps["graph"]["mpjpe_cm"]) > 1e-3
+
+
+@pytest.mark.parametrize("B,L,n", [(1, 20, 20), (2, 20, 20), (3, 20, 20), (3, 5, 3), (1, 1, 1), (9, 7, 40), (1, 30, 25),
+                                   (1, 2, 40), (4, 16, 5)])
 def test_imu_latency_path(handle, handle_latency, B, L, n):
     """Small batches (the reference's own setting is ONE snippet per call, Demo_test.py:61) run IMU_Net on persistent fp32
     kernels with the gate weights resident in shared memory: 7 launches instead of 83, exact fp32 (so it sits at the fp32
-    oracle's own noise, far inside the tolerance), and it agrees with the tensor-core throughput path."""
+    oracle's own noise, far inside the tolerance), and it agrees with the tensor-core throughput path.  Layers with <= 4
+    sequences (rnn_slow at B <= 4; rnn_fast at B*L <= 4) take their input projections for all timesteps up front, 20
+    timesteps per pass: (1, 30, 25) and (1, 2, 40) have more than one pass."""
     sb = P.O.synth_batch(B, L=L, N=64, n_imu=n, seed=40 + B)
     imu = sb["imu"].cuda()
     n0 = handle_latency.launch_count()
