@@ -71,9 +71,17 @@ const char* mmego_last_error(const mmego_handle* h);
  *          "head_gemm"   (fully connected heads: 1 = one fused mma.sync kernel per head, default; 0 = fp32 FFMA GEMMs),
  *          "host_chunk"  (mmego_infer_host: snippets per stage of its H2D / compute / D2H pipeline, default 2048; the
  *                         first stage is an eighth of that so the un-overlappable first copy stays short),
- *          "imu_resident" (1, default: IMU_Net calls of at most 64 frames (B*L) take the latency path -- fp32 weights
- *                         resident in shared memory, one persistent cooperative launch per bi-LSTM layer, 7 launches per
- *                         call; 0 = always the tcgen05 path),
+ *          "imu_resident" (1, default: IMU_Net calls of at most "imu_res_max_seq" frames (B*L; default 80 = the measured
+ *                         break-even, B <= 4 at L = 20) take the latency path -- gate weights resident in shared memory,
+ *                         one persistent cooperative launch per bi-LSTM layer, 7 launches per call; 0 = always the
+ *                         tcgen05 path),
+ *          "imu_res_tc"  (latency path, 1 default: layers with more than 4 sequences (rnn_fast) multiply on mma.sync with
+ *                         fp16 hi/lo split operands and fp32 accumulation, like every other GEMM of the library; 0 = exact
+ *                         fp32 FMAs, 1.8x slower per step),
+ *          "imu_res_pre" (latency path, 1 default: layers with at most 4 sequences (rnn_slow) take their input
+ *                         projections for all timesteps up front; 0 = inside every timestep),
+ *          "gcn_w_res"   (row-tiled ST-GCN GEMMs, 1 default: the weight matrix is loaded once per CTA and stays in shared
+ *                         memory next to the activation ring when it fits),
  *          "gcn_snip"    (ST-GCN temporal convolutions, L <= 20: bit 0 = snippet-resident transposed kernel (one CTA per
  *                         snippet, window loaded once for the nine taps); bit 8+i = layer i stays on the row-tiled GEMM;
  *                         bit 4 / bit 12+i = a second accumulator drain per 64-channel block (all layers / layer i).

@@ -136,16 +136,18 @@ void launch_transform2r(const float* pts, const float* R, const float* t, float*
                         cudaStream_t st);
 
 // small-batch latency path of IMU_Net (lstm_resident.cu): fp32, gate weights resident in shared memory across timesteps
-constexpr int kResMaxSeq = 64;       // B*L up to which the resident path is taken (B <= 3 at L = 20; measured break-even with the
-                                     // tcgen05 path: B = 4, profiles/r02_latency_path.txt)
+constexpr int kResMaxSeq = 80;       // B*L up to which the resident path is taken (B <= 4 at L = 20; measured break-even with the
+                                     // tcgen05 path: B = 5, profiles/r02_latency_path.txt); run-time: option imu_res_max_seq
 struct StateDict;
 void pack_resident_layer(const StateDict& sd, const std::string& prefix, int layer, int In, std::vector<float>& w,
                          std::vector<float>& bias);
 bool resident_supported(int sm_count);
 constexpr int kResPreMaxSeq = 4;     // up to this many sequences a layer's input projections are computed for all timesteps up front
 size_t resident_gx_floats(int S, int T);
-int launch_lstm_resident(const float* x, int In, float* y, const float* w, const float* bias, float* cstate,
-                         unsigned* flags, float* gxs, int S, int T, cudaStream_t st);
+void pack_resident_layer_tc(const StateDict& sd, const std::string& prefix, int layer, int In, std::vector<float>& w,
+                            std::vector<float>& scale);
+int launch_lstm_resident(const float* x, int In, float* y, const float* w, const float* wscale, const float* bias,
+                         float* cstate, unsigned* flags, float* gxs, int S, int T, cudaStream_t st);
 void launch_res_fc1(const float* imu, const float* w, float* u, long long rows, cudaStream_t st);
 
 // snippet builder (snippet.cu): device views of the packed raw cache (scripts/pack_sample_data.py)
@@ -226,6 +228,7 @@ struct ImuWeights {
     // latency path (lstm_resident.cu): fp32 k-major slices per (direction, 8-unit group); order fast l0, l1, slow l0, l1
     bool res_ready = false;
     DevBuf res_w[4], res_b[4];
+    DevBuf res_wtc[2], res_stc[2];   // rnn_fast layers as mma.sync fragments + per-slice scales (tensor-core form of the latency path)
     DevBuf res_fc1;    // [512][15] + [512]
 };
 struct UpperWeights {
@@ -335,6 +338,8 @@ struct mmego_handle {
                               // the row-tiled GEMM (default: the middle layer -- same speed there, and the snippet kernel's long
                               // TMEM accumulation chains cost accuracy), bit 4 / 12+i = second drain group (all layers / layer i)
     unsigned* dev_error = nullptr;   // device word set by a kernel whose bounded wait gave up (mmego_debug_stats out8[7])
+    int imu_res_max_seq = mmego::kResMaxSeq;   // B*L up to which IMU_Net takes the latency path
+    int imu_res_tc = 1;       // latency path: layers with more than kResPreMaxSeq sequences (rnn_fast) on mma.sync (fp16 hi/lo split, fp32 accumulate); 0 = exact fp32 FMAs
     int imu_res_pre = 1;      // latency path: input projections of all timesteps up front when a layer has <= kResPreMaxSeq sequences
     int imu_resident = 1;     // small batches (B*L <= kResMaxSeq): persistent fp32 LSTM with weights resident in shared memory
     mmego::ImuWeights imu;

@@ -4,7 +4,10 @@
 // launches streaming the 92 MB of weights through 16 CTA pairs (2.1 ms per snippet).
 //
 // Here one PERSISTENT kernel per bidirectional layer keeps the gate weights resident in shared memory for all
-// timesteps -- in exact fp32:
+// timesteps.  Two forms of the per-step product share the protocol below: exact fp32 FMAs (described first; used for
+// layers with <= 4 sequences, i.e. rnn_slow, where the product is negligible next to the inter-CTA exchange) and mma.sync
+// with fp16 hi/lo split operands (segment_tc / run_steps_tc; rnn_fast's 20 sequences per snippet, where the fp32 form
+// is bound by the shared-memory pipe: 11.9 -> 6.7 us per step):
 //   * 128 CTAs = 2 directions x 64 groups of 8 hidden units; a CTA owns the 32 gate rows (i,f,g,o of its 8 units) over
 //     the full K = In + 512: 128 / 192 KB of shared memory, loaded once per launch.
 //   * per timestep a warp's lanes are the 32 gate rows, warps split the (sequence group, K slice) items; partial sums
@@ -15,9 +18,10 @@
 //     other CTAs and runs before the wait, hiding the exchange latency.
 //   * launched with cudaLaunchCooperativeKernel (all CTAs co-resident, or the launch fails); the wait gives up after a
 //     bounded number of polls and raises a flag instead of hanging the GPU.
-// Everything around it (fc1, attention pooling, fc2 + 6D decode) is fp32 as well, so this path is the exact-fp32
-// evaluation of IMU_Net; the host picks it when B*L <= kResMaxSeq.
+// Everything around it (fc1, attention pooling, fc2 + 6D decode) is fp32; with imu_res_tc = 0 the whole path is the
+// exact-fp32 evaluation of IMU_Net.  The host picks this path when B*L <= imu_res_max_seq (kResMaxSeq).
 #include "internal.h"
+#include "mma_frag.cuh"
 #include "pack.h"
 #ifndef MMEGO_EMUL
 #include <cuda_pipeline.h>
@@ -42,7 +46,8 @@ constexpr int SBLK = 20;                 // sequences per block of the K loop (4
 struct ResParams {
     const float* x;        // [S][T][In]
     float* y;              // [S][T][1024]  (fwd -> 0..511, bwd -> 512..1023); also the recurrent operand
-    const float* w;        // [2][64][K][32]  k-major slices, col = gate*8 + unit
+    const float* w;        // [2][64][K][32]  k-major slices, col = gate*8 + unit; tensor-core form: [2][64][K/16][4][32] uint4 B fragments
+    const float* wscale;   // tensor-core form: [2][64] output scale of a slice's fragments (pack_mma_weight), else null
     const float* bias;     // [2][64][32]     b_ih + b_hh
     float* cstate;         // [2][S][512]
     unsigned* flags;       // [2][T] arrival counters, zero at launch (null: no inter-CTA waiting, one step per launch)
@@ -130,6 +135,66 @@ __device__ __forceinline__ void segment(const float* __restrict__ sw, float* __r
             }
         }
         __syncthreads();                               // buffer c % 3 is refilled by the issue of the next iteration
+    }
+    copy_wait_prior<0>();
+}
+
+// ---- tensor-core form of `segment` (layers with more than kResPreMaxSeq sequences, i.e. rnn_fast) ---------------------
+// The fp32 FMA form above is bound by the shared-memory pipe (9 LDS.128 per 80 FMAs and lane); here the same chunk
+// (128 k x <= 20 sequences, staged by the same cp.async ring) feeds mma.sync m16n8k16 with fp16 hi/lo split operands and
+// fp32 accumulation (mma_frag.cuh, the scheme of every other GEMM of the library): the CTA's 32 gate rows are four
+// n-tiles (one per gate), the sequences one or two m-tiles, a warp owns ONE 16-k step of every chunk and keeps its
+// partial sums for the whole step (input half + recurrent half); per k-step 6 LDS.64 of activations + 4 LDS.128 of
+// weight fragments for 24 MMAs.  Row stride 136 floats keeps the half-warps' 64-bit reads conflict-free.
+constexpr int KROWT = KC + 8;
+static_assert(NBUF * SBLK * KROWT * 4 <= 33 * 1024, "activation ring of the tensor-core form");
+constexpr int ABUF_TC = NBUF * SBLK * KROWT;
+
+template <int MT>
+__device__ __forceinline__ void segment_tc(const uint4* __restrict__ wf, float* __restrict__ abuf, const float* __restrict__ src,
+                                           size_t stride, int nseq, int ks0, int len, int tid, float (&big)[MT][4][4],
+                                           float (&small)[MT][4][4]) {
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int nchunk = len / KC;
+    auto issue = [&](int c) {
+        if (c < nchunk) {
+            float* buf = abuf + (c % NBUF) * (SBLK * KROWT);
+            for (int i = tid; i < nseq * (KC / 4); i += RT) {
+                const int sq = i / (KC / 4), kq = i % (KC / 4);
+                copy16_async(buf + sq * KROWT + 4 * kq, src + (size_t)sq * stride + c * KC + 4 * kq);
+            }
+        }
+        copy_commit();
+    };
+    issue(0);
+    issue(1);
+    for (int c = 0; c < nchunk; ++c) {
+        issue(c + 2);
+        copy_wait_prior<2>();
+        __syncthreads();
+        const float* buf = abuf + (c % NBUF) * (SBLK * KROWT) + 16 * warp + 2 * t;      // this warp's k-step of the chunk
+        uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            const int r0 = 16 * m + g, r1 = r0 + 8;
+            const float2 z = make_float2(0.f, 0.f);
+            const float2 v0 = r0 < nseq ? *reinterpret_cast<const float2*>(buf + r0 * KROWT) : z;
+            const float2 v1 = r1 < nseq ? *reinterpret_cast<const float2*>(buf + r1 * KROWT) : z;
+            const float2 v2 = r0 < nseq ? *reinterpret_cast<const float2*>(buf + r0 * KROWT + 8) : z;
+            const float2 v3 = r1 < nseq ? *reinterpret_cast<const float2*>(buf + r1 * KROWT + 8) : z;
+            frag::split2(v0.x, v0.y, ah[m][0], al[m][0]);
+            frag::split2(v1.x, v1.y, ah[m][1], al[m][1]);
+            frag::split2(v2.x, v2.y, ah[m][2], al[m][2]);
+            frag::split2(v3.x, v3.y, ah[m][3], al[m][3]);
+        }
+        const uint4* wk = wf + (size_t)(ks0 + c * (KC / 16) + warp) * 4 * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 b = wk[j * 32];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) frag::mma3(big[m][j], small[m][j], ah[m], al[m], b);
+        }
+        __syncthreads();
     }
     copy_wait_prior<0>();
 }
@@ -253,6 +318,93 @@ __device__ __forceinline__ void run_steps(const ResParams& p, float* sw, float* 
     }
 }
 
+// The timestep loop of the tensor-core form: same protocol as run_steps (input half before the wait for h_{t-1}, cell
+// update by one thread per (sequence, unit), one arrival per CTA and step), blocks of up to 20 sequences.
+template <int MT>
+__device__ __forceinline__ void run_steps_tc(const ResParams& p, const uint4* wf, float* abuf, int dir, int ug) {
+    constexpr int SP = SBLK;
+    static_assert(RW * SP * RR <= ABUF_TC, "partial-sum buffer");
+    static_assert(RW * 16 == KC, "one 16-k step of a chunk per warp");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+    const int H2 = 2 * kImuH;
+    const float* bsrc = p.bias + (dir * RGROUPS + ug) * RR;
+    const float os = p.wscale[dir * RGROUPS + ug];
+    for (int t = p.t_begin; t < p.t_end; ++t) {
+        const int tt = dir ? p.T - 1 - t : t, tp = dir ? tt + 1 : tt - 1;
+        const int nblocks = (p.S + SP - 1) / SP;
+        bool waited = t == 0;
+        for (int blk = 0; blk < nblocks; ++blk) {
+            const int s0 = blk * SP, nseq = (p.S - s0) < SP ? (p.S - s0) : SP;
+            float big[MT][4][4], small[MT][4][4];
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) big[m][j][i] = small[m][j][i] = 0.f;
+            segment_tc<MT>(wf, abuf, p.x + ((size_t)s0 * p.T + tt) * p.In, (size_t)p.T * p.In, nseq, 0, p.In, tid, big, small);
+            if (t > 0) {
+                if (!waited) {
+                    if (p.flags && tid == 0) {
+                        volatile unsigned* f = p.flags + dir * p.T + (t - 1);
+                        unsigned polls = 0;
+                        while (*f < (unsigned)RGROUPS) {
+#ifndef MMEGO_EMUL
+                            __nanosleep(20);
+#endif
+                            if (++polls > (1u << 22)) {
+                                *p.error = 1u;
+                                break;
+                            }
+                        }
+                        __threadfence();
+                    }
+                    __syncthreads();
+                    waited = true;
+                }
+                segment_tc<MT>(wf, abuf, p.y + ((size_t)s0 * p.T + tp) * H2 + dir * kImuH, (size_t)p.T * H2, nseq, p.In / 16,
+                               kImuH, tid, big, small);
+            }
+            // cross-warp sum of the k-steps: C fragment (rows g / g+8 of m-tile m, columns 2tq, 2tq+1 of gate j) -> [warp][sequence][32]
+            float* red = abuf;
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r0 = 16 * m + g, r1 = r0 + 8;
+                    if (r0 < nseq)
+                        *reinterpret_cast<float2*>(red + ((size_t)(warp * SP + r0)) * RR + j * RU + 2 * tq) =
+                            make_float2(big[m][j][0] + small[m][j][0], big[m][j][1] + small[m][j][1]);
+                    if (r1 < nseq)
+                        *reinterpret_cast<float2*>(red + ((size_t)(warp * SP + r1)) * RR + j * RU + 2 * tq) =
+                            make_float2(big[m][j][2] + small[m][j][2], big[m][j][3] + small[m][j][3]);
+                }
+            __syncthreads();
+            for (int i = tid; i < nseq * RU; i += RT) {
+                const int sl = i / RU, u = i % RU, s = s0 + sl;
+                float pre[4];
+#pragma unroll
+                for (int gt = 0; gt < 4; ++gt) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int w = 0; w < RW; ++w) v += red[(w * SP + sl) * RR + gt * RU + u];
+                    pre[gt] = fmaf(v, os, bsrc[gt * RU + u]);
+                }
+                const float gi = sigm(pre[0]), gf = sigm(pre[1]), gg = tanhf(pre[2]), go = sigm(pre[3]);
+                float* cp = p.cstate + ((size_t)dir * p.S + s) * kImuH + ug * RU + u;
+                const float cprev = t > 0 ? *cp : 0.f;
+                const float cn = gf * cprev + gi * gg;
+                *cp = cn;
+                p.y[((size_t)s * p.T + tt) * H2 + dir * kImuH + ug * RU + u] = go * tanhf(cn);
+            }
+            __syncthreads();
+        }
+        __threadfence();
+        __syncthreads();
+        if (p.flags && tid == 0) atomicAdd(p.flags + dir * p.T + t, 1u);
+    }
+}
+
 __global__ void __launch_bounds__(RT, 1) lstm_resident_kernel(const ResParams p) {
     MMEGO_DYN_SMEM(float, sm);
     float* sw = sm;                                    // [K][32]
@@ -265,6 +417,11 @@ __global__ void __launch_bounds__(RT, 1) lstm_resident_kernel(const ResParams p)
         for (int i = tid; i < p.K * RR / 4; i += RT) dst[i] = __ldg(src + i);
     }
     __syncthreads();
+    if (p.wscale) {        // tensor-core form: sw holds B fragments
+        if (p.S <= 16) run_steps_tc<1>(p, reinterpret_cast<const uint4*>(sw), abuf, dir, ug);
+        else run_steps_tc<2>(p, reinterpret_cast<const uint4*>(sw), abuf, dir, ug);
+        return;
+    }
     // register tile = 4 gate rows x SQ sequences per lane; a block of the K loop covers 4 SQ sequences
     if (p.S <= 4) run_steps<1>(p, sw, abuf, dir, ug);
     else if (p.S <= 8) run_steps<2>(p, sw, abuf, dir, ug);
@@ -316,8 +473,37 @@ void pack_resident_layer(const StateDict& sd, const std::string& prefix, int lay
     }
 }
 
+// Tensor-core form of the same slices: per (direction, group) the [32 rows][K = In + 512] matrix [W_ih | W_hh] as mma.sync
+// B fragments (n-tile = gate, k-steps in K order), ONE scale per slice (returned in `scale`), so both halves of a step
+// share their accumulators.
+void pack_resident_layer_tc(const StateDict& sd, const std::string& prefix, int layer, int In, std::vector<float>& w,
+                            std::vector<float>& scale) {
+    const int H = kImuH, K = In + H;
+    w.assign((size_t)2 * RGROUPS * K * RR, 0.f);
+    scale.assign((size_t)2 * RGROUPS, 1.f);
+    const char* sfx[2] = {"", "_reverse"};
+    std::vector<float> slice((size_t)RR * K);
+    std::vector<int> kmap(K), nmap(RR);
+    for (int k = 0; k < K; ++k) kmap[k] = k;
+    for (int n = 0; n < RR; ++n) nmap[n] = n;
+    for (int d = 0; d < 2; ++d) {
+        const std::string k = "l" + std::to_string(layer) + sfx[d];
+        const float* wih = sd.get(prefix + "weight_ih_" + k, (long long)4 * H * In);
+        const float* whh = sd.get(prefix + "weight_hh_" + k, (long long)4 * H * H);
+        for (int ug = 0; ug < RGROUPS; ++ug) {
+            for (int col = 0; col < RR; ++col) {
+                const int r = (col / RU) * H + ug * RU + col % RU;
+                for (int kk = 0; kk < In; ++kk) slice[(size_t)col * K + kk] = wih[(size_t)r * In + kk];
+                for (int kk = 0; kk < H; ++kk) slice[(size_t)col * K + In + kk] = whh[(size_t)r * H + kk];
+            }
+            scale[(size_t)d * RGROUPS + ug] =
+                pack_mma_weight(slice.data(), K, kmap, nmap, &w[((size_t)d * RGROUPS + ug) * K * RR]);
+        }
+    }
+}
+
 size_t resident_gx_floats(int S, int T) { return (size_t)2 * RGROUPS * (S < kResPreMaxSeq ? S : kResPreMaxSeq) * T * RR; }
-size_t resident_smem_bytes(int K) { return ((size_t)K * RR + ABUF) * sizeof(float); }
+size_t resident_smem_bytes(int K) { return ((size_t)K * RR + (ABUF_TC > ABUF ? ABUF_TC : ABUF)) * sizeof(float); }
 
 #ifdef MMEGO_EMUL
 bool resident_supported(int) { return true; }          // the emulator runs one timestep per launch: no co-residency needed
@@ -326,11 +512,12 @@ bool resident_supported(int sm_count) { return sm_count >= 2 * RGROUPS; }   // a
 #endif
 
 // One bidirectional H=512 layer over T steps for S <= kResMaxSeq sequences, fp32: x [S][T][In] -> y [S][T][1024].
+// w / wscale: the fp32 slices of pack_resident_layer and null, or the fragments and scales of pack_resident_layer_tc.
 // cstate: [2][S][512] floats, flags: [2][T] unsigned + 1 error word, gxs: resident_gx_floats(S, T) floats or null (all scratch).  Returns 0, or -1 on a launch error.
-int launch_lstm_resident(const float* x, int In, float* y, const float* w, const float* bias, float* cstate,
-                         unsigned* flags, float* gxs, int S, int T, cudaStream_t st) {
+int launch_lstm_resident(const float* x, int In, float* y, const float* w, const float* wscale, const float* bias,
+                         float* cstate, unsigned* flags, float* gxs, int S, int T, cudaStream_t st) {
     ResParams p{};
-    p.x = x; p.y = y; p.w = w; p.bias = bias; p.cstate = cstate;
+    p.x = x; p.y = y; p.w = w; p.wscale = wscale; p.bias = bias; p.cstate = cstate;
     p.gxs = S <= kResPreMaxSeq ? gxs : nullptr;
     p.S = S; p.T = T; p.In = In; p.K = In + kImuH;
     const size_t smem = resident_smem_bytes(p.K);

@@ -27,7 +27,7 @@ def handle():
 
 @pytest.fixture(scope="module")
 def handle_latency():
-    h = P.make_handle()                 # library defaults: B*L <= 64 sequences -> resident-weights fp32 LSTM kernels
+    h = P.make_handle()                 # library defaults: B*L <= 80 sequences -> resident-weights LSTM kernels (latency path)
     yield h
     h.close()
 
@@ -567,9 +567,10 @@ def test_eval_driver_graph_replay_matches_eager_calls(bs):
 @pytest.mark.parametrize("B,L,n", [(1, 20, 20), (2, 20, 20), (3, 20, 20), (3, 5, 3), (1, 1, 1), (9, 7, 40), (1, 30, 25),
                                    (1, 2, 40), (4, 16, 5)])
 def test_imu_latency_path(handle, handle_latency, B, L, n):
-    """Small batches (the reference's own setting is ONE snippet per call, Demo_test.py:61) run IMU_Net on persistent fp32
-    kernels with the gate weights resident in shared memory: 7 launches instead of 83, exact fp32 (so it sits at the fp32
-    oracle's own noise, far inside the tolerance), and it agrees with the tensor-core throughput path.  Layers with <= 4
+    """Small batches (the reference's own setting is ONE snippet per call, Demo_test.py:61) run IMU_Net on persistent
+    kernels with the gate weights resident in shared memory: 7 launches instead of 83; rnn_fast on mma.sync fp16 hi/lo
+    split products with short accumulation chains, rnn_slow in exact fp32 (so it sits at the fp32 oracle's own noise, far
+    inside the tolerance), and it agrees with the tcgen05 throughput path; the exact-fp32 form (imu_res_tc = 0) as well.  Layers with <= 4
     sequences (rnn_slow at B <= 4; rnn_fast at B*L <= 4) take their input projections for all timesteps up front, 20
     timesteps per pass: (1, 30, 25) and (1, 2, 40) have more than one pass."""
     sb = P.O.synth_batch(B, L=L, N=64, n_imu=n, seed=40 + B)
@@ -586,6 +587,13 @@ def test_imu_latency_path(handle, handle_latency, B, L, n):
           f"fp32 oracle {P.rot_angle_deg(Rr, R64):.2e} deg")
     assert e_lat < P.ANG_TOL / 2 and P.maxerr(t, tr) < P.POS_TOL / 10
     assert P.rot_angle_deg(R, Rt) < 2 * P.ANG_TOL and P.maxerr(t, tt) < P.POS_TOL
+    handle_latency.set_option("imu_res_tc", 0)               # exact fp32 FMAs in every layer
+    try:
+        R32, t32 = handle_latency.imu_forward(imu)
+    finally:
+        handle_latency.set_option("imu_res_tc", 1)
+    assert P.rot_angle_deg(R32, R64) < P.ANG_TOL / 2 and P.maxerr(t32, tr) < P.POS_TOL / 10
+    assert P.rot_angle_deg(R32, R) < P.ANG_TOL / 2
 
 
 def test_latency_path_whole_pipeline_batch1(handle_latency):
