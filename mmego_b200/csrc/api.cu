@@ -312,6 +312,7 @@ int imu_chunk_forward(mmego_handle* h, const float* imu, float* R, float* t, lon
 struct ImuResWs {
     float *u, *y0, *y1, *s, *z0, *z1, *cst, *gxs;
     unsigned* flags;
+    unsigned long long* xchg;
 };
 void plan_imu_res(Carver& c, long long B, int L, int n, ImuResWs& w) {
     const size_t S = (size_t)B * L;
@@ -326,6 +327,7 @@ void plan_imu_res(Carver& c, long long B, int L, int n, ImuResWs& w) {
     const size_t gfast = S <= (size_t)kResPreMaxSeq ? resident_gx_floats((int)S, n) : 0;
     const size_t gslow = B <= kResPreMaxSeq ? resident_gx_floats((int)B, L) : 0;
     w.gxs = c.f(gfast > gslow ? gfast : gslow);
+    w.xchg = reinterpret_cast<unsigned long long*>(c.f(2 * resident_xchg_words((int)S)));       // S >= B
 }
 bool use_resident(const mmego_handle* h, long long B, int L) {
     return h->imu_resident && h->imu.res_ready && B * L <= h->imu_res_max_seq && resident_supported(h->sm_count);
@@ -338,16 +340,17 @@ int imu_res_forward(mmego_handle* h, const float* imu, float* R, float* t, long 
     launch_res_fc1(imu, W.res_fc1.p, w.u, S * n, st);                                                            // Net/IMU_Net.py:79
     int rc = 0;
     float* const gxs = h->imu_res_pre ? w.gxs : nullptr;
+    unsigned long long* const xc = h->imu_res_xchg ? w.xchg : nullptr;
     // rnn_fast (S = B*L sequences): tensor-core form above kResPreMaxSeq sequences, where the fp32 form is shared-memory bound
     const bool tc = h->imu_res_tc && S > kResPreMaxSeq && W.res_wtc[0].p && W.res_wtc[1].p;
     rc |= launch_lstm_resident(w.u, kImuH, w.y0, tc ? W.res_wtc[0].p : W.res_w[0].p, tc ? W.res_stc[0].p : nullptr,
-                               W.res_b[0].p, w.cst, w.flags, gxs, (int)S, n, st);                                    // :80
+                               W.res_b[0].p, w.cst, w.flags, gxs, xc, h->imu_res_direct, (int)S, n, st);                                    // :80
     rc |= launch_lstm_resident(w.y0, 2 * kImuH, w.y1, tc ? W.res_wtc[1].p : W.res_w[1].p, tc ? W.res_stc[1].p : nullptr,
-                               W.res_b[1].p, w.cst, w.flags, gxs, (int)S, n, st);
+                               W.res_b[1].p, w.cst, w.flags, gxs, xc, h->imu_res_direct, (int)S, n, st);
     tap(h, "imu.f", w.y1, (size_t)S * n * 2 * kImuH * 4, st);
     launch_imu_pool(w.y1, W.attn.p, w.s, S, n, st);                                                              // :82-83
-    rc |= launch_lstm_resident(w.s, 2 * kImuH, w.z0, W.res_w[2].p, nullptr, W.res_b[2].p, w.cst, w.flags, gxs, (int)B, L, st);  // :85
-    rc |= launch_lstm_resident(w.z0, 2 * kImuH, w.z1, W.res_w[3].p, nullptr, W.res_b[3].p, w.cst, w.flags, gxs, (int)B, L, st);
+    rc |= launch_lstm_resident(w.s, 2 * kImuH, w.z0, W.res_w[2].p, nullptr, W.res_b[2].p, w.cst, w.flags, gxs, xc, h->imu_res_direct, (int)B, L, st);  // :85
+    rc |= launch_lstm_resident(w.z0, 2 * kImuH, w.z1, W.res_w[3].p, nullptr, W.res_b[3].p, w.cst, w.flags, gxs, xc, h->imu_res_direct, (int)B, L, st);
     launch_imu_decode(w.z1, W.fc2.p, R, t, S, st);                                                               // :87-93
     if (rc) return fail(h, MMEGO_ECUDA, "imu_forward: launching the resident-weights LSTM kernel failed (%s)",
                         cudaGetErrorString(cudaGetLastError()));
@@ -793,6 +796,14 @@ int mmego_set_option(mmego_handle* h, const char* key, long long value) {
     if (!strcmp(key, "imu_res_max_seq")) {
         if (value < 0 || value > 4096) return fail(h, MMEGO_EINVAL, "imu_res_max_seq must be in 0..4096");
         h->imu_res_max_seq = (int)value;
+        return MMEGO_OK;
+    }
+    if (!strcmp(key, "imu_res_direct")) {
+        h->imu_res_direct = value != 0;
+        return MMEGO_OK;
+    }
+    if (!strcmp(key, "imu_res_xchg")) {
+        h->imu_res_xchg = value != 0;
         return MMEGO_OK;
     }
     if (!strcmp(key, "imu_res_tc")) {

@@ -146,8 +146,10 @@ constexpr int kResPreMaxSeq = 4;     // up to this many sequences a layer's inpu
 size_t resident_gx_floats(int S, int T);
 void pack_resident_layer_tc(const StateDict& sd, const std::string& prefix, int layer, int In, std::vector<float>& w,
                             std::vector<float>& scale);
+size_t resident_xchg_words(int S);
 int launch_lstm_resident(const float* x, int In, float* y, const float* w, const float* wscale, const float* bias,
-                         float* cstate, unsigned* flags, float* gxs, int S, int T, cudaStream_t st);
+                         float* cstate, unsigned* flags, float* gxs, unsigned long long* xchg, int direct, int S, int T,
+                         cudaStream_t st);
 void launch_res_fc1(const float* imu, const float* w, float* u, long long rows, cudaStream_t st);
 
 // snippet builder (snippet.cu): device views of the packed raw cache (scripts/pack_sample_data.py)
@@ -339,6 +341,8 @@ struct mmego_handle {
                               // TMEM accumulation chains cost accuracy), bit 4 / 12+i = second drain group (all layers / layer i)
     unsigned* dev_error = nullptr;   // device word set by a kernel whose bounded wait gave up (mmego_debug_stats out8[7])
     int imu_res_max_seq = mmego::kResMaxSeq;   // B*L up to which IMU_Net takes the latency path
+    int imu_res_direct = 1;   // latency path, tensor-core form: A fragments straight from L2, no staging ring and no barrier in the K loop
+    int imu_res_xchg = 1;     // latency path: h travels between the CTAs of a direction as tagged 64-bit words (no fence / arrival counter / poll)
     int imu_res_tc = 1;       // latency path: layers with more than kResPreMaxSeq sequences (rnn_fast) on mma.sync (fp16 hi/lo split, fp32 accumulate); 0 = exact fp32 FMAs
     int imu_res_pre = 1;      // latency path: input projections of all timesteps up front when a layer has <= kResPreMaxSeq sequences
     int imu_resident = 1;     // small batches (B*L <= kResMaxSeq): persistent fp32 LSTM with weights resident in shared memory

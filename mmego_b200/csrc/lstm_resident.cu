@@ -52,12 +52,53 @@ struct ResParams {
     float* cstate;         // [2][S][512]
     unsigned* flags;       // [2][T] arrival counters, zero at launch (null: no inter-CTA waiting, one step per launch)
     unsigned* error;       // set to 1 when a wait gave up
+    unsigned long long* xchg;   // [2 dirs][2 step parities][S][512] tagged h words (tag << 32 | float bits), zero at launch, or null:
+                           // the exchange of h between the 64 CTAs of a direction without fence / arrival counter / poll, see wait_tagged
+    int direct;            // tensor-core form: A fragments straight from global memory (segment_tc_direct) instead of the staged chunks
     float* gxs;            // [128 CTAs][S][T][32] input projections of ALL timesteps (S <= 4 only, else null), see precompute_inputs
     int S, T, In, K;
     int t_begin, t_end;
 };
 
 __device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// ---- exchange of h_t between the CTAs of a direction through self-validating words ---------------------------------
+// The first protocol (still used when p.xchg is null) publishes h in the output tensor, fences, adds one arrival per CTA
+// to a per-step counter, and the readers poll the counter, fence, and only then fetch h from L2: four dependent L2 round
+// trips per timestep.  Here every h value travels as ONE naturally aligned 64-bit word (step tag << 32 | float bits),
+// written with st.relaxed.gpu and read with ld.relaxed.gpu: a 64-bit scalar access is single-copy atomic, so a reader
+// that sees the expected tag has the value of that step -- no fence, no counter, and the wait IS the load.  Two buffers
+// by step parity: a CTA writes step t+1 only after it has read step t from everybody, i.e. after every reader of step
+// t-1 (same parity) is done.  The buffer is zeroed by the launch and tags start at 1.
+__device__ __forceinline__ unsigned long long ld_tagged(const unsigned long long* ptr) {
+#ifdef MMEGO_EMUL
+    return *ptr;
+#else
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ void st_tagged(unsigned long long* ptr, unsigned tag, float v) {
+    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+#ifdef MMEGO_EMUL
+    *ptr = w;
+#else
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(ptr), "l"(w) : "memory");
+#endif
+}
+// re-reads the word until it carries `tag` (bounded: a time-out raises the error flag instead of hanging the GPU)
+__device__ __forceinline__ float wait_tagged(const unsigned long long* ptr, unsigned long long w, unsigned tag, unsigned* error) {
+    unsigned polls = 0;
+    while ((unsigned)(w >> 32) != tag) {
+        if (++polls > (1u << 22)) {
+            if (error) *error = 1u;
+            break;
+        }
+        w = ld_tagged(ptr);
+    }
+    return __uint_as_float((unsigned)w);
+}
 
 // One K segment (the input half x_t or the recurrent half h_{t-1}) of one block of <= 4 SQ sequences:
 //   acc[r][j] += sum_k W[kw0 + k][4 rg + r] * a_{sg SQ + j}[k],  k in [0, len),  a_s = src + s * stride.
@@ -92,6 +133,29 @@ __device__ __forceinline__ void copy_wait_prior() {
 #endif
 }
 
+// the FMAs of one staged chunk: buf = the lane's first sequence row of the chunk, wc = the lane's 4 weight columns at the chunk's first k
+template <int SQ>
+__device__ __forceinline__ void chunk_fma(const float* __restrict__ wc, const float* __restrict__ buf, int warp, float (&acc)[4][SQ]) {
+#pragma unroll
+    for (int q = warp; q < KC / 4; q += RW) {
+        const float* wq = wc + (size_t)q * 4 * RR;
+        const float4 w0 = *reinterpret_cast<const float4*>(wq), w1 = *reinterpret_cast<const float4*>(wq + RR);
+        const float4 w2 = *reinterpret_cast<const float4*>(wq + 2 * RR), w3 = *reinterpret_cast<const float4*>(wq + 3 * RR);
+#pragma unroll
+        for (int j = 0; j < SQ; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(buf + j * KROW + 4 * q);
+            acc[0][j] = fmaf(w0.x, v.x, acc[0][j]); acc[1][j] = fmaf(w0.y, v.x, acc[1][j]);
+            acc[2][j] = fmaf(w0.z, v.x, acc[2][j]); acc[3][j] = fmaf(w0.w, v.x, acc[3][j]);
+            acc[0][j] = fmaf(w1.x, v.y, acc[0][j]); acc[1][j] = fmaf(w1.y, v.y, acc[1][j]);
+            acc[2][j] = fmaf(w1.z, v.y, acc[2][j]); acc[3][j] = fmaf(w1.w, v.y, acc[3][j]);
+            acc[0][j] = fmaf(w2.x, v.z, acc[0][j]); acc[1][j] = fmaf(w2.y, v.z, acc[1][j]);
+            acc[2][j] = fmaf(w2.z, v.z, acc[2][j]); acc[3][j] = fmaf(w2.w, v.z, acc[3][j]);
+            acc[0][j] = fmaf(w3.x, v.w, acc[0][j]); acc[1][j] = fmaf(w3.y, v.w, acc[1][j]);
+            acc[2][j] = fmaf(w3.z, v.w, acc[2][j]); acc[3][j] = fmaf(w3.w, v.w, acc[3][j]);
+        }
+    }
+}
+
 template <int SQ>
 __device__ __forceinline__ void segment(const float* __restrict__ sw, float* __restrict__ abuf, const float* __restrict__ src,
                                         size_t stride, int nseq, int kw0, int len, int tid, float (&acc)[4][SQ]) {
@@ -114,26 +178,7 @@ __device__ __forceinline__ void segment(const float* __restrict__ sw, float* __r
         issue(c + 2);
         copy_wait_prior<2>();                          // chunk c has landed (this thread's copies) ...
         __syncthreads();                               // ... and everybody else's
-        const float* buf = abuf + (c % NBUF) * (SBLK * KROW) + (sg * SQ) * KROW;
-        const float* wc = sw + (size_t)(kw0 + c * KC) * RR + 4 * rg;
-#pragma unroll
-        for (int q = warp; q < KC / 4; q += RW) {
-            const float* wq = wc + (size_t)q * 4 * RR;
-            const float4 w0 = *reinterpret_cast<const float4*>(wq), w1 = *reinterpret_cast<const float4*>(wq + RR);
-            const float4 w2 = *reinterpret_cast<const float4*>(wq + 2 * RR), w3 = *reinterpret_cast<const float4*>(wq + 3 * RR);
-#pragma unroll
-            for (int j = 0; j < SQ; ++j) {
-                const float4 v = *reinterpret_cast<const float4*>(buf + j * KROW + 4 * q);
-                acc[0][j] = fmaf(w0.x, v.x, acc[0][j]); acc[1][j] = fmaf(w0.y, v.x, acc[1][j]);
-                acc[2][j] = fmaf(w0.z, v.x, acc[2][j]); acc[3][j] = fmaf(w0.w, v.x, acc[3][j]);
-                acc[0][j] = fmaf(w1.x, v.y, acc[0][j]); acc[1][j] = fmaf(w1.y, v.y, acc[1][j]);
-                acc[2][j] = fmaf(w1.z, v.y, acc[2][j]); acc[3][j] = fmaf(w1.w, v.y, acc[3][j]);
-                acc[0][j] = fmaf(w2.x, v.z, acc[0][j]); acc[1][j] = fmaf(w2.y, v.z, acc[1][j]);
-                acc[2][j] = fmaf(w2.z, v.z, acc[2][j]); acc[3][j] = fmaf(w2.w, v.z, acc[3][j]);
-                acc[0][j] = fmaf(w3.x, v.w, acc[0][j]); acc[1][j] = fmaf(w3.y, v.w, acc[1][j]);
-                acc[2][j] = fmaf(w3.z, v.w, acc[2][j]); acc[3][j] = fmaf(w3.w, v.w, acc[3][j]);
-            }
-        }
+        chunk_fma<SQ>(sw + (size_t)(kw0 + c * KC) * RR + 4 * rg, abuf + (c % NBUF) * (SBLK * KROW) + (sg * SQ) * KROW, warp, acc);
         __syncthreads();                               // buffer c % 3 is refilled by the issue of the next iteration
     }
     copy_wait_prior<0>();
@@ -149,6 +194,112 @@ __device__ __forceinline__ void segment(const float* __restrict__ sw, float* __r
 constexpr int KROWT = KC + 8;
 static_assert(NBUF * SBLK * KROWT * 4 <= 33 * 1024, "activation ring of the tensor-core form");
 constexpr int ABUF_TC = NBUF * SBLK * KROWT;
+
+// the MMAs of this warp's 16-k step of one staged chunk: buf = chunk + 16 warp + 2 t (row stride KROWT), wk = the k-step's fragments + lane
+template <int MT>
+__device__ __forceinline__ void chunk_mma(const uint4* __restrict__ wk, const float* __restrict__ buf, int g, int nseq,
+                                          float (&big)[MT][4][4], float (&small)[MT][4][4]) {
+    uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        const int r0 = 16 * m + g, r1 = r0 + 8;
+        const float2 z = make_float2(0.f, 0.f);
+        const float2 v0 = r0 < nseq ? *reinterpret_cast<const float2*>(buf + r0 * KROWT) : z;
+        const float2 v1 = r1 < nseq ? *reinterpret_cast<const float2*>(buf + r1 * KROWT) : z;
+        const float2 v2 = r0 < nseq ? *reinterpret_cast<const float2*>(buf + r0 * KROWT + 8) : z;
+        const float2 v3 = r1 < nseq ? *reinterpret_cast<const float2*>(buf + r1 * KROWT + 8) : z;
+        frag::split2(v0.x, v0.y, ah[m][0], al[m][0]);
+        frag::split2(v1.x, v1.y, ah[m][1], al[m][1]);
+        frag::split2(v2.x, v2.y, ah[m][2], al[m][2]);
+        frag::split2(v3.x, v3.y, ah[m][3], al[m][3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint4 b = wk[j * 32];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) frag::mma3(big[m][j], small[m][j], ah[m], al[m], b);
+    }
+}
+
+// The recurrent half of the tensor-core form fed by tagged words (p.xchg): the chunk's nseq x 128 words go from L2 into
+// registers (issued before the previous chunk's MMAs), are validated / re-read until they carry the step's tag, and land
+// as plain floats in one of two chunk buffers.  One block barrier per chunk.
+template <int MT>
+__device__ __forceinline__ void recurrent_tc_tagged(const uint4* __restrict__ wf, float* __restrict__ abuf,
+                                                    const unsigned long long* __restrict__ xsrc, int nseq, int ks0,
+                                                    unsigned tag, unsigned* error, int tid, float (&big)[MT][4][4],
+                                                    float (&small)[MT][4][4]) {
+    constexpr int WPT = SBLK * KC / RT;               // words per thread and chunk at 20 sequences (10)
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    unsigned long long w[WPT];
+    auto load = [&](int c) {
+#pragma unroll
+        for (int j = 0; j < WPT; ++j) {
+            const int i = tid + j * RT;
+            if (i < nseq * KC) w[j] = ld_tagged(xsrc + (size_t)(i / KC) * kImuH + c * KC + (i % KC));
+        }
+    };
+    auto commit = [&](int c, float* buf) {
+#pragma unroll
+        for (int j = 0; j < WPT; ++j) {
+            const int i = tid + j * RT;
+            if (i < nseq * KC)
+                buf[(i / KC) * KROWT + (i % KC)] = wait_tagged(xsrc + (size_t)(i / KC) * kImuH + c * KC + (i % KC), w[j], tag, error);
+        }
+    };
+    load(0);
+#pragma unroll 1
+    for (int c = 0; c < kImuH / KC; ++c) {
+        float* buf = abuf + (c & 1) * (SBLK * KROWT);
+        commit(c, buf);
+        __syncthreads();
+        if (c + 1 < kImuH / KC) load(c + 1);
+        chunk_mma<MT>(wf + (size_t)(ks0 + c * (KC / 16) + warp) * 4 * 32 + lane, buf + 16 * warp + 2 * t, g, nseq, big, small);
+    }
+    __syncthreads();                                   // the buffers double as the partial-sum area
+}
+
+// The same for the fp32 form at <= 4 sequences (rnn_slow): all 512 values of every sequence in ONE round trip
+// (<= 8 words per thread), laid out as four chunks [c][4 rows][KROW].
+__device__ __forceinline__ void recurrent_fp32_tagged(const float* __restrict__ sw, float* __restrict__ abuf,
+                                                      const unsigned long long* __restrict__ xsrc, int nseq, int kw0,
+                                                      unsigned tag, unsigned* error, int tid, float (&acc)[4][1]) {
+    constexpr int WPT = 4 * kImuH / RT;               // 8
+    const int lane = tid & 31, warp = tid >> 5, rg = lane >> 2, sg = lane & 3;
+    unsigned long long w[WPT];
+#pragma unroll
+    for (int j = 0; j < WPT; ++j) {
+        const int i = tid + j * RT;
+        if (i < nseq * kImuH) w[j] = ld_tagged(xsrc + i);
+    }
+#pragma unroll
+    for (int j = 0; j < WPT; ++j) {
+        const int i = tid + j * RT;
+        if (i < nseq * kImuH) {
+            const int sq = i / kImuH, k = i % kImuH;
+            abuf[((k / KC) * 4 + sq) * KROW + (k % KC)] = wait_tagged(xsrc + i, w[j], tag, error);
+        }
+    }
+    __syncthreads();
+    // (rows >= nseq of a chunk are never written: their lanes' sums are never read either)
+#pragma unroll 1
+    for (int c = 0; c < kImuH / KC; ++c)
+        chunk_fma<1>(sw + (size_t)(kw0 + c * KC) * RR + 4 * rg, abuf + (c * 4 + sg) * KROW, warp, acc);
+    __syncthreads();
+}
+
+template <int SQ>
+struct TaggedFp32 {       // only the one-sequence-per-lane tile (S <= 4) has a tagged form
+    static __device__ __forceinline__ void run(const float*, float*, const unsigned long long*, int, int, unsigned, unsigned*, int,
+                                               float (&)[4][SQ]) {}
+};
+template <>
+struct TaggedFp32<1> {
+    static __device__ __forceinline__ void run(const float* sw, float* abuf, const unsigned long long* xsrc, int nseq, int kw0,
+                                               unsigned tag, unsigned* error, int tid, float (&acc)[4][1]) {
+        recurrent_fp32_tagged(sw, abuf, xsrc, nseq, kw0, tag, error, tid, acc);
+    }
+};
 
 template <int MT>
 __device__ __forceinline__ void segment_tc(const uint4* __restrict__ wf, float* __restrict__ abuf, const float* __restrict__ src,
@@ -172,28 +323,8 @@ __device__ __forceinline__ void segment_tc(const uint4* __restrict__ wf, float* 
         issue(c + 2);
         copy_wait_prior<2>();
         __syncthreads();
-        const float* buf = abuf + (c % NBUF) * (SBLK * KROWT) + 16 * warp + 2 * t;      // this warp's k-step of the chunk
-        uint32_t ah[MT][4], al[MT][4];
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            const int r0 = 16 * m + g, r1 = r0 + 8;
-            const float2 z = make_float2(0.f, 0.f);
-            const float2 v0 = r0 < nseq ? *reinterpret_cast<const float2*>(buf + r0 * KROWT) : z;
-            const float2 v1 = r1 < nseq ? *reinterpret_cast<const float2*>(buf + r1 * KROWT) : z;
-            const float2 v2 = r0 < nseq ? *reinterpret_cast<const float2*>(buf + r0 * KROWT + 8) : z;
-            const float2 v3 = r1 < nseq ? *reinterpret_cast<const float2*>(buf + r1 * KROWT + 8) : z;
-            frag::split2(v0.x, v0.y, ah[m][0], al[m][0]);
-            frag::split2(v1.x, v1.y, ah[m][1], al[m][1]);
-            frag::split2(v2.x, v2.y, ah[m][2], al[m][2]);
-            frag::split2(v3.x, v3.y, ah[m][3], al[m][3]);
-        }
-        const uint4* wk = wf + (size_t)(ks0 + c * (KC / 16) + warp) * 4 * 32 + lane;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint4 b = wk[j * 32];
-#pragma unroll
-            for (int m = 0; m < MT; ++m) frag::mma3(big[m][j], small[m][j], ah[m], al[m], b);
-        }
+        chunk_mma<MT>(wf + (size_t)(ks0 + c * (KC / 16) + warp) * 4 * 32 + lane, abuf + (c % NBUF) * (SBLK * KROWT) + 16 * warp + 2 * t,
+                      g, nseq, big, small);
         __syncthreads();
     }
     copy_wait_prior<0>();
@@ -261,7 +392,11 @@ __device__ __forceinline__ void run_steps(const ResParams& p, float* sw, float* 
                 for (int j = 0; j < SQ; ++j) acc[r][j] = 0.f;
             // ---- input half: x_t W_ih^T (independent of the other CTAs; runs before the wait for h_{t-1}) ------------
             if (!gx) segment<SQ>(sw, abuf, p.x + ((size_t)s0 * p.T + tt) * p.In, (size_t)p.T * p.In, nseq, 0, p.In, tid, acc);
-            if (t > 0) {
+            if (t > 0 && SQ == 1 && p.xchg) {
+                // ---- recurrent half from tagged words: the load is the wait ----------------------------------------------
+                TaggedFp32<SQ>::run(sw, abuf, p.xchg + ((size_t)(dir * 2 + ((t - 1) & 1)) * p.S + s0) * kImuH, nseq, p.In,
+                                    (unsigned)t, p.error, tid, acc);
+            } else if (t > 0) {
                 if (!waited) {
                     // ---- wait for h_{t-1} of all 64 unit groups of this direction ------------------------------------
                     if (p.flags && tid == 0) {
@@ -308,13 +443,81 @@ __device__ __forceinline__ void run_steps(const ResParams& p, float* sw, float* 
                 const float cprev = t > 0 ? *cp : 0.f;
                 const float cn = gf * cprev + gi * gg;
                 *cp = cn;
-                p.y[((size_t)s * p.T + tt) * H2 + dir * kImuH + ug * RU + u] = go * tanhf(cn);
+                const float hn = go * tanhf(cn);
+                p.y[((size_t)s * p.T + tt) * H2 + dir * kImuH + ug * RU + u] = hn;
+                if (p.xchg) st_tagged(p.xchg + ((size_t)(dir * 2 + (t & 1)) * p.S + s) * kImuH + ug * RU + u, (unsigned)(t + 1), hn);
             }
             __syncthreads();                                     // red is rewritten by the next block / step
         }
-        __threadfence();
-        __syncthreads();
-        if (p.flags && tid == 0) atomicAdd(p.flags + dir * p.T + t, 1u);
+        if (!p.xchg) {
+            __threadfence();
+            __syncthreads();
+            if (p.flags && tid == 0) atomicAdd(p.flags + dir * p.T + t, 1u);
+        }
+    }
+}
+
+// Tensor-core form WITHOUT the shared-memory staging: once the product runs on mma.sync a chunk's MMAs take ~0.1 us, and
+// the cp.async ring (two 10 KB chunks in flight, two block barriers per chunk) became the step: 12 chunks x ~0.7 us of L2
+// latency for ~1.2 us of MMAs (ncu: tensor pipe 17-20 % active, profiles/r02g_resident_ncu_summary.txt).  Here a warp owns
+// a CONTIGUOUS range of 16-k steps and reads its A fragments straight from global memory / L2 -- a lane's float2 is half
+// of a 32-byte sector whose other half its neighbour lanes read, so no byte is fetched twice -- four k-steps of loads in
+// flight per warp, no barrier anywhere in the K loop.  CG = the operand was written by other CTAs of this launch
+// (h_{t-1}): read through L2 (ld.global.cg), after the arrival counter has been seen.
+template <int MT, bool CG>
+__device__ __forceinline__ void segment_tc_direct(const uint4* __restrict__ wf, const float* __restrict__ src, size_t stride,
+                                                  int nseq, int ks0, int len, int tid, float (&big)[MT][4][4],
+                                                  float (&small)[MT][4][4]) {
+    constexpr int U = 4;                               // k-steps of loads in flight
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int per = len / 16 / RW;                     // k-steps per warp (len is a multiple of 128): 4 or 8
+    const int kbase = warp * per;
+    const float* rp[MT][2];
+    bool live[MT][2];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = 16 * m + 8 * h + g;
+            live[m][h] = r < nseq;
+            rp[m][h] = src + (size_t)(live[m][h] ? r : 0) * stride + 2 * t;
+        }
+    auto ld2 = [&](const float* ptr) {
+#ifdef MMEGO_EMUL
+        return *reinterpret_cast<const float2*>(ptr);
+#else
+        return CG ? __ldcg(reinterpret_cast<const float2*>(ptr)) : __ldg(reinterpret_cast<const float2*>(ptr));
+#endif
+    };
+    for (int k0 = 0; k0 < per; k0 += U) {
+        float2 v[U][MT][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int col = 16 * (kbase + k0 + u);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                const float2 z = make_float2(0.f, 0.f);
+                v[u][m][0] = live[m][0] ? ld2(rp[m][0] + col) : z;
+                v[u][m][1] = live[m][1] ? ld2(rp[m][1] + col) : z;
+                v[u][m][2] = live[m][0] ? ld2(rp[m][0] + col + 8) : z;
+                v[u][m][3] = live[m][1] ? ld2(rp[m][1] + col + 8) : z;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) frag::split2(v[u][m][i].x, v[u][m][i].y, ah[m][i], al[m][i]);
+            const uint4* wk = wf + (size_t)(ks0 + kbase + k0 + u) * 4 * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint4 b = wk[j * 32];
+#pragma unroll
+                for (int m = 0; m < MT; ++m) frag::mma3(big[m][j], small[m][j], ah[m], al[m], b);
+            }
+        }
     }
 }
 
@@ -342,8 +545,14 @@ __device__ __forceinline__ void run_steps_tc(const ResParams& p, const uint4* wf
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) big[m][j][i] = small[m][j][i] = 0.f;
-            segment_tc<MT>(wf, abuf, p.x + ((size_t)s0 * p.T + tt) * p.In, (size_t)p.T * p.In, nseq, 0, p.In, tid, big, small);
-            if (t > 0) {
+            if (p.direct)
+                segment_tc_direct<MT, false>(wf, p.x + ((size_t)s0 * p.T + tt) * p.In, (size_t)p.T * p.In, nseq, 0, p.In, tid, big, small);
+            else
+                segment_tc<MT>(wf, abuf, p.x + ((size_t)s0 * p.T + tt) * p.In, (size_t)p.T * p.In, nseq, 0, p.In, tid, big, small);
+            if (t > 0 && p.xchg) {
+                recurrent_tc_tagged<MT>(wf, abuf, p.xchg + ((size_t)(dir * 2 + ((t - 1) & 1)) * p.S + s0) * kImuH, nseq, p.In / 16,
+                                        (unsigned)t, p.error, tid, big, small);
+            } else if (t > 0) {
                 if (!waited) {
                     if (p.flags && tid == 0) {
                         volatile unsigned* f = p.flags + dir * p.T + (t - 1);
@@ -362,8 +571,12 @@ __device__ __forceinline__ void run_steps_tc(const ResParams& p, const uint4* wf
                     __syncthreads();
                     waited = true;
                 }
-                segment_tc<MT>(wf, abuf, p.y + ((size_t)s0 * p.T + tp) * H2 + dir * kImuH, (size_t)p.T * H2, nseq, p.In / 16,
-                               kImuH, tid, big, small);
+                if (p.direct)
+                    segment_tc_direct<MT, true>(wf, p.y + ((size_t)s0 * p.T + tp) * H2 + dir * kImuH, (size_t)p.T * H2, nseq,
+                                                p.In / 16, kImuH, tid, big, small);
+                else
+                    segment_tc<MT>(wf, abuf, p.y + ((size_t)s0 * p.T + tp) * H2 + dir * kImuH, (size_t)p.T * H2, nseq, p.In / 16,
+                                   kImuH, tid, big, small);
             }
             // cross-warp sum of the k-steps: C fragment (rows g / g+8 of m-tile m, columns 2tq, 2tq+1 of gate j) -> [warp][sequence][32]
             float* red = abuf;
@@ -395,13 +608,17 @@ __device__ __forceinline__ void run_steps_tc(const ResParams& p, const uint4* wf
                 const float cprev = t > 0 ? *cp : 0.f;
                 const float cn = gf * cprev + gi * gg;
                 *cp = cn;
-                p.y[((size_t)s * p.T + tt) * H2 + dir * kImuH + ug * RU + u] = go * tanhf(cn);
+                const float hn = go * tanhf(cn);
+                p.y[((size_t)s * p.T + tt) * H2 + dir * kImuH + ug * RU + u] = hn;
+                if (p.xchg) st_tagged(p.xchg + ((size_t)(dir * 2 + (t & 1)) * p.S + s) * kImuH + ug * RU + u, (unsigned)(t + 1), hn);
             }
             __syncthreads();
         }
-        __threadfence();
-        __syncthreads();
-        if (p.flags && tid == 0) atomicAdd(p.flags + dir * p.T + t, 1u);
+        if (!p.xchg) {
+            __threadfence();
+            __syncthreads();
+            if (p.flags && tid == 0) atomicAdd(p.flags + dir * p.T + t, 1u);
+        }
     }
 }
 
@@ -502,6 +719,7 @@ void pack_resident_layer_tc(const StateDict& sd, const std::string& prefix, int 
     }
 }
 
+size_t resident_xchg_words(int S) { return (size_t)2 * 2 * S * kImuH; }
 size_t resident_gx_floats(int S, int T) { return (size_t)2 * RGROUPS * (S < kResPreMaxSeq ? S : kResPreMaxSeq) * T * RR; }
 size_t resident_smem_bytes(int K) { return ((size_t)K * RR + (ABUF_TC > ABUF ? ABUF_TC : ABUF)) * sizeof(float); }
 
@@ -513,12 +731,22 @@ bool resident_supported(int sm_count) { return sm_count >= 2 * RGROUPS; }   // a
 
 // One bidirectional H=512 layer over T steps for S <= kResMaxSeq sequences, fp32: x [S][T][In] -> y [S][T][1024].
 // w / wscale: the fp32 slices of pack_resident_layer and null, or the fragments and scales of pack_resident_layer_tc.
+// xchg: resident_xchg_words(S) 64-bit words or null (then the fence + arrival-counter exchange is used).
 // cstate: [2][S][512] floats, flags: [2][T] unsigned + 1 error word, gxs: resident_gx_floats(S, T) floats or null (all scratch).  Returns 0, or -1 on a launch error.
 int launch_lstm_resident(const float* x, int In, float* y, const float* w, const float* wscale, const float* bias,
-                         float* cstate, unsigned* flags, float* gxs, int S, int T, cudaStream_t st) {
+                         float* cstate, unsigned* flags, float* gxs, unsigned long long* xchg, int direct, int S, int T,
+                         cudaStream_t st) {
     ResParams p{};
+    p.direct = (wscale && direct) ? 1 : 0;
     p.x = x; p.y = y; p.w = w; p.wscale = wscale; p.bias = bias; p.cstate = cstate;
     p.gxs = S <= kResPreMaxSeq ? gxs : nullptr;
+    // tagged-word exchange: the one-sequence-per-lane fp32 form (S <= 4: all of h in one round trip) and the tensor-core form
+    // with a single block of sequences per step.  With several blocks the counter exchange is paid once per step while the
+    // register-staged tagged chunks cost every block more than the cp.async ring (measured, IMU_Net per call: B = 1 0.582 ->
+    // 0.530 ms, but B = 2 0.857 -> 0.913, B = 4 1.421 -> 1.688 with tagged words everywhere).
+    // The direct tensor-core form reads h as plain floats after the arrival counter.
+    p.xchg = ((wscale && S <= SBLK && !p.direct) || (!wscale && S <= 4)) ? xchg : nullptr;
+    if (p.xchg && cudaMemsetAsync(p.xchg, 0, resident_xchg_words(S) * sizeof(unsigned long long), st) != cudaSuccess) return -1;
     p.S = S; p.T = T; p.In = In; p.K = In + kImuH;
     const size_t smem = resident_smem_bytes(p.K);
     static int attr_bytes[64] = {0};
