@@ -75,14 +75,14 @@ const char* mmego_last_error(const mmego_handle* h);
  *                         break-even, B <= 4 at L = 20) take the latency path -- gate weights resident in shared memory,
  *                         one persistent cooperative launch per bi-LSTM layer, 7 launches per call; 0 = always the
  *                         tcgen05 path),
- *          "imu_res_tc"  (latency path, 1 default: layers with more than 4 sequences (rnn_fast) multiply on mma.sync with
+ *          "imu_res_tc"  (latency path, 1 default: rnn_fast multiplies on mma.sync with
  *                         fp16 hi/lo split operands and fp32 accumulation, like every other GEMM of the library; 0 = exact
  *                         fp32 FMAs, 1.8x slower per step),
  *          "imu_res_direct" (latency path, 1 default: the mma.sync form reads its A fragments straight from L2, a contiguous
  *                         k range per warp and no barrier in the K loop; 0 = activations staged through a cp.async ring),
  *          "imu_res_xchg" (latency path, 1 default: layers with at most 4 sequences exchange h between the CTAs of a
  *                         direction as 64-bit words carrying a step tag -- no fence, arrival counter or poll; 0 = counter),
- *          "imu_res_pre" (latency path, 1 default: layers with at most 4 sequences (rnn_slow) take their input
+ *          "imu_res_pre" (latency path, 1 default: rnn_slow's layers take their input
  *                         projections for all timesteps up front; 0 = inside every timestep),
  *          "gcn_w_res"   (row-tiled ST-GCN GEMMs, 1 default: the weight matrix is loaded once per CTA and stays in shared
  *                         memory next to the activation ring when it fits),

@@ -324,9 +324,7 @@ void plan_imu_res(Carver& c, long long B, int L, int n, ImuResWs& w) {
     w.z1 = c.f(S * 2 * kImuH);
     w.cst = c.f(2 * S * kImuH);
     w.flags = reinterpret_cast<unsigned*>(c.f(2 * (size_t)(n > L ? n : L) + 8));
-    const size_t gfast = S <= (size_t)kResPreMaxSeq ? resident_gx_floats((int)S, n) : 0;
-    const size_t gslow = B <= kResPreMaxSeq ? resident_gx_floats((int)B, L) : 0;
-    w.gxs = c.f(gfast > gslow ? gfast : gslow);
+    w.gxs = c.f(resident_gx_floats((int)B, L));      // rnn_slow: B sequences x L timesteps
     w.xchg = reinterpret_cast<unsigned long long*>(c.f(2 * resident_xchg_words((int)S)));       // S >= B
 }
 bool use_resident(const mmego_handle* h, long long B, int L) {
@@ -341,12 +339,13 @@ int imu_res_forward(mmego_handle* h, const float* imu, float* R, float* t, long 
     int rc = 0;
     float* const gxs = h->imu_res_pre ? w.gxs : nullptr;
     unsigned long long* const xc = h->imu_res_xchg ? w.xchg : nullptr;
-    // rnn_fast (S = B*L sequences): tensor-core form above kResPreMaxSeq sequences, where the fp32 form is shared-memory bound
-    const bool tc = h->imu_res_tc && S > kResPreMaxSeq && W.res_wtc[0].p && W.res_wtc[1].p;
+    // rnn_fast (S = B*L sequences of n samples): tensor-core form; rnn_slow (B sequences of L frames): fp32 with its input
+    // projections up front.  The choice never depends on the batch size, so results do not depend on batch-mates / chunking.
+    const bool tc = h->imu_res_tc && W.res_wtc[0].p && W.res_wtc[1].p;
     rc |= launch_lstm_resident(w.u, kImuH, w.y0, tc ? W.res_wtc[0].p : W.res_w[0].p, tc ? W.res_stc[0].p : nullptr,
-                               W.res_b[0].p, w.cst, w.flags, gxs, xc, h->imu_res_direct, (int)S, n, st);                                    // :80
+                               W.res_b[0].p, w.cst, w.flags, nullptr, xc, h->imu_res_direct, (int)S, n, st);                                    // :80
     rc |= launch_lstm_resident(w.y0, 2 * kImuH, w.y1, tc ? W.res_wtc[1].p : W.res_w[1].p, tc ? W.res_stc[1].p : nullptr,
-                               W.res_b[1].p, w.cst, w.flags, gxs, xc, h->imu_res_direct, (int)S, n, st);
+                               W.res_b[1].p, w.cst, w.flags, nullptr, xc, h->imu_res_direct, (int)S, n, st);
     tap(h, "imu.f", w.y1, (size_t)S * n * 2 * kImuH * 4, st);
     launch_imu_pool(w.y1, W.attn.p, w.s, S, n, st);                                                              // :82-83
     rc |= launch_lstm_resident(w.s, 2 * kImuH, w.z0, W.res_w[2].p, nullptr, W.res_b[2].p, w.cst, w.flags, gxs, xc, h->imu_res_direct, (int)B, L, st);  // :85

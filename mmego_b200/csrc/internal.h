@@ -142,7 +142,6 @@ struct StateDict;
 void pack_resident_layer(const StateDict& sd, const std::string& prefix, int layer, int In, std::vector<float>& w,
                          std::vector<float>& bias);
 bool resident_supported(int sm_count);
-constexpr int kResPreMaxSeq = 4;     // up to this many sequences a layer's input projections are computed for all timesteps up front
 size_t resident_gx_floats(int S, int T);
 void pack_resident_layer_tc(const StateDict& sd, const std::string& prefix, int layer, int In, std::vector<float>& w,
                             std::vector<float>& scale);
@@ -343,8 +342,8 @@ struct mmego_handle {
     int imu_res_max_seq = mmego::kResMaxSeq;   // B*L up to which IMU_Net takes the latency path
     int imu_res_direct = 1;   // latency path, tensor-core form: A fragments straight from L2, no staging ring and no barrier in the K loop
     int imu_res_xchg = 1;     // latency path: h travels between the CTAs of a direction as tagged 64-bit words (no fence / arrival counter / poll)
-    int imu_res_tc = 1;       // latency path: layers with more than kResPreMaxSeq sequences (rnn_fast) on mma.sync (fp16 hi/lo split, fp32 accumulate); 0 = exact fp32 FMAs
-    int imu_res_pre = 1;      // latency path: input projections of all timesteps up front when a layer has <= kResPreMaxSeq sequences
+    int imu_res_tc = 1;       // latency path: rnn_fast on mma.sync (fp16 hi/lo split, fp32 accumulate); 0 = exact fp32 FMAs
+    int imu_res_pre = 1;      // latency path: rnn_slow's input projections of all timesteps up front
     int imu_resident = 1;     // small batches (B*L <= kResMaxSeq): persistent fp32 LSTM with weights resident in shared memory
     mmego::ImuWeights imu;
     mmego::UpperWeights upper;

@@ -184,7 +184,7 @@ __device__ __forceinline__ void segment(const float* __restrict__ sw, float* __r
     copy_wait_prior<0>();
 }
 
-// ---- tensor-core form of `segment` (layers with more than kResPreMaxSeq sequences, i.e. rnn_fast) ---------------------
+// ---- tensor-core form of `segment` (rnn_fast: S = B*L sequences of n samples) ---------------------
 // The fp32 FMA form above is bound by the shared-memory pipe (9 LDS.128 per 80 FMAs and lane); here the same chunk
 // (128 k x <= 20 sequences, staged by the same cp.async ring) feeds mma.sync m16n8k16 with fp16 hi/lo split operands and
 // fp32 accumulation (mma_frag.cuh, the scheme of every other GEMM of the library): the CTA's 32 gate rows are four
@@ -330,9 +330,9 @@ __device__ __forceinline__ void segment_tc(const uint4* __restrict__ wf, float* 
     copy_wait_prior<0>();
 }
 
-// S <= 4 sequences (rnn_slow at the reference's one snippet per call): a step's input half x_t W_ih^T would read the
-// CTA's whole W_ih slice (128 KB) from shared memory for ONE activation row, once per timestep and inside the lock-step
-// cycle of the 64 CTAs (signal -> input half -> recurrent half -> cell).  The timesteps of a sequence are independent
+// rnn_slow (one sequence per snippet: S = B, S * T <= kResMaxSeq): a step's input half x_t W_ih^T would read the
+// CTA's whole W_ih slice (128 KB) from shared memory for ONE activation row per sequence, once per timestep and inside
+// the lock-step cycle of the 64 CTAs (signal -> input half -> recurrent half -> cell).  The timesteps of a sequence are independent
 // rows for that product, so it is done up front for all of them, 20 timesteps per pass through the 4 x 5 register tile
 // that rnn_fast uses for 20 sequences: W_ih is read T/20 times instead of T times, and the per-step cycle keeps only the
 // recurrent half.  gx [S][T][32] (this CTA's gate rows) lives in global scratch: written and read by this CTA only.
@@ -375,7 +375,7 @@ __device__ __forceinline__ void run_steps(const ResParams& p, float* sw, float* 
     const int H2 = 2 * kImuH;
     const float* bsrc = p.bias + (dir * RGROUPS + ug) * RR;      // 32 floats, L1-resident
     float* gx = nullptr;
-    if (SQ == 1 && p.gxs) {
+    if (p.gxs) {
         gx = p.gxs + (size_t)blockIdx.x * p.S * p.T * RR;
         if (p.t_begin == 0) precompute_inputs(p, sw, abuf, gx);  // (the emulator's later one-step launches find it in place)
     }
@@ -720,7 +720,7 @@ void pack_resident_layer_tc(const StateDict& sd, const std::string& prefix, int 
 }
 
 size_t resident_xchg_words(int S) { return (size_t)2 * 2 * S * kImuH; }
-size_t resident_gx_floats(int S, int T) { return (size_t)2 * RGROUPS * (S < kResPreMaxSeq ? S : kResPreMaxSeq) * T * RR; }
+size_t resident_gx_floats(int S, int T) { return (size_t)2 * RGROUPS * S * T * RR; }
 size_t resident_smem_bytes(int K) { return ((size_t)K * RR + (ABUF_TC > ABUF ? ABUF_TC : ABUF)) * sizeof(float); }
 
 #ifdef MMEGO_EMUL
@@ -732,14 +732,15 @@ bool resident_supported(int sm_count) { return sm_count >= 2 * RGROUPS; }   // a
 // One bidirectional H=512 layer over T steps for S <= kResMaxSeq sequences, fp32: x [S][T][In] -> y [S][T][1024].
 // w / wscale: the fp32 slices of pack_resident_layer and null, or the fragments and scales of pack_resident_layer_tc.
 // xchg: resident_xchg_words(S) 64-bit words or null (then the fence + arrival-counter exchange is used).
-// cstate: [2][S][512] floats, flags: [2][T] unsigned + 1 error word, gxs: resident_gx_floats(S, T) floats or null (all scratch).  Returns 0, or -1 on a launch error.
+// cstate: [2][S][512] floats, flags: [2][T] unsigned + 1 error word, gxs: resident_gx_floats(S, T) floats or null (all scratch).
+// Which form runs never depends on S, so a snippet's result does not depend on its batch-mates or on how a caller chunks a batch.  Returns 0, or -1 on a launch error.
 int launch_lstm_resident(const float* x, int In, float* y, const float* w, const float* wscale, const float* bias,
                          float* cstate, unsigned* flags, float* gxs, unsigned long long* xchg, int direct, int S, int T,
                          cudaStream_t st) {
     ResParams p{};
     p.direct = (wscale && direct) ? 1 : 0;
     p.x = x; p.y = y; p.w = w; p.wscale = wscale; p.bias = bias; p.cstate = cstate;
-    p.gxs = S <= kResPreMaxSeq ? gxs : nullptr;
+    p.gxs = wscale ? nullptr : gxs;      // up-front input projections: fp32 form only (the caller passes it for rnn_slow)
     // tagged-word exchange: the one-sequence-per-lane fp32 form (S <= 4: all of h in one round trip) and the tensor-core form
     // with a single block of sequences per step.  With several blocks the counter exchange is paid once per step while the
     // register-staged tagged chunks cost every block more than the cp.async ring (measured, IMU_Net per call: B = 1 0.582 ->

@@ -570,9 +570,8 @@ def test_imu_latency_path(handle, handle_latency, B, L, n):
     """Small batches (the reference's own setting is ONE snippet per call, Demo_test.py:61) run IMU_Net on persistent
     kernels with the gate weights resident in shared memory: 7 launches instead of 83; rnn_fast on mma.sync fp16 hi/lo
     split products with short accumulation chains, rnn_slow in exact fp32 (so it sits at the fp32 oracle's own noise, far
-    inside the tolerance), and it agrees with the tcgen05 throughput path; the exact-fp32 form (imu_res_tc = 0) as well.  Layers with <= 4
-    sequences (rnn_slow at B <= 4; rnn_fast at B*L <= 4) take their input projections for all timesteps up front, 20
-    timesteps per pass: (1, 30, 25) and (1, 2, 40) have more than one pass."""
+    inside the tolerance), and it agrees with the tcgen05 throughput path; the exact-fp32 form (imu_res_tc = 0) as well.  rnn_slow takes
+    its input projections for all timesteps up front, 20 timesteps per pass: (1, 30, 25) has more than one pass."""
     sb = P.O.synth_batch(B, L=L, N=64, n_imu=n, seed=40 + B)
     imu = sb["imu"].cuda()
     n0 = handle_latency.launch_count()
