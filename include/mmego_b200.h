@@ -71,8 +71,8 @@ const char* mmego_last_error(const mmego_handle* h);
  *          "head_gemm"   (fully connected heads: 1 = one fused mma.sync kernel per head, default; 0 = fp32 FFMA GEMMs),
  *          "host_chunk"  (mmego_infer_host: snippets per stage of its H2D / compute / D2H pipeline, default 2048; the
  *                         first stage is an eighth of that so the un-overlappable first copy stays short),
- *          "imu_resident" (1, default: IMU_Net calls of at most "imu_res_max_seq" frames (B*L; default 80 = the measured
- *                         break-even, B <= 4 at L = 20) take the latency path -- gate weights resident in shared memory,
+ *          "imu_resident" (1, default: IMU_Net calls of at most "imu_res_max_seq" frames (B*L; default 120 = the measured
+ *                         break-even, B <= 6 at L = 20) take the latency path -- gate weights resident in shared memory,
  *                         one persistent cooperative launch per bi-LSTM layer, 7 launches per call; 0 = always the
  *                         tcgen05 path),
  *          "imu_res_tc"  (latency path, 1 default: rnn_fast multiplies on mma.sync with

@@ -28,7 +28,7 @@ from ...pipeline import SUMS_LEN, GraphedStep, MMEgoPipeline, report_from_sums
 
 
 class MMEgo:
-    GRAPH_MAX_SEQ = 80          # batch_size * frame_no up to which a step is replayed as a CUDA graph (the library's latency regime)
+    GRAPH_MAX_SEQ = 120         # batch_size * frame_no up to which a step is replayed as a CUDA graph (the library's latency regime)
 
     def __init__(self, batch_size=None, device=None, imu_surrogate=None, quiet=False, from_raw=False, use_graph=True,
                  fused=True):

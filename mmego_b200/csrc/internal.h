@@ -136,8 +136,8 @@ void launch_transform2r(const float* pts, const float* R, const float* t, float*
                         cudaStream_t st);
 
 // small-batch latency path of IMU_Net (lstm_resident.cu): fp32, gate weights resident in shared memory across timesteps
-constexpr int kResMaxSeq = 80;       // B*L up to which the resident path is taken (B <= 4 at L = 20; measured break-even with the
-                                     // tcgen05 path: B = 5, profiles/r02_latency_path.txt); run-time: option imu_res_max_seq
+constexpr int kResMaxSeq = 120;      // B*L up to which the resident path is taken (B <= 6 at L = 20; measured break-even with the
+                                     // tcgen05 path: B = 7, profiles/r02_latency_break_even_final.txt); run-time: option imu_res_max_seq
 struct StateDict;
 void pack_resident_layer(const StateDict& sd, const std::string& prefix, int layer, int In, std::vector<float>& w,
                          std::vector<float>& bias);

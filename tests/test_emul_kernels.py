@@ -24,6 +24,10 @@ def lib():
 @pytest.fixture(scope="module")
 def handle(lib):
     h = P.make_handle(lib=lib, require_cuda=False)
+    # The small batches of this suite take IMU_Net's latency path.  Its tensor-core form is emulated MMA by MMA (a 32-lane
+    # exchange each): it is switched on only where it is the subject (test_imu_latency_path...), everything else runs the
+    # exact-fp32 form of the same kernel so that the CPU suite stays at a few minutes.
+    h.set_option("imu_res_tc", 0)
     yield h
     h.close()
 
@@ -186,9 +190,15 @@ def test_imu_latency_path_matches_oracle_and_ffma_path(handle):
     """The resident-weights fp32 LSTM kernels (small-batch latency path) on the emulator -- one launch per timestep there,
     the same kernel code -- against the oracle and against the fp32 FFMA generation."""
     from oracle import mmego_oracle as O
-    for B, L, n in ((1, 20, 20), (3, 5, 3), (3, 20, 2), (1, 23, 2)):     # (1, 23, 2): rnn_slow's up-front input pass has a ragged second block
+    # (1, 23, 2): rnn_slow's up-front input pass has a ragged second block.  tc: rnn_fast on (emulated) mma.sync fragments --
+    # two m-tiles at 20 sequences, three blocks of sequences at 60, one m-tile at 15 -- kept to few timesteps (see `handle`)
+    for B, L, n, tc in ((1, 20, 20, 0), (1, 20, 3, 1), (3, 5, 3, 1), (3, 20, 2, 1), (1, 23, 2, 0)):
         sb = O.synth_batch(B, L=L, N=64, n_imu=n, seed=5 + B)
-        R1, t1 = handle.imu_forward(sb["imu"])
+        handle.set_option("imu_res_tc", tc)
+        try:
+            R1, t1 = handle.imu_forward(sb["imu"])
+        finally:
+            handle.set_option("imu_res_tc", 0)
         handle.set_option("imu_resident", 0)
         try:
             R0, t0 = handle.imu_forward(sb["imu"])

@@ -27,7 +27,7 @@ def handle():
 
 @pytest.fixture(scope="module")
 def handle_latency():
-    h = P.make_handle()                 # library defaults: B*L <= 80 sequences -> resident-weights LSTM kernels (latency path)
+    h = P.make_handle()                 # library defaults: B*L <= 120 sequences -> resident-weights LSTM kernels (latency path)
     yield h
     h.close()
 
@@ -565,7 +565,7 @@ def test_eval_driver_graph_replay_matches_eager_calls(bs):
 
 
 @pytest.mark.parametrize("B,L,n", [(1, 20, 20), (2, 20, 20), (3, 20, 20), (3, 5, 3), (1, 1, 1), (9, 7, 40), (1, 30, 25),
-                                   (1, 2, 40), (4, 16, 5)])
+                                   (1, 2, 40), (4, 16, 5), (5, 20, 20), (6, 20, 20)])
 def test_imu_latency_path(handle, handle_latency, B, L, n):
     """Small batches (the reference's own setting is ONE snippet per call, Demo_test.py:61) run IMU_Net on persistent
     kernels with the gate weights resident in shared memory: 7 launches instead of 83; rnn_fast on mma.sync fp16 hi/lo
