@@ -191,8 +191,8 @@ def test_imu_latency_path_matches_oracle_and_ffma_path(handle):
     the same kernel code -- against the oracle and against the fp32 FFMA generation."""
     from oracle import mmego_oracle as O
     # (1, 23, 2): rnn_slow's up-front input pass has a ragged second block.  tc: rnn_fast on (emulated) mma.sync fragments --
-    # two m-tiles at 20 sequences, three blocks of sequences at 60, one m-tile at 15 -- kept to few timesteps (see `handle`)
-    for B, L, n, tc in ((1, 20, 20, 0), (1, 20, 3, 1), (3, 5, 3, 1), (3, 20, 2, 1), (1, 23, 2, 0)):
+    # two m-tiles at 20 sequences, two blocks of sequences at 22 (20 + 2), one m-tile at 15 -- kept to few timesteps (see `handle`)
+    for B, L, n, tc in ((1, 20, 20, 0), (1, 20, 2, 1), (3, 5, 3, 1), (2, 11, 2, 1), (3, 20, 2, 0), (1, 23, 2, 0)):
         sb = O.synth_batch(B, L=L, N=64, n_imu=n, seed=5 + B)
         handle.set_option("imu_res_tc", tc)
         try:

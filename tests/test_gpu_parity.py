@@ -41,6 +41,7 @@ def handle_ffma():
     if not os.path.exists(path):
         path = B.build(variant="ffma")          # needs nvcc; __graft_entry__.build() normally did this already
     h = P.make_handle(lib=_capi.Lib(path))
+    h.set_option("imu_resident", 0)     # small test batches must reach the FFMA / tcgen05 generations, not the latency path
     yield h
     h.close()
 
