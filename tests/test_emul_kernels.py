@@ -207,3 +207,28 @@ def test_imu_latency_path_matches_oracle_and_ffma_path(handle):
         Rr, tr = O.imu_forward(O.synth_imu_state_dict(0), sb["imu"])
         assert P.rot_angle_deg(R1, Rr) < P.ANG_TOL / 2 and P.maxerr(t1, tr) < 1e-6
         assert P.rot_angle_deg(R1, R0) < P.ANG_TOL / 2
+
+
+def test_imu_latency_path_option_forms_agree(handle):
+    """Every selectable form of the resident kernel is the same math.  Promised: (a) tagged words vs arrival counter as the
+    exchange of h: bit-identical; (b) staged vs direct tensor-core operands, up-front vs in-step input projections, and the
+    exact-fp32 form: different summation orders / operand splits of the same products, far inside the tolerance."""
+    from oracle import mmego_oracle as O
+    sb = O.synth_batch(1, L=3, N=64, n_imu=2, seed=21)
+    Rr, tr = O.imu_forward(O.synth_imu_state_dict(0), sb["imu"])
+    base = dict(imu_res_tc=1, imu_res_direct=1, imu_res_xchg=1, imu_res_pre=1)
+    out = {}
+    try:
+        for name, kw in (("default", {}), ("counter", dict(imu_res_xchg=0)), ("staged", dict(imu_res_direct=0)),
+                         ("staged_counter", dict(imu_res_direct=0, imu_res_xchg=0)), ("in_step", dict(imu_res_pre=0)),
+                         ("fp32", dict(imu_res_tc=0))):
+            for k, v in {**base, **kw}.items():
+                handle.set_option(k, v)
+            out[name] = handle.imu_forward(sb["imu"])
+    finally:
+        for k, v in {**base, "imu_res_tc": 0}.items():          # the fixture's setting
+            handle.set_option(k, v)
+    for a, b in (("default", "counter"), ("staged", "staged_counter")):
+        assert torch.equal(out[a][0], out[b][0]) and torch.equal(out[a][1], out[b][1]), (a, b)
+    for name, (R, t) in out.items():
+        assert P.rot_angle_deg(R, Rr) < P.ANG_TOL / 2 and P.maxerr(t, tr) < 1e-6, name
