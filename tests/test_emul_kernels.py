@@ -199,14 +199,15 @@ def test_imu_latency_path_matches_oracle_and_ffma_path(handle):
             R1, t1 = handle.imu_forward(sb["imu"])
         finally:
             handle.set_option("imu_res_tc", 0)
-        handle.set_option("imu_resident", 0)
-        try:
-            R0, t0 = handle.imu_forward(sb["imu"])
-        finally:
-            handle.set_option("imu_resident", 1)
         Rr, tr = O.imu_forward(O.synth_imu_state_dict(0), sb["imu"])
         assert P.rot_angle_deg(R1, Rr) < P.ANG_TOL / 2 and P.maxerr(t1, tr) < 1e-6
-        assert P.rot_angle_deg(R1, R0) < P.ANG_TOL / 2
+        if (B, L, n) in ((3, 5, 3), (3, 20, 2)):        # ... and against the fp32 FFMA generation (the emulated big-LSTM path is slow)
+            handle.set_option("imu_resident", 0)
+            try:
+                R0, t0 = handle.imu_forward(sb["imu"])
+            finally:
+                handle.set_option("imu_resident", 1)
+            assert P.rot_angle_deg(R1, R0) < P.ANG_TOL / 2
 
 
 def test_imu_latency_path_option_forms_agree(handle):
